@@ -1,0 +1,259 @@
+// concat_volume.cu — concatenation volume with the ACV attention weights and the DDIM filter
+// multiply fused into the single producing pass (a3, a4, a9) for sm_100a.
+//
+// Replaces build_concat_volume (variant M: SceneFlow/models/submodule.py:180-191,
+// KITTI15/core/submodule.py:206-217; variant T: SceneFlow/submodule.py:137-148,
+// KITTI12/models/submodule.py:86-97), `F.softmax(att_weights, dim=2) * concat_volume`
+// (SceneFlow/models/acv_ddim.py:390, acv.py:203) and the filter multiply
+// `volume * noise.unsqueeze(1).float()` (acv_ddim.py:254-260).  The reference runs these as
+// memset + 2*D strided copies, a softmax, a 398 MB read+write multiply and (per DDIM step)
+// another 398 MB read+write multiply.  Here the [B,2C,D,H,W] volume is written once,
+// straight from the 1/4-resolution features (20 MB), with 128-bit streaming stores.
+//
+// The op is write-bound (398 MB written per 20 MB read), so there is no reuse to stage:
+// CTA = (span of 32 quads of the flattened plane, channel group, batch).  It first builds
+// the per-(d,pixel) factors of its span in shared memory (softmax over D of the attention
+// logits and/or the filter factor n), then every thread = (quad, channel slot) streams the
+// D planes of its channels: left half = one float4 of ref reused for all d; right half =
+// a sliding window over tgt (one new aligned float4 per 4 disparities).
+#include "common.cuh"
+
+namespace dv {
+
+constexpr int kConcatSQ = 32;           // quads per span  (one warp wide)
+constexpr int kConcatSpan = kConcatSQ * 4;
+constexpr int kConcatSlots = 8;         // channel slots per CTA
+constexpr int kConcatThreads = kConcatSQ * kConcatSlots;
+
+template <typename XT>
+__device__ __forceinline__ void fill_filter_factor(float *sn, const XT *__restrict__ xt, const float *__restrict__ shift,
+                                                   XT scale, int b, int D, int HW, int p0) {
+    for (int e = threadIdx.x; e < D * kConcatSpan; e += kConcatThreads) {
+        const int d = e / kConcatSpan, px = e % kConcatSpan;
+        const int p = p0 + px;
+        float v = 0.0f;
+        if (p < HW) {
+            const XT x = xt[(static_cast<int64_t>(b) * D + d) * HW + p];
+            const float sh = shift ? shift[b * D + d] : 0.0f;
+            v = static_cast<float>(filter_n<XT>(x, sh, scale));
+        }
+        sn[e] = v;
+    }
+}
+
+template <bool HAS_ATT, bool HAS_N>
+__global__ void __launch_bounds__(kConcatThreads)
+concat_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out,
+                     int C, int HW, int W, int D, int mask_left, int chans_per_cta,
+                     const float *__restrict__ att, const void *__restrict__ xt, int xt_is_f64,
+                     const float *__restrict__ shift, double scale) {
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;                                       // [D][span] softmax weights
+    float *sn = smem + (HAS_ATT ? D * kConcatSpan : 0);     // [D][span] filter factor
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * kConcatSpan;
+    const int c_begin = blockIdx.y * chans_per_cta;
+    const int c_end = min(c_begin + chans_per_cta, 2 * C);
+
+    if (HAS_ATT) {
+        // softmax over D of att[b,0,:,p] (F.softmax(att_weights, dim=2)): exp(a - max) / sum
+        if (threadIdx.x < kConcatSpan) {
+            const int px = threadIdx.x, p = p0 + px;
+            if (p < HW) {
+                const float *ap = att + static_cast<int64_t>(b) * D * HW + p;
+                float mx = -INFINITY;
+                for (int d = 0; d < D; ++d) {
+                    const float a = ap[static_cast<int64_t>(d) * HW];
+                    sw[d * kConcatSpan + px] = a;
+                    mx = fmaxf(mx, a);
+                }
+                float sum = 0.0f;
+                for (int d = 0; d < D; ++d) {
+                    const float e = expf(sw[d * kConcatSpan + px] - mx);
+                    sw[d * kConcatSpan + px] = e;
+                    sum += e;
+                }
+                for (int d = 0; d < D; ++d) sw[d * kConcatSpan + px] = sw[d * kConcatSpan + px] / sum;
+            } else {
+                for (int d = 0; d < D; ++d) sw[d * kConcatSpan + px] = 0.0f;
+            }
+        }
+    }
+    if (HAS_N) {
+        if (xt_is_f64)
+            fill_filter_factor<double>(sn, static_cast<const double *>(xt), shift, scale, b, D, HW, p0);
+        else
+            fill_filter_factor<float>(sn, static_cast<const float *>(xt), shift, static_cast<float>(scale), b, D, HW, p0);
+    }
+    if (HAS_ATT || HAS_N) __syncthreads();
+
+    const int q = threadIdx.x % kConcatSQ;
+    const int slot = threadIdx.x / kConcatSQ;
+    const int p = p0 + 4 * q;
+    if (p >= HW) return;
+    int xs[4];
+    xs[0] = p % W;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        xs[i] = xs[i - 1] + 1;
+        if (xs[i] >= W) xs[i] -= W;
+    }
+
+    for (int c = c_begin + slot; c < c_end; c += kConcatSlots) {
+        float *op = out + ((static_cast<int64_t>(b) * 2 * C + c) * D) * HW + p;
+        if (c < C) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(ref + (static_cast<int64_t>(b) * C + c) * HW + p));
+#pragma unroll 4
+            for (int d = 0; d < D; ++d) {
+                float4 o = v;
+                if (mask_left) {
+                    o.x = xs[0] >= d ? o.x : 0.0f;
+                    o.y = xs[1] >= d ? o.y : 0.0f;
+                    o.z = xs[2] >= d ? o.z : 0.0f;
+                    o.w = xs[3] >= d ? o.w : 0.0f;
+                }
+                if (HAS_ATT) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(sw + d * kConcatSpan + 4 * q);
+                    o.x *= w4.x; o.y *= w4.y; o.z *= w4.z; o.w *= w4.w;
+                }
+                if (HAS_N) {
+                    const float4 n4 = *reinterpret_cast<const float4 *>(sn + d * kConcatSpan + 4 * q);
+                    o.x *= n4.x; o.y *= n4.y; o.z *= n4.z; o.w *= n4.w;
+                }
+                stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(d) * HW), o);
+            }
+        } else {
+            // right half: out[d] = tgt[p - d + i]; aligned blocks blk(m) = tgt[p-4m .. p-4m+3]
+            const int64_t base = (static_cast<int64_t>(b) * C + (c - C)) * HW + p;  // flat index into tgt
+            float4 cur = __ldg(reinterpret_cast<const float4 *>(tgt + base));
+            for (int m = 0; 4 * m < D; ++m) {
+                const int64_t nb = base - 4 * (m + 1);
+                // only the first plane of the tensor can reach below index 0; x < d there
+                float4 prev = nb >= 0 ? __ldg(reinterpret_cast<const float4 *>(tgt + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int d = 4 * m + j;
+                    if (d < D) {
+                        float4 o;
+                        if (j == 0) o = cur;
+                        else if (j == 1) o = make_float4(prev.w, cur.x, cur.y, cur.z);
+                        else if (j == 2) o = make_float4(prev.z, prev.w, cur.x, cur.y);
+                        else o = make_float4(prev.y, prev.z, prev.w, cur.x);
+                        o.x = xs[0] >= d ? o.x : 0.0f;
+                        o.y = xs[1] >= d ? o.y : 0.0f;
+                        o.z = xs[2] >= d ? o.z : 0.0f;
+                        o.w = xs[3] >= d ? o.w : 0.0f;
+                        if (HAS_ATT) {
+                            const float4 w4 = *reinterpret_cast<const float4 *>(sw + d * kConcatSpan + 4 * q);
+                            o.x *= w4.x; o.y *= w4.y; o.z *= w4.z; o.w *= w4.w;
+                        }
+                        if (HAS_N) {
+                            const float4 n4 = *reinterpret_cast<const float4 *>(sn + d * kConcatSpan + 4 * q);
+                            o.x *= n4.x; o.y *= n4.y; o.z *= n4.z; o.w *= n4.w;
+                        }
+                        stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(d) * HW), o);
+                    }
+                }
+                cur = prev;
+            }
+        }
+    }
+}
+
+// Shape-agnostic path ((H*W) % 4 != 0 or unaligned pointers): one thread per output element.
+template <typename XT>
+__global__ void concat_volume_generic_kernel(const float *__restrict__ ref, const float *__restrict__ tgt,
+                                             float *__restrict__ out, int C, int HW, int W, int D, int mask_left,
+                                             const float *__restrict__ att, const XT *__restrict__ xt,
+                                             const float *__restrict__ shift, XT scale, int64_t total) {
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(idx % HW);
+        int64_t t = idx / HW;
+        const int d = static_cast<int>(t % D);
+        t /= D;
+        const int c = static_cast<int>(t % (2 * C));
+        const int64_t b = t / (2 * C);
+        const int x = p % W;
+        float v;
+        if (c < C)
+            v = (!mask_left || x >= d) ? ref[(b * C + c) * HW + p] : 0.0f;
+        else
+            v = x >= d ? tgt[(b * C + (c - C)) * HW + p - d] : 0.0f;
+        if (att) {
+            const float *ap = att + b * D * HW + p;
+            float mx = -INFINITY;
+            for (int k = 0; k < D; ++k) mx = fmaxf(mx, ap[static_cast<int64_t>(k) * HW]);
+            float sum = 0.0f;
+            for (int k = 0; k < D; ++k) sum += expf(ap[static_cast<int64_t>(k) * HW] - mx);
+            v *= expf(ap[static_cast<int64_t>(d) * HW] - mx) / sum;
+        }
+        if (xt) {
+            const float sh = shift ? shift[b * D + d] : 0.0f;
+            v *= static_cast<float>(filter_n<XT>(xt[(b * D + d) * HW + p], sh, scale));
+        }
+        out[idx] = v;
+    }
+}
+
+template <bool HAS_ATT, bool HAS_N>
+static int launch_concat(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D,
+                         int mask_left, const float *att, const void *xt, int xt_is_f64, const float *shift,
+                         double scale, cudaStream_t st) {
+    const size_t smem = sizeof(float) * static_cast<size_t>(D) * kConcatSpan * ((HAS_ATT ? 1 : 0) + (HAS_N ? 1 : 0));
+    if (smem > 200 * 1024) return DV_ERR_UNSUPPORTED;
+    auto kern = concat_volume_kernel<HAS_ATT, HAS_N>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+            return DV_ERR_LAUNCH;
+    }
+    const int spans = (HW + kConcatSpan - 1) / kConcatSpan;
+    // channels per CTA: amortise the per-CTA factor build, keep >= ~8 waves of CTAs
+    int cpc = (HAS_ATT || HAS_N) ? 16 : 8;
+    while (cpc > 8 && static_cast<int64_t>(spans) * B * ((2 * C + cpc - 1) / cpc) < 8LL * kNumSMs * 4) cpc /= 2;
+    dim3 grid(spans, (2 * C + cpc - 1) / cpc, B);
+    kern<<<grid, kConcatThreads, smem, st>>>(ref, tgt, out, C, HW, W, D, mask_left, cpc, att, xt, xt_is_f64, shift,
+                                            scale);
+    return finish_launch();
+}
+
+}  // namespace dv
+
+extern "C" int dv_concat_volume_f32(const float *ref, const float *tgt, float *out, int64_t B, int64_t C, int64_t H,
+                                    int64_t W, int64_t D, int mask_left, const float *att_logits, const void *xt,
+                                    int xt_is_f64, const float *shift, double scale, void *stream) {
+    using namespace dv;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!ref || !tgt || !out) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return DV_ERR_BAD_SHAPE;
+    if (xt && xt_is_f64 != 0 && xt_is_f64 != 1) return DV_ERR_BAD_DTYPE;
+    if (xt && !(scale > 0.0)) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || 2 * C > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    const bool fast = (HW % 4 == 0) && aligned16(ref) && aligned16(tgt) && aligned16(out) && W >= 4;
+    if (fast) {
+        int rc;
+        if (att_logits && xt)
+            rc = launch_concat<true, true>(ref, tgt, out, B, C, HW, W, D, mask_left, att_logits, xt, xt_is_f64, shift, scale, st);
+        else if (att_logits)
+            rc = launch_concat<true, false>(ref, tgt, out, B, C, HW, W, D, mask_left, att_logits, xt, xt_is_f64, shift, scale, st);
+        else if (xt)
+            rc = launch_concat<false, true>(ref, tgt, out, B, C, HW, W, D, mask_left, att_logits, xt, xt_is_f64, shift, scale, st);
+        else
+            rc = launch_concat<false, false>(ref, tgt, out, B, C, HW, W, D, mask_left, att_logits, xt, xt_is_f64, shift, scale, st);
+        if (rc != DV_ERR_UNSUPPORTED) return rc;
+    }
+    const int64_t total = B * 2 * C * D * HW;
+    const int threads = 256;
+    const int64_t blocks = (total + threads - 1) / threads;
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+    if (xt && xt_is_f64)
+        concat_volume_generic_kernel<double><<<grid, threads, 0, st>>>(
+            ref, tgt, out, static_cast<int>(C), static_cast<int>(HW), static_cast<int>(W), static_cast<int>(D), mask_left,
+            att_logits, static_cast<const double *>(xt), shift, scale, total);
+    else
+        concat_volume_generic_kernel<float><<<grid, threads, 0, st>>>(
+            ref, tgt, out, static_cast<int>(C), static_cast<int>(HW), static_cast<int>(W), static_cast<int>(D), mask_left,
+            att_logits, static_cast<const float *>(xt), shift, static_cast<float>(scale), total);
+    return finish_launch();
+}

@@ -1,0 +1,312 @@
+// ddim_step.cu — the DiffuVolume DDIM sampler arithmetic on the [B,D,h,w] state
+// (a7, a8, a10, a11, a12, a13) for sm_100a.
+//
+// Replaces ~40 tiny ATen launches per sampler step of the reference
+// (SceneFlow/models/acv_ddim.py:272-294 x_start + pred_noise, :320-338 renewal mask,
+//  :344-362 DDIM update + re-noising; KITTI12/models/pwcnet_ddim.py:504-526,:551-593;
+//  KITTI15/core/igev_stereo_ddim.py:268-290,:315-346) including two scatter_ calls, three
+// allocations and a hidden host->device copy of the mask every step.  One kernel, one thread
+// per quarter-resolution pixel, looping over the D=48 hypothesis planes; everything the
+// reference computes in float64 (the schedule buffers are float64, acv_ddim.py:113-119,
+// 147-157) is computed in float64 here, and every fp32 intermediate of the reference is
+// rounded to fp32 at the same point (dtype notes inline).
+#include "common.cuh"
+
+namespace dv {
+
+// F.interpolate(x, size=(h, w), mode='bilinear') with align_corners=False at one output pixel
+// (ATen area_pixel_compute_source_index + guard_index_and_lambda); `f` maps (row, col) -> value.
+struct BilinearTap {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ BilinearTap bilinear_tap(int dst, int in_size, int out_size) {
+    const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+    float src = __fsub_rn(__fmul_rn(scale, static_cast<float>(dst) + 0.5f), 0.5f);
+    if (src < 0.0f) src = 0.0f;
+    BilinearTap t;
+    t.i0 = min(static_cast<int>(floorf(src)), in_size - 1);
+    t.i1 = min(t.i0 + 1, in_size - 1);
+    t.l1 = fminf(fmaxf(src - static_cast<float>(t.i0), 0.0f), 1.0f);
+    t.l0 = 1.0f - t.l1;
+    return t;
+}
+__device__ __forceinline__ float bilinear_mix(const BilinearTap &ty, const BilinearTap &tx, float v00, float v01,
+                                              float v10, float v11) {
+    // rows first along x, then along y; no FMA contraction (matches the CPU reference bit for bit
+    // in the exact-ratio case)
+    const float r0 = __fadd_rn(__fmul_rn(tx.l0, v00), __fmul_rn(tx.l1, v01));
+    const float r1 = __fadd_rn(__fmul_rn(tx.l0, v10), __fmul_rn(tx.l1, v11));
+    return __fadd_rn(__fmul_rn(ty.l0, r0), __fmul_rn(ty.l1, r1));
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// disp_q -> (r, coff): 2-tap hypothesis weights of acv_ddim.py:279-283
+struct TwoTap {
+    int r;        // floor(disp_q), clamped to [0, D-1]
+    float coff;   // weight at r;  1 - coff at min(r+1, D-1)
+};
+__device__ __forceinline__ TwoTap two_tap(float dq, int D) {
+    TwoTap t;
+    const float rf = floorf(dq);
+    t.r = max(0, min(static_cast<int>(rf), D - 1));
+    t.coff = __fadd_rn(__fsub_rn(static_cast<float>(t.r), dq), 1.0f);  // real - disp + 1
+    return t;
+}
+__device__ __forceinline__ float x0_from_tap(const TwoTap &t, int d, int D, float s) {
+    float vol;
+    if (t.r == D - 1)
+        vol = d == D - 1 ? 1.0f : 0.0f;  // where(real == D-1, one_hot(D-1), ...)
+    else
+        vol = d == t.r ? t.coff : (d == t.r + 1 ? __fsub_rn(1.0f, t.coff) : 0.0f);
+    const float x0 = __fmul_rn(s, __fsub_rn(__fmul_rn(vol, 2.0f), 1.0f));  // scale * (x*2 - 1)
+    return clampf(x0, -s, s);
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(128)
+ddim_step_kernel(const dv_ddim_step_args a) {
+    const int hw = static_cast<int>(a.h * a.w);
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= hw) return;
+    const int b = blockIdx.y;
+    const int D = static_cast<int>(a.D), H = static_cast<int>(a.H), W = static_cast<int>(a.W);
+    const int y = pix / static_cast<int>(a.w), x = pix % static_cast<int>(a.w);
+    const BilinearTap ty = bilinear_tap(y, H, static_cast<int>(a.h));
+    const BilinearTap tx = bilinear_tap(x, W, static_cast<int>(a.w));
+    const int64_t fb = static_cast<int64_t>(b) * H * W;
+    const int64_t o00 = fb + static_cast<int64_t>(ty.i0) * W + tx.i0, o01 = fb + static_cast<int64_t>(ty.i0) * W + tx.i1;
+    const int64_t o10 = fb + static_cast<int64_t>(ty.i1) * W + tx.i0, o11 = fb + static_cast<int64_t>(ty.i1) * W + tx.i1;
+
+    // ---- a10: down-sampled disparity -> 2-tap x_start
+    const float d00 = a.disp[o00], d01 = a.disp[o01], d10 = a.disp[o10], d11 = a.disp[o11];
+    const float hi = a.disp_clamp_hi;
+    float dq = bilinear_mix(ty, tx, clampf(d00, 0.f, hi), clampf(d01, 0.f, hi), clampf(d10, 0.f, hi), clampf(d11, 0.f, hi));
+    dq = dq / 4.0f;
+    if (a.coords0) dq = clampf(dq + a.coords0[static_cast<int64_t>(b) * hw + pix], 0.0f, static_cast<float>(D - 1));
+    const TwoTap tap = two_tap(dq, D);
+
+    // ---- a11: renewal mask  mask = clamp(mask + down4(vote), 0, 1)
+    float m = a.mask ? a.mask[static_cast<int64_t>(b) * hw + pix] : 1.0f;
+    if (a.mask && (a.vote || a.used)) {
+        float v00, v01, v10, v11;
+        if (a.vote) {
+            v00 = a.vote[o00]; v01 = a.vote[o01]; v10 = a.vote[o10]; v11 = a.vote[o11];
+        } else {
+            const float th = a.vote_thr_dif;
+            v00 = fabsf(d00 - a.used[o00]) < th ? 1.f : 0.f;
+            v01 = fabsf(d01 - a.used[o01]) < th ? 1.f : 0.f;
+            v10 = fabsf(d10 - a.used[o10]) < th ? 1.f : 0.f;
+            v11 = fabsf(d11 - a.used[o11]) < th ? 1.f : 0.f;
+        }
+        m = clampf(m + bilinear_mix(ty, tx, v00, v01, v10, v11), 0.0f, 1.0f);
+        a.mask[static_cast<int64_t>(b) * hw + pix] = m;
+    }
+    const bool renoise_px = (a.renoise_mode != 0) && (m == 0.0f);
+
+    const float s32 = static_cast<float>(a.scale);
+    const XT sX = static_cast<XT>(a.scale);
+    const float san32 = static_cast<float>(a.sqrt_alpha_next);   // 0-dim fp64 tensor times fp32 tensor: fp32 math
+    const float sig32 = static_cast<float>(a.sigma);
+    const XT *xt = static_cast<const XT *>(a.xt);
+    const XT *sn = static_cast<const XT *>(a.step_noise);
+
+    for (int d = 0; d < D; ++d) {
+        const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
+        const float x0 = x0_from_tap(tap, d, D, s32);
+        a.x0_out[e] = x0;
+        // a8: pred_noise from the time-embedded, clamped, renormalised state (fp64)
+        const XT n = filter_n<XT>(xt[e], a.shift ? a.shift[b * D + d] : 0.0f, sX);
+        const double eps = (a.sqrt_recip * static_cast<double>(n) - static_cast<double>(x0)) / a.sqrt_recipm1;
+        if (a.eps_out) a.eps_out[e] = eps;
+        if (a.last_step) {
+            static_cast<float *>(a.x_next)[e] = x0;  // img = x_start (fp32)
+            continue;
+        }
+        // a12: img = x0 * sqrt(alpha_next) + c * eps + sigma * noise
+        const float t1 = __fmul_rn(x0, san32);
+        const double t2 = a.c * eps;
+        double t3;
+        if constexpr (sizeof(XT) == 4)
+            t3 = static_cast<double>(__fmul_rn(sig32, static_cast<float>(sn[e])));
+        else
+            t3 = a.sigma * static_cast<double>(sn[e]);
+        double img = (static_cast<double>(t1) + t2) + t3;
+        if (a.renoise_mode == 1) {
+            if (renoise_px) img = static_cast<const double *>(a.renoise)[e];
+        } else if (a.renoise_mode == 2) {
+            const double as = a.asd_is_f64 ? static_cast<const double *>(a.asd)[e]
+                                           : static_cast<double>(static_cast<const float *>(a.asd)[e]);
+            const double qn = a.q_noise_is_f64 ? static_cast<const double *>(a.q_noise)[e]
+                                               : static_cast<double>(static_cast<const float *>(a.q_noise)[e]);
+            const double rn = a.sqrt_ac * as + a.sqrt_1m_ac * qn;   // q_sample(asd, t)
+            if (a.asd_out) a.asd_out[e] = rn;
+            if (renoise_px) img = rn;
+        }
+        static_cast<double *>(a.x_next)[e] = img;
+    }
+}
+
+template <typename TX, typename TN>
+__global__ void q_sample_kernel(const TX *__restrict__ x, const TN *__restrict__ noise, double sa, double s1,
+                                double *__restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out[i] = sa * static_cast<double>(x[i]) + s1 * static_cast<double>(noise[i]);
+}
+
+template <typename TX, typename T0>
+__global__ void predict_noise_kernel(const TX *__restrict__ xt, const T0 *__restrict__ x0, double sr, double srm1,
+                                     double *__restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out[i] = (sr * static_cast<double>(xt[i]) - static_cast<double>(x0[i])) / srm1;
+}
+
+__global__ void xstart_kernel(const float *__restrict__ dq, float *__restrict__ out, int D, int hw, float s) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= hw) return;
+    const int b = blockIdx.y;
+    const TwoTap tap = two_tap(dq[static_cast<int64_t>(b) * hw + pix], D);
+    for (int d = 0; d < D; ++d) out[(static_cast<int64_t>(b) * D + d) * hw + pix] = x0_from_tap(tap, d, D, s);
+}
+
+__global__ void downsample_kernel(const float *__restrict__ in, float *__restrict__ out, int H, int W, int h, int w,
+                                  float lo, float hi, float post) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= h * w) return;
+    const int b = blockIdx.y;
+    const int y = pix / w, x = pix % w;
+    const BilinearTap ty = bilinear_tap(y, H, h), tx = bilinear_tap(x, W, w);
+    const float *ip = in + static_cast<int64_t>(b) * H * W;
+    float v00 = ip[static_cast<int64_t>(ty.i0) * W + tx.i0], v01 = ip[static_cast<int64_t>(ty.i0) * W + tx.i1];
+    float v10 = ip[static_cast<int64_t>(ty.i1) * W + tx.i0], v11 = ip[static_cast<int64_t>(ty.i1) * W + tx.i1];
+    if (lo <= hi) {
+        v00 = clampf(v00, lo, hi); v01 = clampf(v01, lo, hi); v10 = clampf(v10, lo, hi); v11 = clampf(v11, lo, hi);
+    }
+    out[static_cast<int64_t>(b) * h * w + pix] = __fmul_rn(bilinear_mix(ty, tx, v00, v01, v10, v11), post);
+}
+
+struct EnsembleArgs {
+    const float *maps[8];
+    float cof[8];
+    int n_maps;
+};
+__global__ void ensemble_kernel(const EnsembleArgs a, float *__restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        // torch.sum(final * cof, dim=0): products rounded, then summed in order
+        float acc = 0.0f;
+        for (int k = 0; k < a.n_maps; ++k) acc = __fadd_rn(acc, __fmul_rn(a.maps[k][i], a.cof[k]));
+        out[i] = acc;
+    }
+}
+
+static inline int ew_grid(int64_t n) {
+    const int64_t blocks = (n + 255) / 256;
+    return static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 16 ? (blocks > 0 ? blocks : 1)
+                                                                        : static_cast<int64_t>(kNumSMs) * 16);
+}
+
+}  // namespace dv
+
+extern "C" int dv_ddim_step(const dv_ddim_step_args *args, void *stream) {
+    using namespace dv;
+    if (!args) return DV_ERR_NULL;
+    const dv_ddim_step_args &a = *args;
+    if (!a.disp || !a.xt || !a.x0_out || !a.x_next) return DV_ERR_NULL;
+    if (a.B <= 0 || a.D <= 1 || a.h <= 0 || a.w <= 0 || a.H <= 0 || a.W <= 0 || !(a.scale > 0.0)) return DV_ERR_BAD_SHAPE;
+    if (a.B > 65535 || a.h * a.w > INT32_MAX || a.H * a.W > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    if (!a.last_step) {
+        if (!a.step_noise) return DV_ERR_NULL;
+        if (a.renoise_mode == 1 && !a.renoise) return DV_ERR_NULL;
+        if (a.renoise_mode == 2 && (!a.asd || !a.q_noise)) return DV_ERR_NULL;
+        if (a.renoise_mode < 0 || a.renoise_mode > 2) return DV_ERR_BAD_DTYPE;
+        if (a.renoise_mode != 0 && !a.mask) return DV_ERR_NULL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(static_cast<unsigned>((a.h * a.w + 127) / 128), static_cast<unsigned>(a.B));
+    if (a.xt_is_f64 == 1)
+        ddim_step_kernel<double><<<grid, 128, 0, st>>>(a);
+    else if (a.xt_is_f64 == 0)
+        ddim_step_kernel<float><<<grid, 128, 0, st>>>(a);
+    else
+        return DV_ERR_BAD_DTYPE;
+    return finish_launch();
+}
+
+extern "C" int dv_q_sample(const void *x_start, int x_is_f64, const void *noise, int noise_is_f64, double sqrt_ac,
+                           double sqrt_1m_ac, double *out, int64_t n, void *stream) {
+    using namespace dv;
+    if (!x_start || !noise || !out) return DV_ERR_NULL;
+    if (n <= 0) return DV_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int g = ew_grid(n);
+    if (x_is_f64 && noise_is_f64)
+        q_sample_kernel<double, double><<<g, 256, 0, st>>>(static_cast<const double *>(x_start), static_cast<const double *>(noise), sqrt_ac, sqrt_1m_ac, out, n);
+    else if (x_is_f64)
+        q_sample_kernel<double, float><<<g, 256, 0, st>>>(static_cast<const double *>(x_start), static_cast<const float *>(noise), sqrt_ac, sqrt_1m_ac, out, n);
+    else if (noise_is_f64)
+        q_sample_kernel<float, double><<<g, 256, 0, st>>>(static_cast<const float *>(x_start), static_cast<const double *>(noise), sqrt_ac, sqrt_1m_ac, out, n);
+    else
+        q_sample_kernel<float, float><<<g, 256, 0, st>>>(static_cast<const float *>(x_start), static_cast<const float *>(noise), sqrt_ac, sqrt_1m_ac, out, n);
+    return finish_launch();
+}
+
+extern "C" int dv_predict_noise_from_start(const void *x_t, int xt_is_f64, const void *x0, int x0_is_f64,
+                                           double sqrt_recip, double sqrt_recipm1, double *out, int64_t n,
+                                           void *stream) {
+    using namespace dv;
+    if (!x_t || !x0 || !out) return DV_ERR_NULL;
+    if (n <= 0) return DV_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int g = ew_grid(n);
+    if (xt_is_f64 && x0_is_f64)
+        predict_noise_kernel<double, double><<<g, 256, 0, st>>>(static_cast<const double *>(x_t), static_cast<const double *>(x0), sqrt_recip, sqrt_recipm1, out, n);
+    else if (xt_is_f64)
+        predict_noise_kernel<double, float><<<g, 256, 0, st>>>(static_cast<const double *>(x_t), static_cast<const float *>(x0), sqrt_recip, sqrt_recipm1, out, n);
+    else if (x0_is_f64)
+        predict_noise_kernel<float, double><<<g, 256, 0, st>>>(static_cast<const float *>(x_t), static_cast<const double *>(x0), sqrt_recip, sqrt_recipm1, out, n);
+    else
+        predict_noise_kernel<float, float><<<g, 256, 0, st>>>(static_cast<const float *>(x_t), static_cast<const float *>(x0), sqrt_recip, sqrt_recipm1, out, n);
+    return finish_launch();
+}
+
+extern "C" int dv_xstart_from_disp_f32(const float *disp_q, float *out, int64_t B, int64_t D, int64_t h, int64_t w,
+                                       double scale, void *stream) {
+    using namespace dv;
+    if (!disp_q || !out) return DV_ERR_NULL;
+    if (B <= 0 || D <= 1 || h <= 0 || w <= 0 || !(scale > 0.0) || B > 65535 || h * w > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    dim3 grid(static_cast<unsigned>((h * w + 127) / 128), static_cast<unsigned>(B));
+    xstart_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(disp_q, out, static_cast<int>(D),
+                                                                       static_cast<int>(h * w), static_cast<float>(scale));
+    return finish_launch();
+}
+
+extern "C" int dv_downsample_bilinear_f32(const float *in, float *out, int64_t B, int64_t H, int64_t W, int64_t h,
+                                          int64_t w, float lo, float hi, float post_scale, void *stream) {
+    using namespace dv;
+    if (!in || !out) return DV_ERR_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0 || B > 65535 || H * W > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    dim3 grid(static_cast<unsigned>((h * w + 127) / 128), static_cast<unsigned>(B));
+    downsample_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, out, static_cast<int>(H), static_cast<int>(W), static_cast<int>(h), static_cast<int>(w), lo, hi, post_scale);
+    return finish_launch();
+}
+
+extern "C" int dv_ensemble_f32(const float *const *maps, const float *cof, int n_maps, float *out, int64_t n,
+                               void *stream) {
+    using namespace dv;
+    if (!maps || !cof || !out) return DV_ERR_NULL;
+    if (n_maps <= 0 || n_maps > 8 || n <= 0) return DV_ERR_BAD_SHAPE;
+    EnsembleArgs a;
+    a.n_maps = n_maps;
+    for (int k = 0; k < n_maps; ++k) {
+        if (!maps[k]) return DV_ERR_NULL;
+        a.maps[k] = maps[k];
+        a.cof[k] = cof[k];
+    }
+    ensemble_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, out, n);
+    return finish_launch();
+}

@@ -1,0 +1,275 @@
+// gwc_volume.cu — group-wise correlation volume (a1, a2) for sm_100a.
+//
+// Replaces build_gwc_volume / groupwise_correlation of the reference
+// (SceneFlow/models/submodule.py:209-215,228-238; KITTI12/models/submodule.py:100-119;
+//  KITTI15/core/submodule.py:151-169), which launches 1 memset + 3*D ATen kernels and
+// re-reads both feature maps D times.  Here every feature byte is staged ONCE into shared
+// memory by the TMA engine (1-D bulk copies, cp.async.bulk -> SASS UBLKCP) and reused for
+// all D shifts; the [B,G,D,H,W] volume is written exactly once with 128-bit streaming
+// stores, zeros for x < d included (no memset).
+//
+// Data layout trick: a channel plane [H,W] is contiguous, so the kernel tiles the FLATTENED
+// plane into spans of SQ quads (4 floats).  tgt[y, x-d] is just flat index p-d; whenever
+// that index crosses a row start (x < d) the output is defined to be 0 and is selected,
+// never multiplied, so whatever the staged window holds there (previous row / previous
+// plane) is irrelevant.  This removes all row-tail handling and keeps every bulk copy and
+// every store 16-byte aligned for any W with (H*W) % 4 == 0.
+//
+// Work decomposition: CTA = (span, group g, batch b); thread = (quad q, disparity chunk):
+// it keeps a DC x 4 accumulator tile in registers and, per channel k, reads one float4 of
+// ref and a (DC+4)-float sliding window of tgt from shared memory (conflict-free: lanes map
+// to consecutive quads).  A warp's stores for one d cover 512 contiguous bytes.
+#include "common.cuh"
+
+namespace dv {
+
+template <int CPG, int DC, int SQ, int NCH>
+__global__ void __launch_bounds__(SQ * NCH)
+gwc_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out,
+                  int C, int HW, int W, int D, int G, int Dpad, int Dtot, int dofs) {
+    // Dtot = planes per (b,g) in `out`, dofs = slot of shift 0 (plain gwc: Dtot = D, dofs = 0;
+    // two-sided correlation volume: Dtot = 2m+1, dofs = m)
+    static_assert(DC % 4 == 0, "DC must be a multiple of 4");
+    constexpr int SPAN = SQ * 4;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    float *sL = smem;               // [CPG][SPAN]
+    float *sR = smem + CPG * SPAN;  // [CPG][SPAN + Dpad]; element Dpad of a row is flat index p0
+    const int rpitch = SPAN + Dpad;
+
+    const int b = blockIdx.z, g = blockIdx.y;
+    const int p0 = blockIdx.x * SPAN;
+    const int len = min(SPAN, HW - p0);  // multiple of 4 (HW % 4 == 0)
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (threadIdx.x < 32) {
+        const int64_t plane0 = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * CPG) * HW;
+        // The tgt window starts Dpad floats before the span; only the very first plane of the
+        // tensor can make that negative (those values are never used: x < d there).
+        int64_t roff0 = plane0 + p0 - Dpad;
+        const int skip0 = roff0 < 0 ? static_cast<int>(-roff0) : 0;
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = static_cast<uint32_t>(CPG) * (2u * len + Dpad) * 4u - 4u * skip0;
+            mbar_expect_tx(&bar, bytes);
+        }
+        __syncwarp();
+        for (int k = threadIdx.x; k < CPG; k += 32) {
+            bulk_g2s(sL + k * SPAN, ref + plane0 + static_cast<int64_t>(k) * HW + p0, 4u * len, &bar);
+            const int skip = k == 0 ? skip0 : 0;
+            bulk_g2s(sR + k * rpitch + skip, tgt + roff0 + static_cast<int64_t>(k) * HW + skip,
+                     4u * (len + Dpad - skip), &bar);
+        }
+    }
+    mbar_wait(&bar, 0);
+
+    const int q = threadIdx.x % SQ;
+    const int ch0 = threadIdx.x / SQ;
+    const int p = p0 + 4 * q;
+    if (p >= HW) return;
+    int xs[4];
+    xs[0] = p % W;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        xs[i] = xs[i - 1] + 1;
+        if (xs[i] >= W) xs[i] -= W;
+    }
+    constexpr float inv = 1.0f / CPG;  // mean over the group (torch's mean multiplies by 1/n on CUDA)
+
+    for (int ch = ch0; ch * DC < D; ch += NCH) {
+        const int d0 = ch * DC;
+        float acc[DC][4];
+#pragma unroll
+        for (int j = 0; j < DC; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
+
+        const float *lp = sL + 4 * q;
+        const float *rp = sR + Dpad + 4 * q - d0 - DC;  // 16-byte aligned: Dpad, d0, DC % 4 == 0
+#pragma unroll
+        for (int k = 0; k < CPG; ++k) {
+            const float4 l4 = *reinterpret_cast<const float4 *>(lp + k * SPAN);
+            const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+            float rw[DC + 4];
+#pragma unroll
+            for (int m = 0; m < DC / 4 + 1; ++m) {
+                const float4 r4 = *reinterpret_cast<const float4 *>(rp + k * rpitch + 4 * m);
+                rw[4 * m + 0] = r4.x;
+                rw[4 * m + 1] = r4.y;
+                rw[4 * m + 2] = r4.z;
+                rw[4 * m + 3] = r4.w;
+            }
+            // out(d0+j, x+i) += ref(x+i) * tgt(x+i-d0-j);  window index = DC + i - j
+#pragma unroll
+            for (int j = 0; j < DC; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(l[i], rw[DC + i - j], acc[j][i]);
+        }
+
+        float *op = out + ((static_cast<int64_t>(b) * G + g) * Dtot + dofs + d0) * HW + p;
+#pragma unroll
+        for (int j = 0; j < DC; ++j) {
+            const int d = d0 + j;
+            if (d < D) {
+                float4 v;
+                v.x = xs[0] >= d ? acc[j][0] * inv : 0.0f;
+                v.y = xs[1] >= d ? acc[j][1] * inv : 0.0f;
+                v.z = xs[2] >= d ? acc[j][2] * inv : 0.0f;
+                v.w = xs[3] >= d ? acc[j][3] * inv : 0.0f;
+                stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(j) * HW), v);
+            }
+        }
+    }
+}
+
+// Shape-agnostic kernel for planes with (H*W) % 4 != 0, unaligned pointers or an unusual
+// channels-per-group: one thread per output element, coalesced along x.  <1 % of the bytes
+// of any reference configuration ever take this path.
+__global__ void gwc_volume_generic_kernel(const float *__restrict__ ref, const float *__restrict__ tgt,
+                                          float *__restrict__ out, int C, int HW, int W, int D, int G,
+                                          int cpg, int Dtot, int dofs, int64_t total) {
+    const float inv = 1.0f / static_cast<float>(cpg);
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(idx % HW);
+        int64_t t = idx / HW;
+        const int d = static_cast<int>(t % D);
+        t /= D;
+        const int g = static_cast<int>(t % G);
+        const int64_t b = t / G;
+        const int x = p % W;
+        float v = 0.0f;
+        if (x >= d) {
+            const float *l = ref + (b * C + static_cast<int64_t>(g) * cpg) * HW + p;
+            const float *r = tgt + (b * C + static_cast<int64_t>(g) * cpg) * HW + p - d;
+            float acc = 0.0f;
+            for (int k = 0; k < cpg; ++k) acc = fmaf(l[static_cast<int64_t>(k) * HW], r[static_cast<int64_t>(k) * HW], acc);
+            v = acc * inv;
+        }
+        out[((b * G + g) * Dtot + dofs + d) * HW + p] = v;
+    }
+}
+
+// Negative shifts of build_corrleation_volume (KITTI12/models/submodule.py:128-131): for
+// i = -k the reference writes `volume[..., :-i] = gwc(ref[..., :-i], tgt[..., i:])`, i.e. only
+// the FIRST k columns, pairing ref[x] with tgt[W-k+x]; everything else in the plane stays 0.
+__global__ void corr_negative_kernel(const float *__restrict__ ref, const float *__restrict__ tgt,
+                                     float *__restrict__ out, int C, int HW, int W, int m, int G, int cpg,
+                                     int64_t total) {
+    const float inv = 1.0f / static_cast<float>(cpg);
+    const int Dtot = 2 * m + 1;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(idx % HW);
+        int64_t t = idx / HW;
+        const int slot = static_cast<int>(t % m);  // i = slot - m, k = m - slot
+        t /= m;
+        const int g = static_cast<int>(t % G);
+        const int64_t b = t / G;
+        const int k = m - slot;
+        const int x = p % W;
+        float v = 0.0f;
+        if (x < k) {  // k > W: both slices degenerate to the whole row (offset 0)
+            const float *l = ref + (b * C + static_cast<int64_t>(g) * cpg) * HW + p;
+            const float *r = tgt + (b * C + static_cast<int64_t>(g) * cpg) * HW + p + max(W - k, 0);
+            float acc = 0.0f;
+            for (int c = 0; c < cpg; ++c) acc = fmaf(l[static_cast<int64_t>(c) * HW], r[static_cast<int64_t>(c) * HW], acc);
+            v = acc * inv;
+        }
+        out[((b * G + g) * Dtot + slot) * HW + p] = v;
+    }
+}
+
+template <int CPG, int DC, int SQ, int NCH>
+static int launch_gwc(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int G,
+                      int Dtot, int dofs, cudaStream_t st) {
+    constexpr int SPAN = SQ * 4;
+    const int Dpad = ((D + DC - 1) / DC) * DC;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(CPG) * SPAN + static_cast<size_t>(CPG) * (SPAN + Dpad));
+    if (smem > 200 * 1024) return DV_ERR_UNSUPPORTED;
+    auto kern = gwc_volume_kernel<CPG, DC, SQ, NCH>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+            return DV_ERR_LAUNCH;
+    }
+    dim3 grid((HW + SPAN - 1) / SPAN, G, B);
+    kern<<<grid, SQ * NCH, smem, st>>>(ref, tgt, out, C, HW, W, D, G, Dpad, Dtot, dofs);
+    return finish_launch();
+}
+
+template <int CPG>
+static int dispatch_gwc(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int G,
+                        int Dtot, int dofs, cudaStream_t st) {
+    constexpr int DC = 12, SQ = 64;
+    const int nch = (D + DC - 1) / DC;
+    if (nch >= 4) return launch_gwc<CPG, DC, SQ, 4>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+    if (nch >= 2) return launch_gwc<CPG, DC, SQ, 2>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+    return launch_gwc<CPG, DC, SQ, 1>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+}
+
+static int gwc_volume_impl(const float *ref, const float *tgt, float *out, int64_t B, int64_t C, int64_t H, int64_t W,
+                           int64_t D, int64_t G, int64_t Dtot, int64_t dofs, cudaStream_t st) {
+    if (!ref || !tgt || !out) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0 || G <= 0 || C % G != 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || G > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    const int cpg = static_cast<int>(C / G);
+    const bool fast = (HW % 4 == 0) && aligned16(ref) && aligned16(tgt) && aligned16(out) && HW >= 64 && D <= 512 &&
+                      W >= 4;
+    if (fast) {
+        int rc = DV_ERR_UNSUPPORTED;
+        switch (cpg) {
+            case 4: rc = dispatch_gwc<4>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            case 8: rc = dispatch_gwc<8>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            case 12: rc = dispatch_gwc<12>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            case 16: rc = dispatch_gwc<16>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            case 32: rc = dispatch_gwc<32>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            default: break;
+        }
+        if (rc != DV_ERR_UNSUPPORTED) return rc;
+    }
+    const int64_t total = B * G * D * HW;
+    const int threads = 256;
+    const int64_t blocks = (total + threads - 1) / threads;
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+    gwc_volume_generic_kernel<<<grid, threads, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(HW),
+                                                        static_cast<int>(W), static_cast<int>(D), static_cast<int>(G), cpg,
+                                                        static_cast<int>(Dtot), static_cast<int>(dofs), total);
+    return finish_launch();
+}
+
+}  // namespace dv
+
+extern "C" int dv_gwc_volume_f32(const float *ref, const float *tgt, float *out, int64_t B, int64_t C, int64_t H,
+                                 int64_t W, int64_t D, int64_t G, void *stream) {
+    return dv::gwc_volume_impl(ref, tgt, out, B, C, H, W, D, G, D, 0, static_cast<cudaStream_t>(stream));
+}
+
+// a1: a single shift-0 plane of the volume is exactly groupwise_correlation.
+extern "C" int dv_groupwise_correlation_f32(const float *fea1, const float *fea2, float *out, int64_t B, int64_t C,
+                                            int64_t H, int64_t W, int64_t G, void *stream) {
+    return dv::gwc_volume_impl(fea1, fea2, out, B, C, H, W, 1, G, 1, 0, static_cast<cudaStream_t>(stream));
+}
+
+// a5: slots [m, 2m] are a gwc volume with D = m+1 written at plane offset m of a (2m+1)-plane
+// output; slots [0, m) are the reference's first-k-columns quirk.
+extern "C" int dv_corr_volume_2sided_f32(const float *ref, const float *tgt, float *out, int64_t B, int64_t C,
+                                         int64_t H, int64_t W, int64_t maxdisp, int64_t G, void *stream) {
+    using namespace dv;
+    if (maxdisp < 0) return DV_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rc = gwc_volume_impl(ref, tgt, out, B, C, H, W, maxdisp + 1, G, 2 * maxdisp + 1, maxdisp, st);
+    if (rc != DV_OK || maxdisp == 0) return rc;
+    const int64_t HW = H * W;
+    const int64_t total = B * G * maxdisp * HW;
+    const int64_t blocks = (total + 255) / 256;
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+    corr_negative_kernel<<<grid, 256, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(HW),
+                                               static_cast<int>(W), static_cast<int>(maxdisp), static_cast<int>(G),
+                                               static_cast<int>(C / G), total);
+    return finish_launch();
+}

@@ -1,0 +1,327 @@
+// softmax_regress.cu — softmax over D + disparity regression, with the renewal-mask
+// uncertainty, vote and ensemble accumulation fused (a6, a11, a13) for sm_100a.
+//
+// Replaces F.softmax(cost, dim=1) + disparity_regression (SceneFlow/models/submodule.py:173-177;
+// call sites acv_ddim.py:269-270, pwcnet_ddim.py:483-484, igev_stereo_ddim.py:384-385) and the
+// second full pass over the probability volume that ddim_sample makes for the renewal mask
+// (acv_ddim.py:320-331: |disp-used| < 1  &  sum_d |disp-d| p[d] < 3).  The reference writes
+// the 398 MB softmax, writes a 398 MB product, reads it back, then builds and reduces another
+// [B,192,H,W] temporary; here the cost volume is read from HBM exactly once and only
+// [B,H,W] maps are written.
+//
+// CTA = 32 quads of pixels x 8 disparity slices (256 threads).  A thread owns DPT
+// disparities (d = j*8 + slice) of one pixel quad and keeps them in registers (DPT float4,
+// all loads issued up front: 24 independent 128-bit loads per thread at D=192).  Max, sum,
+// sum d*e and sum |disp-d|*e are combined across the 8 slices through shared memory
+// (three block barriers); the warp of slice 0 writes the outputs.  exp is exp2 of a
+// pre-scaled argument (one FFMA + MUFU.EX2 per element).
+#include "common.cuh"
+
+namespace dv {
+
+constexpr int kSrSlices = 8;
+constexpr int kSrLanes = 32;
+constexpr int kSrThreads = kSrSlices * kSrLanes;
+
+template <int V>
+struct alignas(V * 4) Vec {
+    float v[V];
+};
+
+template <int V>
+__device__ __forceinline__ Vec<V> load_vec(const float *p) {
+    Vec<V> r;
+    if constexpr (V == 4) {
+        const float4 t = ldg_stream(reinterpret_cast<const float4 *>(p));
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+        r.v[0] = __ldg(p);
+    }
+    return r;
+}
+template <int V>
+__device__ __forceinline__ void store_vec(float *p, const Vec<V> &r) {
+    if constexpr (V == 4)
+        *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    else
+        *p = r.v[0];
+}
+
+// cost [B,D,HW];  pixel-vector index pv in [0, HW/V)
+template <int DPT, int V>
+__global__ void __launch_bounds__(kSrThreads)
+softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__restrict__ disp_out,
+                       float *__restrict__ prob_out, const float *__restrict__ used, float *__restrict__ unc_out,
+                       float *__restrict__ vote_out, float thr_dif, float thr_unc, float *__restrict__ ens_acc,
+                       float ens_coef, int ens_init) {
+    __shared__ Vec<V> red[3][kSrSlices][kSrLanes];
+    const int lane = threadIdx.x % kSrLanes;
+    const int slice = threadIdx.x / kSrLanes;
+    const int b = blockIdx.y;
+    const int64_t pv = blockIdx.x * static_cast<int64_t>(kSrLanes) + lane;
+    const bool live = pv * V < HW;
+    const float *cp = cost + static_cast<int64_t>(b) * D * HW + pv * V;
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    Vec<V> x[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+        const int d = j * kSrSlices + slice;
+        if (live && d < D) {
+            x[j] = load_vec<V>(cp + static_cast<int64_t>(d) * HW);
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) x[j].v[i] = -INFINITY;
+        }
+    }
+    // ---- max over D
+    Vec<V> m;
+#pragma unroll
+    for (int i = 0; i < V; ++i) m.v[i] = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j)
+#pragma unroll
+        for (int i = 0; i < V; ++i) m.v[i] = fmaxf(m.v[i], x[j].v[i]);
+    red[0][slice][lane] = m;
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < kSrSlices; ++s) {
+        const Vec<V> o = red[0][s][lane];
+#pragma unroll
+        for (int i = 0; i < V; ++i) m.v[i] = fmaxf(m.v[i], o.v[i]);
+    }
+    // ---- e = exp(x - max); S = sum e; Wd = sum d * e
+    Vec<V> mL, S, Wd;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        mL.v[i] = live ? m.v[i] * kLog2e : 0.0f;
+        S.v[i] = 0.0f;
+        Wd.v[i] = 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+        const float df = static_cast<float>(j * kSrSlices + slice);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float e = exp2f(fmaf(x[j].v[i], kLog2e, -mL.v[i]));  // exp2(-inf) = 0 for d >= D
+            x[j].v[i] = e;
+            S.v[i] += e;
+            Wd.v[i] = fmaf(df, e, Wd.v[i]);
+        }
+    }
+    red[1][slice][lane] = S;
+    red[2][slice][lane] = Wd;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        S.v[i] = 0.0f;
+        Wd.v[i] = 0.0f;
+    }
+#pragma unroll
+    for (int s = 0; s < kSrSlices; ++s) {
+        const Vec<V> a = red[1][s][lane], w = red[2][s][lane];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            S.v[i] += a.v[i];
+            Wd.v[i] += w.v[i];
+        }
+    }
+    Vec<V> rS, disp;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        rS.v[i] = 1.0f / S.v[i];
+        disp.v[i] = Wd.v[i] * rS.v[i];
+    }
+    if (prob_out && live) {
+        float *pp = prob_out + static_cast<int64_t>(b) * D * HW + pv * V;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const int d = j * kSrSlices + slice;
+            if (d < D) {
+                Vec<V> p;
+#pragma unroll
+                for (int i = 0; i < V; ++i) p.v[i] = x[j].v[i] * rS.v[i];
+                store_vec<V>(pp + static_cast<int64_t>(d) * HW, p);
+            }
+        }
+    }
+    const bool need_unc = (unc_out != nullptr) || (vote_out != nullptr);
+    Vec<V> U;
+#pragma unroll
+    for (int i = 0; i < V; ++i) U.v[i] = 0.0f;
+    if (need_unc) {  // uniform across the block
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const float df = static_cast<float>(j * kSrSlices + slice);
+#pragma unroll
+            for (int i = 0; i < V; ++i) U.v[i] = fmaf(fabsf(disp.v[i] - df), x[j].v[i], U.v[i]);
+        }
+        __syncthreads();  // red[0] is free again only after everyone has read the max
+        red[0][slice][lane] = U;
+        __syncthreads();
+        if (slice == 0) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) U.v[i] = 0.0f;
+#pragma unroll
+            for (int s = 0; s < kSrSlices; ++s) {
+                const Vec<V> a = red[0][s][lane];
+#pragma unroll
+                for (int i = 0; i < V; ++i) U.v[i] += a.v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) U.v[i] *= rS.v[i];
+        }
+    }
+    if (slice == 0 && live) {
+        const int64_t o = static_cast<int64_t>(b) * HW + pv * V;
+        if (disp_out) store_vec<V>(disp_out + o, disp);
+        if (unc_out) store_vec<V>(unc_out + o, U);
+        if (vote_out) {
+            const Vec<V> u0 = load_vec<V>(used + o);
+            Vec<V> vt;
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                vt.v[i] = (fabsf(disp.v[i] - u0.v[i]) < thr_dif && U.v[i] < thr_unc) ? 1.0f : 0.0f;
+            store_vec<V>(vote_out + o, vt);
+        }
+        if (ens_acc) {
+            Vec<V> a;
+            if (ens_init) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) a.v[i] = 0.0f;
+            } else {
+                a = load_vec<V>(ens_acc + o);
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) a.v[i] = fmaf(ens_coef, disp.v[i], a.v[i]);
+            store_vec<V>(ens_acc + o, a);
+        }
+    }
+}
+
+// Any D: one thread per pixel, three passes over D (the re-reads hit L2).
+__global__ void softmax_regress_generic_kernel(const float *__restrict__ cost, int D, int HW,
+                                               float *__restrict__ disp_out, float *__restrict__ prob_out,
+                                               const float *__restrict__ used, float *__restrict__ unc_out,
+                                               float *__restrict__ vote_out, float thr_dif, float thr_unc,
+                                               float *__restrict__ ens_acc, float ens_coef, int ens_init,
+                                               int64_t total) {
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t b = idx / HW, p = idx % HW;
+        const float *cp = cost + b * D * HW + p;
+        float m = -INFINITY;
+        for (int d = 0; d < D; ++d) m = fmaxf(m, cp[static_cast<int64_t>(d) * HW]);
+        float S = 0.0f, Wd = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            const float e = expf(cp[static_cast<int64_t>(d) * HW] - m);
+            S += e;
+            Wd = fmaf(static_cast<float>(d), e, Wd);
+        }
+        const float rS = 1.0f / S, disp = Wd * rS;
+        float U = 0.0f;
+        if (prob_out || unc_out || vote_out) {
+            for (int d = 0; d < D; ++d) {
+                const float pr = expf(cp[static_cast<int64_t>(d) * HW] - m) * rS;
+                if (prob_out) prob_out[b * D * HW + static_cast<int64_t>(d) * HW + p] = pr;
+                U = fmaf(fabsf(disp - static_cast<float>(d)), pr, U);
+            }
+        }
+        if (disp_out) disp_out[idx] = disp;
+        if (unc_out) unc_out[idx] = U;
+        if (vote_out) vote_out[idx] = (fabsf(disp - used[idx]) < thr_dif && U < thr_unc) ? 1.0f : 0.0f;
+        if (ens_acc) ens_acc[idx] = fmaf(ens_coef, disp, ens_init ? 0.0f : ens_acc[idx]);
+    }
+}
+
+// disparity_regression alone: out[b,p] = sum_d d * x[b,d,p] (sequential over d like the reference's sum)
+template <int V>
+__global__ void __launch_bounds__(256)
+disparity_regression_kernel(const float *__restrict__ x, float *__restrict__ out, int D, int HW) {
+    const int b = blockIdx.y;
+    const int64_t pv = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (pv * V >= HW) return;
+    const float *xp = x + static_cast<int64_t>(b) * D * HW + pv * V;
+    Vec<V> acc;
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc.v[i] = 0.0f;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) {
+        const Vec<V> t = load_vec<V>(xp + static_cast<int64_t>(d) * HW);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] = fmaf(t.v[i], static_cast<float>(d), acc.v[i]);
+    }
+    store_vec<V>(out + static_cast<int64_t>(b) * HW + pv * V, acc);
+}
+
+template <int DPT, int V>
+static void launch_sr(const float *cost, int B, int D, int HW, float *disp_out, float *prob_out, const float *used,
+                      float *unc_out, float *vote_out, float thr_dif, float thr_unc, float *ens_acc, float ens_coef,
+                      int ens_init, cudaStream_t st) {
+    const int pvs = (HW + V - 1) / V;
+    dim3 grid((pvs + kSrLanes - 1) / kSrLanes, B);
+    softmax_regress_kernel<DPT, V><<<grid, kSrThreads, 0, st>>>(cost, D, HW, disp_out, prob_out, used, unc_out, vote_out,
+                                                               thr_dif, thr_unc, ens_acc, ens_coef, ens_init);
+}
+
+}  // namespace dv
+
+extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, int64_t H, int64_t W, float *disp_out,
+                                      float *prob_out, const float *used, float *unc_out, float *vote_out,
+                                      float thr_dif, float thr_unc, float *ens_acc, float ens_coef, int ens_init,
+                                      void *stream) {
+    using namespace dv;
+    if (!cost) return DV_ERR_NULL;
+    if (vote_out && !used) return DV_ERR_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || D > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (HW % 4 == 0) && aligned16(cost) && (!disp_out || aligned16(disp_out)) &&
+                     (!prob_out || aligned16(prob_out)) && (!used || aligned16(used)) &&
+                     (!unc_out || aligned16(unc_out)) && (!vote_out || aligned16(vote_out)) &&
+                     (!ens_acc || aligned16(ens_acc));
+#define DV_SR(DPT)                                                                                                    \
+    do {                                                                                                              \
+        if (vec)                                                                                                      \
+            launch_sr<DPT, 4>(cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, \
+                              ens_coef, ens_init, st);                                                                \
+        else                                                                                                          \
+            launch_sr<DPT, 1>(cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, \
+                              ens_coef, ens_init, st);                                                                \
+    } while (0)
+    if (D <= 48) {
+        DV_SR(6);
+    } else if (D <= 96) {
+        DV_SR(12);
+    } else if (D <= 192) {
+        DV_SR(24);
+    } else {
+        const int64_t total = B * HW;
+        const int64_t blocks = (total + 255) / 256;
+        const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+        softmax_regress_generic_kernel<<<grid, 256, 0, st>>>(cost, static_cast<int>(D), static_cast<int>(HW), disp_out,
+                                                             prob_out, used, unc_out, vote_out, thr_dif, thr_unc,
+                                                             ens_acc, ens_coef, ens_init, total);
+    }
+#undef DV_SR
+    return finish_launch();
+}
+
+extern "C" int dv_disparity_regression_f32(const float *x, float *out, int64_t B, int64_t D, int64_t H, int64_t W,
+                                           void *stream) {
+    using namespace dv;
+    if (!x || !out) return DV_ERR_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535) return DV_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((HW % 4 == 0) && aligned16(x) && aligned16(out)) {
+        dim3 grid(static_cast<unsigned>((HW / 4 + 255) / 256), static_cast<unsigned>(B));
+        disparity_regression_kernel<4><<<grid, 256, 0, st>>>(x, out, static_cast<int>(D), static_cast<int>(HW));
+    } else {
+        dim3 grid(static_cast<unsigned>((HW + 255) / 256), static_cast<unsigned>(B));
+        disparity_regression_kernel<1><<<grid, 256, 0, st>>>(x, out, static_cast<int>(D), static_cast<int>(HW));
+    }
+    return finish_launch();
+}

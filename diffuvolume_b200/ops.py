@@ -1,0 +1,460 @@
+"""Torch-facing functional ops over the C-ABI library (include/dv_b200.h).
+
+PyTorch is plumbing here: it owns device memory (outputs are allocated with `torch.empty` on
+the input's device, so the caching allocator and stream-ordered reuse are respected) and the
+current stream.  Every op launches hand-written sm_100a kernels through ctypes; nothing in
+this module computes with ATen, and there is no CPU path: CPU tensors raise.
+
+Error conventions follow the reference: the conditions the reference guards
+with a bare `assert` raise AssertionError here too; anything else that the C layer rejects
+raises DvLibraryError with the dv_status name.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import DdimStepArgs, DvLibraryError, check
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise DvLibraryError(
+                "diffuvolume_b200 ops run on CUDA (sm_100a) tensors only; got a CPU tensor "
+                "(there is deliberately no CPU fallback)"
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"Expected all tensors to be on the same device, but found {dev} and {t.device}")
+    assert dev is not None
+    return dev
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise DvLibraryError(f"{name}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _is_f64(t: torch.Tensor, name: str) -> int:
+    if t.dtype == torch.float64:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise DvLibraryError(f"{name}: expected float32 or float64, got {t.dtype}")
+
+
+# --------------------------------------------------------------------------------------------
+# volumes
+# --------------------------------------------------------------------------------------------
+def groupwise_correlation(fea1: torch.Tensor, fea2: torch.Tensor, num_groups: int) -> torch.Tensor:
+    """a1 — SceneFlow/models/submodule.py:209-215."""
+    B, Cc, H, W = fea1.shape
+    assert Cc % num_groups == 0
+    _need_cuda(fea1, fea2)
+    fea1, fea2 = _f32c(fea1, "fea1"), _f32c(fea2, "fea2")
+    if fea2.shape != fea1.shape:
+        raise RuntimeError(f"The size of tensor a {tuple(fea1.shape)} must match the size of tensor b {tuple(fea2.shape)}")
+    out = torch.empty((B, num_groups, H, W), dtype=torch.float32, device=fea1.device)
+    with torch.cuda.device(fea1.device):
+        check(_lib.lib().dv_groupwise_correlation_f32(_ptr(fea1), _ptr(fea2), _ptr(out), B, Cc, H, W, num_groups,
+                                                      _stream(fea1)), "dv_groupwise_correlation_f32")
+    assert out.shape == (B, num_groups, H, W)
+    return out
+
+
+def gwc_volume(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, num_groups: int) -> torch.Tensor:
+    """a2 — build_gwc_volume, SceneFlow/models/submodule.py:228-238 -> [B,G,maxdisp,H,W]."""
+    B, Cc, H, W = ref.shape
+    assert Cc % num_groups == 0
+    _need_cuda(ref, tgt)
+    ref, tgt = _f32c(ref, "refimg_fea"), _f32c(tgt, "targetimg_fea")
+    if tgt.shape != ref.shape:
+        raise RuntimeError(f"The size of tensor a {tuple(ref.shape)} must match the size of tensor b {tuple(tgt.shape)}")
+    out = torch.empty((B, num_groups, maxdisp, H, W), dtype=torch.float32, device=ref.device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(ref.device):
+        check(_lib.lib().dv_gwc_volume_f32(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp, num_groups,
+                                           _stream(ref)), "dv_gwc_volume_f32")
+    return out
+
+
+def concat_volume(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, *, mask_left: bool,
+                  att_logits: Optional[torch.Tensor] = None, xt: Optional[torch.Tensor] = None,
+                  shift: Optional[torch.Tensor] = None, scale: float = 1.0,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a3 (+a4 +a9) — build_concat_volume with the optional fused factors.
+
+    mask_left=False: variant M (SceneFlow/models/submodule.py:180-191, KITTI15/core/submodule.py:206-217);
+    mask_left=True : variant T (SceneFlow/submodule.py:137-148, KITTI12/models/submodule.py:86-97).
+    att_logits [B,1,D,H,W]: multiply by softmax over D (acv_ddim.py:390).
+    xt [B,D,H,W] (+ shift [B,D]): multiply by the DDIM filter factor (acv_ddim.py:254-260).
+    """
+    B, Cc, H, W = ref.shape
+    _need_cuda(ref, tgt, att_logits, xt, shift)
+    ref, tgt = _f32c(ref, "refimg_fea"), _f32c(tgt, "targetimg_fea")
+    if tgt.shape != ref.shape:
+        raise RuntimeError(f"The size of tensor a {tuple(ref.shape)} must match the size of tensor b {tuple(tgt.shape)}")
+    if att_logits is not None:
+        att_logits = _f32c(att_logits, "att_logits")
+        if att_logits.numel() != B * maxdisp * H * W:
+            raise RuntimeError(f"att_logits has shape {tuple(att_logits.shape)}, expected [B,1,{maxdisp},{H},{W}]")
+    xt_f64 = 0
+    if xt is not None:
+        xt_f64 = _is_f64(xt, "xt")
+        xt = xt.contiguous()
+        if xt.numel() != B * maxdisp * H * W:
+            raise RuntimeError(f"xt has shape {tuple(xt.shape)}, expected [B,{maxdisp},{H},{W}]")
+        if shift is not None:
+            shift = _f32c(shift.reshape(B, maxdisp), "shift")
+    if out is None:
+        out = torch.empty((B, 2 * Cc, maxdisp, H, W), dtype=torch.float32, device=ref.device)
+    else:
+        assert out.shape == (B, 2 * Cc, maxdisp, H, W) and out.dtype == torch.float32 and out.is_contiguous()
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(ref.device):
+        check(_lib.lib().dv_concat_volume_f32(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp, int(mask_left),
+                                              _ptr(att_logits), _ptr(xt), xt_f64, _ptr(shift), float(scale),
+                                              _stream(ref)), "dv_concat_volume_f32")
+    return out
+
+
+def volume_filter(vol: torch.Tensor, xt: torch.Tensor, shift: Optional[torch.Tensor] = None, scale: float = 1.0, *,
+                  out: Optional[torch.Tensor] = None, return_n: bool = False):
+    """a9 — `volume * ((clamp(xt + shift, -s, s)/s + 1)/2).unsqueeze(1).float()` (acv_ddim.py:254-260)."""
+    B, Cc, D, H, W = vol.shape
+    _need_cuda(vol, xt, shift)
+    vol = _f32c(vol, "volume")
+    xt_f64 = _is_f64(xt, "noise")
+    xt = xt.contiguous()
+    if tuple(xt.shape) != (B, D, H, W):
+        raise RuntimeError(f"noise has shape {tuple(xt.shape)}, expected {(B, D, H, W)}")
+    if shift is not None:
+        shift = _f32c(shift.reshape(B, D), "shift")
+    if out is None:
+        out = torch.empty_like(vol)
+    n_out = torch.empty_like(xt) if return_n else None
+    if vol.numel():
+        with torch.cuda.device(vol.device):
+            check(_lib.lib().dv_volume_filter_f32(_ptr(vol), _ptr(out), B, Cc, D, H, W, _ptr(xt), xt_f64, _ptr(shift),
+                                                  float(scale), _ptr(n_out), _stream(vol)), "dv_volume_filter_f32")
+    return (out, n_out) if return_n else out
+
+
+def corr_volume_2sided(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, num_groups: int) -> torch.Tensor:
+    """a5 — build_corrleation_volume, KITTI12/models/submodule.py:121-135 -> [B,G,2*maxdisp+1,H,W]."""
+    B, Cc, H, W = ref.shape
+    assert Cc % num_groups == 0
+    _need_cuda(ref, tgt)
+    ref, tgt = _f32c(ref, "refimg_fea"), _f32c(tgt, "targetimg_fea")
+    if tgt.shape != ref.shape:
+        raise RuntimeError(f"The size of tensor a {tuple(ref.shape)} must match the size of tensor b {tuple(tgt.shape)}")
+    out = torch.empty((B, num_groups, 2 * maxdisp + 1, H, W), dtype=torch.float32, device=ref.device)
+    with torch.cuda.device(ref.device):
+        check(_lib.lib().dv_corr_volume_2sided_f32(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp, num_groups,
+                                                   _stream(ref)), "dv_corr_volume_2sided_f32")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# regression
+# --------------------------------------------------------------------------------------------
+def softmax_regress(cost: torch.Tensor, *, return_prob: bool = False, used: Optional[torch.Tensor] = None,
+                    want_unc: bool = False, vote_thresholds: Optional[Sequence[float]] = None,
+                    ens_acc: Optional[torch.Tensor] = None, ens_coef: float = 0.0, ens_init: bool = False):
+    """a6 (+a11 +a13) — softmax over dim 1 then disparity regression, one read of `cost`.
+
+    Returns a dict with 'disp' [B,H,W] and, when requested, 'prob' [B,D,H,W], 'unc' [B,H,W],
+    'vote' [B,H,W] (needs `used` and `vote_thresholds=(thr_dif, thr_unc)`).
+    """
+    assert len(cost.shape) == 4
+    B, D, H, W = cost.shape
+    _need_cuda(cost, used, ens_acc)
+    cost = _f32c(cost, "cost")
+    dev = cost.device
+    res = {"disp": torch.empty((B, H, W), dtype=torch.float32, device=dev)}
+    if return_prob:
+        res["prob"] = torch.empty_like(cost)
+    if want_unc:
+        res["unc"] = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    thr_dif = thr_unc = 0.0
+    if vote_thresholds is not None:
+        if used is None:
+            raise DvLibraryError("vote needs `used`")
+        used = _f32c(used.reshape(B, H, W), "used")
+        thr_dif, thr_unc = float(vote_thresholds[0]), float(vote_thresholds[1])
+        res["vote"] = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    if ens_acc is not None:
+        assert ens_acc.dtype == torch.float32 and ens_acc.is_contiguous() and ens_acc.numel() == B * H * W
+    with torch.cuda.device(dev):
+        check(_lib.lib().dv_softmax_regress_f32(_ptr(cost), B, D, H, W, _ptr(res["disp"]), _ptr(res.get("prob")),
+                                                _ptr(used), _ptr(res.get("unc")), _ptr(res.get("vote")), thr_dif,
+                                                thr_unc, _ptr(ens_acc), float(ens_coef), int(ens_init),
+                                                _stream(cost)), "dv_softmax_regress_f32")
+    return res
+
+
+def disparity_regression(x: torch.Tensor, maxdisp: int, keepdim: bool = False) -> torch.Tensor:
+    """a6 — SceneFlow/models/submodule.py:173-177 (keepdim=True: KITTI15/core/submodule.py:219-223)."""
+    assert len(x.shape) == 4
+    B, D, H, W = x.shape
+    if D != maxdisp:
+        raise RuntimeError(
+            f"The size of tensor a ({D}) must match the size of tensor b ({maxdisp}) at non-singleton dimension 1")
+    _need_cuda(x)
+    x = _f32c(x, "x")
+    out = torch.empty((B, 1, H, W) if keepdim else (B, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().dv_disparity_regression_f32(_ptr(x), _ptr(out), B, D, H, W, _stream(x)),
+              "dv_disparity_regression_f32")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# DDIM elementwise pieces
+# --------------------------------------------------------------------------------------------
+def q_sample(x_start: torch.Tensor, noise: torch.Tensor, sqrt_ac: float, sqrt_1m_ac: float) -> torch.Tensor:
+    """a7 — acv_ddim.py:241-246; result is float64 (the schedule buffers are float64)."""
+    _need_cuda(x_start, noise)
+    x_start, noise = x_start.contiguous(), noise.contiguous()
+    if x_start.shape != noise.shape:
+        raise RuntimeError("x_start and noise must have the same shape")
+    out = torch.empty(x_start.shape, dtype=torch.float64, device=x_start.device)
+    with torch.cuda.device(x_start.device):
+        check(_lib.lib().dv_q_sample(_ptr(x_start), _is_f64(x_start, "x_start"), _ptr(noise), _is_f64(noise, "noise"),
+                                     float(sqrt_ac), float(sqrt_1m_ac), _ptr(out), out.numel(), _stream(out)),
+              "dv_q_sample")
+    return out
+
+
+def predict_noise_from_start(x_t: torch.Tensor, x0: torch.Tensor, sqrt_recip: float, sqrt_recipm1: float) -> torch.Tensor:
+    """a8 — acv_ddim.py:248-252; float64 result."""
+    _need_cuda(x_t, x0)
+    x_t, x0 = x_t.contiguous(), x0.contiguous()
+    if x_t.shape != x0.shape:
+        raise RuntimeError("x_t and x0 must have the same shape")
+    out = torch.empty(x_t.shape, dtype=torch.float64, device=x_t.device)
+    with torch.cuda.device(x_t.device):
+        check(_lib.lib().dv_predict_noise_from_start(_ptr(x_t), _is_f64(x_t, "x_t"), _ptr(x0), _is_f64(x0, "x0"),
+                                                     float(sqrt_recip), float(sqrt_recipm1), _ptr(out), out.numel(),
+                                                     _stream(out)), "dv_predict_noise_from_start")
+    return out
+
+
+def xstart_from_disp(disp_q: torch.Tensor, D: int = 48, scale: float = 1.0) -> torch.Tensor:
+    """a10 — quarter-res disparity [B,h,w] (already /4) -> 2-tap x_start volume [B,D,h,w] in [-s, s]."""
+    _need_cuda(disp_q)
+    disp_q = _f32c(disp_q, "disp")
+    B, h, w = disp_q.shape[0], disp_q.shape[-2], disp_q.shape[-1]
+    assert disp_q.numel() == B * h * w
+    out = torch.empty((B, D, h, w), dtype=torch.float32, device=disp_q.device)
+    with torch.cuda.device(disp_q.device):
+        check(_lib.lib().dv_xstart_from_disp_f32(_ptr(disp_q), _ptr(out), B, D, h, w, float(scale), _stream(out)),
+              "dv_xstart_from_disp_f32")
+    return out
+
+
+def downsample_bilinear(x: torch.Tensor, size, clamp=None, post_scale: float = 1.0) -> torch.Tensor:
+    """F.interpolate(clamp(x), size=size, mode='bilinear') * post_scale for [B,H,W] maps."""
+    _need_cuda(x)
+    x = _f32c(x, "x")
+    B, H, W = x.shape[0], x.shape[-2], x.shape[-1]
+    assert x.numel() == B * H * W
+    h, w = int(size[0]), int(size[1])
+    lo, hi = (1.0, 0.0) if clamp is None else (float(clamp[0]), float(clamp[1]))
+    out = torch.empty((B, h, w), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().dv_downsample_bilinear_f32(_ptr(x), _ptr(out), B, H, W, h, w, lo, hi, float(post_scale),
+                                                    _stream(out)), "dv_downsample_bilinear_f32")
+    return out
+
+
+def ensemble(maps: Sequence[torch.Tensor], cof: Sequence[float]) -> torch.Tensor:
+    """a13 — torch.sum(cat(maps) * cof, dim=0) (acv_ddim.py:365-369)."""
+    assert len(maps) == len(cof) and 0 < len(maps) <= 8
+    _need_cuda(*maps)
+    maps = [_f32c(m, "map") for m in maps]
+    n = maps[0].numel()
+    assert all(m.numel() == n for m in maps)
+    out = torch.empty_like(maps[0])
+    ptrs = (C.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
+    cofs = (C.c_float * len(maps))(*[float(c) for c in cof])
+    with torch.cuda.device(out.device):
+        check(_lib.lib().dv_ensemble_f32(ptrs, cofs, len(maps), _ptr(out), n, _stream(out)), "dv_ensemble_f32")
+    return out
+
+
+def ddim_step(*, disp: torch.Tensor, xt: torch.Tensor, shift: Optional[torch.Tensor], scale: float,
+              sqrt_recip: float, sqrt_recipm1: float, last_step: bool,
+              disp_clamp_hi: float = 191.0, coords0: Optional[torch.Tensor] = None,
+              vote: Optional[torch.Tensor] = None, used: Optional[torch.Tensor] = None, vote_thr_dif: float = 0.0,
+              mask: Optional[torch.Tensor] = None,
+              sqrt_alpha_next: float = 0.0, c: float = 0.0, sigma: float = 0.0,
+              step_noise: Optional[torch.Tensor] = None,
+              renoise: Optional[torch.Tensor] = None,
+              asd: Optional[torch.Tensor] = None, q_noise: Optional[torch.Tensor] = None,
+              sqrt_ac: float = 0.0, sqrt_1m_ac: float = 0.0, want_asd_out: bool = False,
+              want_eps: bool = False):
+    """a8+a10+a11+a12 — one fused DDIM sampler step (see dv_ddim_step_args in include/dv_b200.h).
+
+    Returns dict(x0=[B,D,h,w] fp32, x_next=[B,D,h,w] fp64 (fp32 when last_step), eps=fp64 or None,
+    asd_out=fp64 or None).  `mask` is updated in place.
+    """
+    _need_cuda(disp, xt, shift, coords0, vote, used, mask, step_noise, renoise, asd, q_noise)
+    B, D, h, w = xt.shape
+    disp = _f32c(disp, "disp")
+    H, W = disp.shape[-2], disp.shape[-1]
+    assert disp.numel() == B * H * W
+    xt = xt.contiguous()
+    dev = xt.device
+    a = DdimStepArgs()
+    a.B, a.D, a.h, a.w, a.H, a.W = B, D, h, w, H, W
+    a.disp = _ptr(disp)
+    a.disp_clamp_hi = float(disp_clamp_hi)
+    keep = [disp, xt]
+    if coords0 is not None:
+        coords0 = _f32c(coords0, "coords0")
+        assert coords0.numel() == B * h * w
+        keep.append(coords0)
+    a.coords0 = _ptr(coords0)
+    a.xt = _ptr(xt)
+    a.xt_is_f64 = _is_f64(xt, "xt")
+    if shift is not None:
+        shift = _f32c(shift.reshape(B, D), "shift")
+        keep.append(shift)
+    a.shift = _ptr(shift)
+    a.scale = float(scale)
+    if vote is not None:
+        vote = _f32c(vote, "vote")
+        assert vote.numel() == B * H * W
+        keep.append(vote)
+    if used is not None:
+        used = _f32c(used, "used")
+        assert used.numel() == B * H * W
+        keep.append(used)
+    a.vote, a.used, a.vote_thr_dif = _ptr(vote), _ptr(used), float(vote_thr_dif)
+    if mask is not None:
+        assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.numel() == B * h * w
+    a.mask = _ptr(mask)
+    a.sqrt_recip, a.sqrt_recipm1 = float(sqrt_recip), float(sqrt_recipm1)
+    a.last_step = int(last_step)
+    a.sqrt_alpha_next, a.c, a.sigma = float(sqrt_alpha_next), float(c), float(sigma)
+    if step_noise is not None:
+        if step_noise.dtype != xt.dtype:
+            raise DvLibraryError("step_noise must have the dtype of xt (it is randn_like(img) in the reference)")
+        step_noise = step_noise.contiguous()
+        assert step_noise.shape == xt.shape
+        keep.append(step_noise)
+    a.step_noise = _ptr(step_noise)
+    a.renoise_mode = 0
+    asd_out = None
+    if not last_step:
+        if renoise is not None:
+            if renoise.dtype != torch.float64:
+                raise DvLibraryError("renoise must be float64 (rand_like of a float64 tensor in the reference)")
+            renoise = renoise.contiguous()
+            assert renoise.shape == xt.shape
+            keep.append(renoise)
+            a.renoise_mode = 1
+            a.renoise = _ptr(renoise)
+        elif asd is not None:
+            assert q_noise is not None
+            asd, q_noise = asd.contiguous(), q_noise.contiguous()
+            assert asd.shape == xt.shape and q_noise.shape == xt.shape
+            keep += [asd, q_noise]
+            a.renoise_mode = 2
+            a.asd, a.asd_is_f64 = _ptr(asd), _is_f64(asd, "asd")
+            a.q_noise, a.q_noise_is_f64 = _ptr(q_noise), _is_f64(q_noise, "q_noise")
+            a.sqrt_ac, a.sqrt_1m_ac = float(sqrt_ac), float(sqrt_1m_ac)
+            if want_asd_out:
+                asd_out = torch.empty(xt.shape, dtype=torch.float64, device=dev)
+            a.asd_out = _ptr(asd_out)
+    x0 = torch.empty((B, D, h, w), dtype=torch.float32, device=dev)
+    eps = torch.empty((B, D, h, w), dtype=torch.float64, device=dev) if want_eps else None
+    x_next = torch.empty((B, D, h, w), dtype=torch.float32 if last_step else torch.float64, device=dev)
+    a.x0_out, a.eps_out, a.x_next = _ptr(x0), _ptr(eps), _ptr(x_next)
+    with torch.cuda.device(dev):
+        check(_lib.lib().dv_ddim_step(C.byref(a), _stream(xt)), "dv_ddim_step")
+    del keep
+    return {"x0": x0, "x_next": x_next, "eps": eps, "asd_out": asd_out}
+
+
+# --------------------------------------------------------------------------------------------
+# IGEV geometry
+# --------------------------------------------------------------------------------------------
+def corr1d_allpairs(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:
+    """a14 — Combined_Geo_Encoding_Volume.corr (geometry_ddim.py:72-80) -> [B,H,W1,1,W2]."""
+    B, D, H, W1 = fmap1.shape
+    _, _, _, W2 = fmap2.shape
+    _need_cuda(fmap1, fmap2)
+    fmap1, fmap2 = _f32c(fmap1, "fmap1"), _f32c(fmap2, "fmap2")
+    out = torch.empty((B, H, W1, 1, W2), dtype=torch.float32, device=fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        check(_lib.lib().dv_corr1d_allpairs_f32(_ptr(fmap1), _ptr(fmap2), _ptr(out), B, D, H, W1, W2, _stream(out)),
+              "dv_corr1d_allpairs_f32")
+    return out
+
+
+def geo_permute(geo: torch.Tensor) -> torch.Tensor:
+    """geo [B,C,D,h,w] -> [B*h*w, C, 1, D] (geometry_ddim.py:19)."""
+    B, Cc, D, h, w = geo.shape
+    _need_cuda(geo)
+    geo = _f32c(geo, "geo_volume")
+    out = torch.empty((B * h * w, Cc, 1, D), dtype=torch.float32, device=geo.device)
+    with torch.cuda.device(geo.device):
+        check(_lib.lib().dv_geo_permute_f32(_ptr(geo), _ptr(out), B, Cc, D, h, w, _stream(out)), "dv_geo_permute_f32")
+    return out
+
+
+def avgpool_w2(rows: torch.Tensor) -> torch.Tensor:
+    """F.avg_pool2d(rows, [1,2], stride=[1,2]) for [N, C, 1, L] rows (geometry_ddim.py:24-30)."""
+    _need_cuda(rows)
+    rows = _f32c(rows, "rows")
+    L = rows.shape[-1]
+    N = rows.numel() // L
+    out = torch.empty((*rows.shape[:-1], L // 2), dtype=torch.float32, device=rows.device)
+    with torch.cuda.device(rows.device):
+        check(_lib.lib().dv_avgpool_w2_f32(_ptr(rows), _ptr(out), N, L, _stream(out)), "dv_avgpool_w2_f32")
+    return out
+
+
+def geo_lookup(geo_pyr: Sequence[torch.Tensor], corr_pyr: Sequence[torch.Tensor], disp: torch.Tensor,
+               coords: torch.Tensor, noisy: Optional[torch.Tensor], radius: int) -> torch.Tensor:
+    """a15 — Combined_Geo_Encoding_Volume.__call__ (geometry_ddim.py:33-69) -> [B, L*(C+1)*(2r+1), h, w]."""
+    b, _, h, w = disp.shape
+    _need_cuda(disp, coords, noisy, *geo_pyr, *corr_pyr)
+    levels = len(geo_pyr)
+    Cc, D = geo_pyr[0].shape[1], geo_pyr[0].shape[-1]
+    W2 = corr_pyr[0].shape[-1]
+    disp, coords = _f32c(disp, "disp"), _f32c(coords, "coords")
+    assert coords.numel() == b * h * w
+    if noisy is not None:
+        noisy = _f32c(noisy, "noisy")
+        assert noisy.numel() == b * h * w * D
+    geo_pyr = [_f32c(g, "geo_pyramid") for g in geo_pyr]
+    corr_pyr = [_f32c(c_, "corr_pyramid") for c_ in corr_pyr]
+    out = torch.empty((b, levels * (Cc + 1) * (2 * radius + 1), h, w), dtype=torch.float32, device=disp.device)
+    gp = (C.c_void_p * levels)(*[g.data_ptr() for g in geo_pyr])
+    cp = (C.c_void_p * levels)(*[c_.data_ptr() for c_ in corr_pyr])
+    with torch.cuda.device(disp.device):
+        check(_lib.lib().dv_geo_lookup_f32(gp, cp, _ptr(noisy), _ptr(disp), _ptr(coords), _ptr(out), b, Cc, D, h, w,
+                                           W2, levels, radius, _stream(out)), "dv_geo_lookup_f32")
+    return out

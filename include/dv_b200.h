@@ -1,0 +1,228 @@
+/*
+ * dv_b200.h — C-ABI of the B200-native DiffuVolume cost-volume hot path.
+ *
+ * Every entry point is `extern "C" int f(...)`: raw device pointers, int64 sizes, a
+ * `cudaStream_t` passed as `void*`; it returns a dv_status (0 = ok) and never throws,
+ * allocates, frees or retains memory.  The caller owns every buffer.  All launches go to
+ * the stream given (0 = legacy default stream).  The library is re-entrant: no globals
+ * except a relaxed launch counter (dv_launch_count), so it can be called from one host
+ * thread per device concurrently (the reference runs under nn.DataParallel,
+ * SceneFlow/main.py:67).
+ *
+ * The reference (iSEE-Laboratory/DiffuVolume) has no FFI of its own: the hot path is a set
+ * of module-level Python functions.  Each function below names the
+ * reference function (file:line, paths relative to the reference root) it replaces; the
+ * Python mirror of those names lives in diffuvolume_b200/{sceneflow,kitti12,kitti15}.py and
+ * the binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Layouts: all tensors are contiguous NCHW / NCDHW, fp32 unless a `*_is_f64` flag says
+ * otherwise.  "HW" below is H*W.
+ */
+#ifndef DV_B200_H
+#define DV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DV_OK = 0,
+    DV_ERR_BAD_SHAPE = 1,   /* a dimension is <= 0, C % G != 0, D out of the supported range ... */
+    DV_ERR_BAD_DTYPE = 2,   /* dtype flag not understood */
+    DV_ERR_MISALIGNED = 3,  /* a pointer that must be 16-byte aligned is not */
+    DV_ERR_LAUNCH = 4,      /* cudaGetLastError() after the launch was not cudaSuccess */
+    DV_ERR_NULL = 5,        /* a required pointer is NULL */
+    DV_ERR_UNSUPPORTED = 6  /* valid request outside what the kernels implement */
+} dv_status;
+
+/* ---- library introspection ------------------------------------------------------------ */
+int dv_version(void);                       /* 10000*major + 100*minor + patch */
+const char *dv_status_string(int status);   /* static string */
+int64_t dv_launch_count(void);              /* kernels launched by this library so far */
+int dv_built_for_sm(void);                  /* 100 (sm_100a) */
+
+/* ---- a1: groupwise_correlation  (SceneFlow/models/submodule.py:209-215;
+ *          KITTI12/models/submodule.py:100-106; KITTI15/core/submodule.py:151-157)
+ * out[b,g,p] = mean_k fea1[b,g*cpg+k,p] * fea2[b,g*cpg+k,p],  p in [0,HW)                  */
+int dv_groupwise_correlation_f32(const float *fea1, const float *fea2, float *out,
+                                 int64_t B, int64_t C, int64_t H, int64_t W, int64_t G,
+                                 void *stream);
+
+/* ---- a2: build_gwc_volume  (SceneFlow/models/submodule.py:228-238;
+ *          KITTI12/models/submodule.py:109-119; KITTI15/core/submodule.py:159-169)
+ * out[b,g,d,y,x] = mean_k ref[b,g*cpg+k,y,x] * tgt[b,g*cpg+k,y,x-d]  for x >= d, else +0.0
+ * out is [B,G,D,H,W]; every element is written (no memset needed).                          */
+int dv_gwc_volume_f32(const float *ref, const float *tgt, float *out,
+                      int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int64_t G,
+                      void *stream);
+
+/* ---- a3 (+a4, +a9 fused): build_concat_volume
+ *   variant M (mask_left=0): SceneFlow/models/submodule.py:180-191, KITTI15/core/submodule.py:206-217
+ *   variant T (mask_left=1): SceneFlow/submodule.py:137-148, KITTI12/models/submodule.py:86-97
+ * out[b,c,d,y,x]   = ref[b,c,y,x]      (variant M: all x; variant T: x >= d else 0)
+ * out[b,C+c,d,y,x] = tgt[b,c,y,x-d]    (x >= d else 0)
+ * Optional fused factors, applied in the reference's rounding order:
+ *   att_logits [B,1,D,H,W] != NULL : out = softmax_d(att_logits) * out   (acv_ddim.py:390, acv.py:203)
+ *   xt != NULL                     : out = out * float(n),  n = ((clamp(xt + shift[b,d], -s, s)/s)+1)/2
+ *                                    (acv_ddim.py:254-260; shift = DynamicHead output, head.py:74-77)
+ *     xt is [B,D,H,W] fp32 (xt_is_f64=0) or fp64 (=1); shift is [B,D] fp32 or NULL (= 0).      */
+int dv_concat_volume_f32(const float *ref, const float *tgt, float *out,
+                         int64_t B, int64_t C, int64_t H, int64_t W, int64_t D,
+                         int mask_left,
+                         const float *att_logits,
+                         const void *xt, int xt_is_f64, const float *shift, double scale,
+                         void *stream);
+
+/* ---- a9 at the op boundary: the DDIM filter multiply on an existing volume
+ *          (SceneFlow/models/acv_ddim.py:254-260; KITTI12/models/pwcnet_ddim.py:466-472)
+ * out[b,c,d,p] = vol[b,c,d,p] * float(n[b,d,p]);  n as above.  out may alias vol.
+ * n_out (optional, same dtype as xt, [B,D,H,W]) receives n itself (the tensor the
+ * reference passes on to predict_noise_from_start, acv_ddim.py:294).                        */
+int dv_volume_filter_f32(const float *vol, float *out,
+                         int64_t B, int64_t C, int64_t D, int64_t H, int64_t W,
+                         const void *xt, int xt_is_f64, const float *shift, double scale,
+                         void *n_out, void *stream);
+
+/* ---- a5: build_corrleation_volume (sic)  (KITTI12/models/submodule.py:121-135;
+ *          SceneFlow/submodule.py:172-186) — two-sided shifts i in [-m, m], slot i+m.
+ * i >= 0: out[b,g,i+m,y,x] = mean_k ref[..,x]*tgt[..,x-i]        for x >= i, else 0
+ * i <  0 (k=-i): out[b,g,i+m,y,x] = mean_k ref[..,x]*tgt[..,W-k+x] for x <  k, else 0
+ *         (the reference's `[..., :-i]` slices select the FIRST k columns — reproduced).   */
+int dv_corr_volume_2sided_f32(const float *ref, const float *tgt, float *out,
+                              int64_t B, int64_t C, int64_t H, int64_t W, int64_t maxdisp,
+                              int64_t G, void *stream);
+
+/* ---- a6 (+a11, +a13 fused): softmax over D followed by disparity_regression
+ *          (F.softmax(cost,1) + SceneFlow/models/submodule.py:173-177; call sites
+ *          acv_ddim.py:269-270; KITTI12 pwcnet_ddim.py:483-484; KITTI15 igev_stereo_ddim.py:384-385)
+ * cost [B,D,H,W] -> disp[b,p] = sum_d d * softmax_d(cost)[b,d,p]
+ * Optional outputs (NULL to skip):
+ *   prob_out [B,D,H,W]  the softmax itself (PWCNet_ddim returns it, pwcnet_ddim.py:528)
+ *   unc_out  [B,H,W]    sum_d |disp - d| * p[d]            (acv_ddim.py:324-329)
+ *   vote_out [B,H,W]    1.0f if |disp-used|<thr_dif && unc<thr_unc else 0.0f (acv_ddim.py:322-331);
+ *                       needs `used` [B,H,W]
+ *   ens_acc  [B,H,W]    ens_acc = (ens_init ? 0 : ens_acc) + ens_coef * disp   (acv_ddim.py:365-369) */
+int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, int64_t H, int64_t W,
+                           float *disp_out, float *prob_out,
+                           const float *used, float *unc_out, float *vote_out,
+                           float thr_dif, float thr_unc,
+                           float *ens_acc, float ens_coef, int ens_init,
+                           void *stream);
+
+/* ---- a6 alone: disparity_regression on an already-normalised volume
+ *          (SceneFlow/models/submodule.py:173-177)  out[b,p] = sum_d d * x[b,d,p]              */
+int dv_disparity_regression_f32(const float *x, float *out,
+                                int64_t B, int64_t D, int64_t H, int64_t W, void *stream);
+
+/* ---- a7: q_sample  (SceneFlow/models/acv_ddim.py:241-246)
+ * out = sqrt_ac * x_start + sqrt_1m_ac * noise, computed and stored in fp64 (buffer
+ * promotion); x_start / noise are fp32 or fp64 per flag; n = element count.                  */
+int dv_q_sample(const void *x_start, int x_is_f64, const void *noise, int noise_is_f64,
+                double sqrt_ac, double sqrt_1m_ac, double *out, int64_t n, void *stream);
+
+/* ---- a8: predict_noise_from_start  (SceneFlow/models/acv_ddim.py:248-252)
+ * out = (sqrt_recip * x_t - x0) / sqrt_recipm1   in fp64                                     */
+int dv_predict_noise_from_start(const void *x_t, int xt_is_f64, const void *x0, int x0_is_f64,
+                                double sqrt_recip, double sqrt_recipm1, double *out,
+                                int64_t n, void *stream);
+
+/* ---- a10: disparity map -> 2-tap x_start volume
+ *          (SceneFlow/models/acv_ddim.py:272-292, :403-419; KITTI15 igev_stereo_ddim.py:268-288)
+ * disp_q [B,h,w] is the quarter-resolution disparity already divided by 4 (and, for IGEV,
+ * offset and clamped); r = floor(disp_q); vol[r] = r+1-disp_q; vol[min(r+1,D-1)] = disp_q-r
+ * (written second, so it wins when r == D-1 ... then r == D-1 is forced to one-hot(D-1));
+ * x0 = clamp(scale*(2*vol-1), -scale, scale).  out [B,D,h,w] fp32.                           */
+int dv_xstart_from_disp_f32(const float *disp_q, float *out,
+                            int64_t B, int64_t D, int64_t h, int64_t w, double scale,
+                            void *stream);
+
+/* ---- bilinear /4 down-sampling of a full-resolution map (F.interpolate(..., size=(H//4, W//4),
+ *          mode='bilinear'), align_corners=False; acv_ddim.py:274, :333)
+ * out[b,y,x] = post_scale * bilinear(clamp(in, lo, hi))   (clamp skipped when lo > hi)        */
+int dv_downsample_bilinear_f32(const float *in, float *out,
+                               int64_t B, int64_t H, int64_t W, int64_t h, int64_t w,
+                               float lo, float hi, float post_scale, void *stream);
+
+/* ---- a8+a10+a11+a12 fused: one DDIM sampler step on the [B,D,h,w] state
+ *          (SceneFlow/models/acv_ddim.py:272-294, :320-362; KITTI12 pwcnet_ddim.py:504-526, :551-593;
+ *           KITTI15 igev_stereo_ddim.py:268-290, :315-346)
+ * See dv_ddim_step_args below; every tensor is caller-owned.                                  */
+typedef struct {
+    int64_t B, D, h, w;        /* state shape [B,D,h,w] (D = 48 in the reference)               */
+    int64_t H, W;              /* full-resolution shape of `disp` / `vote` ([B,H,W])            */
+    /* inputs */
+    const float *disp;         /* [B,H,W] regressed disparity of this step                       */
+    float disp_clamp_hi;       /* clamp(disp, 0, disp_clamp_hi) before down-sampling (191 / 47)  */
+    const float *coords0;      /* IGEV only: [B,h,w] init disparity added after /4, then clamp
+                                  to [0, D-1] (igev_stereo_ddim.py:271-273); NULL otherwise      */
+    const void *xt;            /* [B,D,h,w] current noisy state (pre time-embedding)             */
+    int xt_is_f64;
+    const float *shift;        /* [B,D] time-embedding shift or NULL                              */
+    double scale;              /* self.scale (1.0)                                               */
+    const float *vote;         /* [B,H,W] 0/1 renewal votes at full res (from dv_softmax_regress_f32), or NULL */
+    const float *used;         /* when vote == NULL and used != NULL: vote = |disp - used| < vote_thr_dif
+                                  computed inline (IGEV: igev_stereo_ddim.py:316-317); both NULL: mask unchanged */
+    float vote_thr_dif;
+    float *mask;               /* [B,h,w] renewal mask, updated in place: clamp(mask+down4(vote),0,1) */
+    /* schedule scalars (host-computed in fp64 from the cosine schedule) */
+    double sqrt_recip, sqrt_recipm1;   /* at t                                                   */
+    int last_step;             /* time_next < 0: x_next = x0, nothing else                        */
+    double sqrt_alpha_next, c, sigma;  /* DDIM update coefficients                                */
+    const void *step_noise;    /* [B,D,h,w] randn_like(img) of this step (dtype = xt's)           */
+    /* re-noising of un-renewed pixels: x_next = where(mask==0, renoise, x_next)                  */
+    int renoise_mode;          /* 0 none; 1 `renoise` given directly (ACV: uniform rand fp64);
+                                  2 renoise = sqrt_ac*asd + sqrt_1m_ac*q_noise (PCW / IGEV)        */
+    const void *renoise;       /* mode 1: [B,D,h,w] fp64                                         */
+    const void *asd;           /* mode 2: [B,D,h,w] x_start of `used` (fp32 or fp64)              */
+    int asd_is_f64;
+    const void *q_noise;       /* mode 2: [B,D,h,w] randn_like(asd), fp32 or fp64 per flag          */
+    int q_noise_is_f64;
+    double sqrt_ac, sqrt_1m_ac;
+    double *asd_out;           /* mode 2, optional: q_sample result (PCW keeps it cumulatively)    */
+    /* outputs */
+    float *x0_out;             /* [B,D,h,w] fp32 x_start                                          */
+    double *eps_out;           /* [B,D,h,w] fp64 pred_noise, optional                             */
+    void *x_next;              /* [B,D,h,w]: fp64 normally; fp32 x0 copy when last_step           */
+} dv_ddim_step_args;
+
+int dv_ddim_step(const dv_ddim_step_args *args, void *stream);
+
+/* ---- a14: all-pairs 1-D correlation  (KITTI15/core/geometry_ddim.py:72-80)
+ * out[b,y,x1,x2] = sum_c fmap1[b,c,y,x1] * fmap2[b,c,y,x2]   ([B,H,W1,W2], no 1/sqrt(C))     */
+int dv_corr1d_allpairs_f32(const float *fmap1, const float *fmap2, float *out,
+                           int64_t B, int64_t C, int64_t H, int64_t W1, int64_t W2, void *stream);
+
+/* ---- a14: pyramid helpers (geometry_ddim.py:18-30)
+ * geo [B,C,D,h,w] -> geo_rows [B*h*w, C, D] (permute(0,3,4,1,2));
+ * rows [N, L] -> pooled [N, L/2] (avg_pool2d([1,2], stride [1,2]), floor)                     */
+int dv_geo_permute_f32(const float *geo, float *rows, int64_t B, int64_t C, int64_t D,
+                       int64_t h, int64_t w, void *stream);
+int dv_avgpool_w2_f32(const float *rows, float *pooled, int64_t N, int64_t L, void *stream);
+
+/* ---- a15: Combined_Geo_Encoding_Volume.__call__  (KITTI15/core/geometry_ddim.py:33-69,
+ *          geometry.py:34-58; bilinear_sampler core/utils/utils.py:59-77)
+ * For level i in [0,num_levels): taps dx = -r..r
+ *   geo part : bilinear sample (zero padding, align_corners=True) of geo_pyr[i][n, c, :] * noise_i[n, :]
+ *              at x = disp[n]/2^i + dx            -> channel  base_i + c*(2r+1) + tap
+ *   corr part: bilinear sample of corr_pyr[i][n, :] at x = (coords[n] - disp[n])/2^i + dx
+ *                                                 -> channel  base_i + C*(2r+1) + tap
+ * out is [B, num_levels*(C+1)*(2r+1), h, w].  noisy may be NULL (geometry.py: no multiply).
+ * noisy is the raw [B*h*w, D] reinterpretation of the caller's [B,D,h,w] tensor (the
+ * reference reshapes without a permute, geometry_ddim.py:37 — reproduced bit-compatibly);
+ * level-i noise is noisy avg-pooled i times.                                                  */
+int dv_geo_lookup_f32(const float *const *geo_pyr, const float *const *corr_pyr,
+                      const float *noisy, const float *disp, const float *coords, float *out,
+                      int64_t B, int64_t C, int64_t D, int64_t h, int64_t w, int64_t W2,
+                      int num_levels, int radius, void *stream);
+
+/* ---- a13: ensemble (acv_ddim.py:365-369): out[p] = sum_i cof[i] * maps[i][p], i < n_maps <= 8
+ * `maps` is a HOST array of n_maps device pointers, `cof` a HOST array of n_maps floats.          */
+int dv_ensemble_f32(const float *const *maps, const float *cof, int n_maps, float *out,
+                    int64_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DV_B200_H */
