@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on B200: "volume+DDIM-filter pairs/s @540x960 D=192".
+
+A step = one pass of the ACVNet+DiffuVolume hot path (diffuvolume_b200.pipeline.AcvHotPath) over a
+batch of B synthetic stereo pairs per GPU: 1x gwc volume (C=320, G=40, D=48 at 135x240), 1x concat
+volume + ACV softmax weights, T=5 x {DDIM filter, softmax + regression + uncertainty + vote +
+ensemble over [B,192,540,960], fused DDIM state update}.  The 2-D/3-D convolutions are out of scope;
+their outputs are the synthetic inputs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 8]
+                    [--filter regenerate|volume]
+
+N > 1: launched by torchrun, one rank per GPU, batch-sharded (weak scaling: B pairs per rank, no
+data-path collective; one all_reduce of the timing / checksum at the end).  Rank 0 prints ONE JSON
+line.  `--impl reference` times the reference's op sequence on the host CPU (oracle/torch_port.py,
+all ATen threads) — the only place where the oracle is the thing measured.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "volume+DDIM-filter pairs/s @540x960 D=192"
+H, W, MAXDISP, C_GWC, G, C_CAT, T_STEPS = 540, 960, 192, 320, 40, 32, 5
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class KernelTimer:
+    """CUDA-event pairs around each kernel category, recorded on torch's current stream (the stream the
+    C-ABI launches on), resolved after the timed region."""
+
+    def __init__(self):
+        self.pairs = {}
+
+    @contextlib.contextmanager
+    def __call__(self, name):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self.pairs.setdefault(name, []).append((a, b))
+
+    def resolve(self):
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.pairs.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_inputs(B: int, device, seed: int):
+    """Synthetic inputs of SURVEY.md §8d, generated on the device with a seeded torch generator."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    h, w, D = H // 4, W // 4, MAXDISP // 4
+    rn = lambda *s, dt=torch.float32: torch.randn(*s, generator=g, device=device, dtype=dt)
+    ru = lambda *s, dt=torch.float32: torch.rand(*s, generator=g, device=device, dtype=dt)
+    inp = dict(
+        feat_l=rn(B, C_GWC, h, w), feat_r=rn(B, C_GWC, h, w),
+        cfeat_l=rn(B, C_CAT, h, w), cfeat_r=rn(B, C_CAT, h, w),
+        att_logits=rn(B, 1, D, h, w),
+        costs=[rn(B, MAXDISP, H, W) * 4.0],            # one 3.2 GB logits buffer, re-read by every step (>> L2)
+        used=ru(B, H, W) * 191.0,
+        disp_q=ru(B, h, w) * 47.75,
+        shifts=[rn(B, D) * 0.1 for _ in range(T_STEPS)],
+        step_noises=[rn(B, D, h, w, dt=torch.float32 if i == 0 else torch.float64) for i in range(T_STEPS - 1)],
+        renoises=[ru(B, D, h, w, dt=torch.float64) for _ in range(T_STEPS - 1)],
+    )
+    return inp
+
+
+def algorithmic_bytes(B: int, filter_mode: str):
+    """Compulsory unique reads + writes per launch, fp32, for a batch of B pairs."""
+    hw, HW, D = (H // 4) * (W // 4), H * W, MAXDISP // 4
+    vol = 2 * C_CAT * D * hw * 4
+    state64 = D * hw * 8
+    per_pair = {
+        "gwc_volume": 2 * C_GWC * hw * 4 + G * D * hw * 4,
+        "concat_acv": 2 * C_CAT * hw * 4 + D * hw * 4 + vol,
+        "filter": (2 * C_CAT * hw * 4 + D * hw * 4 + state64 + vol) if filter_mode == "regenerate" else (2 * vol + state64),
+        "softmax_regress": MAXDISP * HW * 4 + 5 * HW * 4,      # cost read; used read; disp, vote written; ens read+write
+        "ddim_step": 4 * HW * 2 + D * hw * (8 + 8 + 8 + 4 + 8),  # disp+vote taps; xt, noise, renoise read; x0, x_next written
+    }
+    return {k: v * B for k, v in per_pair.items()}
+
+
+def run_ours(args):
+    from diffuvolume_b200 import _lib
+    from diffuvolume_b200.pipeline import AcvHotPath
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    inp = make_inputs(B, dev, seed=1234 + rank)   # rank-offset seeds: every rank owns different pairs
+    path = AcvHotPath(filter_mode=args.filter)
+    timer = KernelTimer()
+
+    def step(t=None):
+        return path(**inp, timer=t)
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    launches0 = _lib.launch_count()
+    gpu_index = int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local]) if os.environ.get("CUDA_VISIBLE_DEVICES") else local
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(gpu_index) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step(timer)
+        ev1.record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    checksum = float(out["pred"].double().sum())
+    if dist is not None:
+        tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+        # the one collective of the path: the end-of-sweep metric reduction
+        cs = torch.tensor([checksum, float(B)], device=dev, dtype=torch.float64)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+        checksum = float(cs[0].item())
+    ms_per_step = ms_total / args.steps
+    value = (B * world) / (ms_per_step / 1e3)
+
+    result = None
+    if rank == 0:
+        kt = timer.resolve()
+        ab = algorithmic_bytes(B, args.filter)
+        peak, peak_src = measured_peak_gbs()
+        kernels = {}
+        for name, times in kt.items():
+            avg = sum(times) / len(times)
+            kernels[name] = {"launches_per_step": len(times) // args.steps, "avg_ms": round(avg, 4),
+                             "ms_per_step": round(sum(times) / args.steps, 4),
+                             "algorithmic_GB": round(ab[name] / 1e9, 4), "achieved_GBs": round(ab[name] / 1e9 / (avg / 1e3), 1),
+                             "frac_of_peak": round(ab[name] / 1e9 / (avg / 1e3) / peak, 4)}
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        step_bytes = sum(ab[k] * kernels[k]["launches_per_step"] for k in kernels)
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(dom, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        result = {
+            "metric": METRIC, "value": round(value, 2), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]/[4]: gwc G=40 D=48 @135x240 + concat/ACV + T=5 DDIM filter + "
+                                   "softmax/regression over [B,192,540,960]", "pairs_per_gpu": B, "global_batch": B * world,
+                       "filter_mode": args.filter, "l2": "inputs larger than L2 (3.2 GB logits, 3.2 GB volumes per step)",
+                       "parallelism": f"batch-sharded x{world}"},
+            "clocks": clk.summary(),
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBs"], "peak": peak,
+                         "unit": "GB/s", "frac": kernels[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
+                         "whole_step_achieved": round(step_bytes / 1e9 / (ms_per_step / 1e3), 1),
+                         "whole_step_frac": round(step_bytes / 1e9 / (ms_per_step / 1e3) / peak, 4)},
+            "kernels": kernels,
+            "checksum": checksum,
+        }
+    # ---- e2e: the same step through the public API with HOST buffers ------------------------
+    e2e = None if args.no_e2e else run_e2e(args, path, inp, dev, barrier, dist, world)
+    if rank == 0:
+        result["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_reference(steps=args.cpu_steps, warmup=1)
+        print(json.dumps(result))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, path, inp, dev, barrier, dist, world):
+    """Host-resident inputs (pinned) -> H2D copies -> hot path -> D2H of the prediction, every step inside the
+    timed region.  The per-step logits are part of the step's inputs, so they are copied too."""
+    B = args.batch
+    names = ["feat_l", "feat_r", "cfeat_l", "cfeat_r", "att_logits", "used", "disp_q"]
+    host = {k: inp[k].cpu().pin_memory() for k in names}
+    host["costs"] = [inp["costs"][0].cpu().pin_memory()]
+    for k in ("shifts", "step_noises", "renoises"):
+        host[k] = [t.cpu().pin_memory() for t in inp[k]]
+    pred_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    h2d = sum(host[k].numel() * host[k].element_size() for k in names)
+    h2d += T_STEPS * host["costs"][0].numel() * 4      # the logits of each of the T steps are step inputs
+    h2d += sum(t.numel() * t.element_size() for k in ("shifts", "step_noises", "renoises") for t in host[k])
+    d2h = pred_host.numel() * 4
+    dst = {k: torch.empty_like(inp[k]) for k in names}
+    dst["costs"] = [torch.empty_like(inp["costs"][0]) for _ in range(2)]   # double buffer for the per-step logits
+    for k in ("shifts", "step_noises", "renoises"):
+        dst[k] = [torch.empty_like(t) for t in inp[k]]
+
+    def stage_logits(i):
+        # the logits of step i arrive from the host right before that step consumes them; two device buffers
+        # alternate (stream order guarantees step i-2 has consumed a buffer before it is overwritten)
+        buf = dst["costs"][i % 2]
+        buf.copy_(host["costs"][0], non_blocking=True)
+        return buf
+
+    def one():
+        for k in names:
+            dst[k].copy_(host[k], non_blocking=True)
+        for k in ("shifts", "step_noises", "renoises"):
+            for d, s in zip(dst[k], host[k]):
+                d.copy_(s, non_blocking=True)
+        out = path(**{k: dst[k] for k in names}, costs=stage_logits, shifts=dst["shifts"],
+                   step_noises=dst["step_noises"], renoises=dst["renoises"])
+        pred_host.copy_(out["pred"], non_blocking=True)
+
+    steps = max(2, min(args.steps, args.e2e_steps))
+    one()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        one()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return {"value": round(B * world * steps / (ms / 1e3), 2), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": round(ms / steps, 3),
+            "note": "pinned host inputs incl. the T=5 per-step [B,192,540,960] logits; PCIe-bound"}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(steps: int, warmup: int):
+    """The reference's op sequence on the host CPU (oracle/torch_port.py), one pair (B=1) per step."""
+    from oracle import dv_oracle as O
+    from oracle import torch_port as P
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
+    g = torch.Generator().manual_seed(0)
+    h, w, D = H // 4, W // 4, MAXDISP // 4
+    rn = lambda *s, dt=torch.float32: torch.randn(*s, generator=g, dtype=dt)
+    sched = O.Schedule()
+    a = dict(feat_l=rn(1, C_GWC, h, w), feat_r=rn(1, C_GWC, h, w), cfeat_l=rn(1, C_CAT, h, w), cfeat_r=rn(1, C_CAT, h, w),
+             att_logits=rn(1, 1, D, h, w), costs=[rn(1, MAXDISP, H, W) * 4.0] * T_STEPS,
+             used=torch.rand(1, H, W, generator=g) * 191.0,
+             asd=P.xstart_from_pred(torch.rand(1, H, W, generator=g) * 191.0),
+             shifts=[rn(1, D) * 0.1 for _ in range(T_STEPS)],
+             step_noises=[rn(1, D, h, w, dt=torch.float32 if i == 0 else torch.float64) for i in range(T_STEPS - 1)],
+             renoises=[torch.rand(1, D, h, w, generator=g, dtype=torch.float64) for _ in range(T_STEPS - 1)])
+    with torch.no_grad():
+        for _ in range(warmup):
+            P.hot_path_pair(**a, sched=sched)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            P.hot_path_pair(**a, sched=sched)
+            ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return {"value": round(1.0 / sec, 4), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} x 1 pair (B=1, all T=5 steps, 540x960 D=192), torch CPU op-for-op port of the reference "
+                      f"(oracle/torch_port.py), {sec:.2f} s/pair",
+            "seconds_per_pair": round(sec, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference(steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+    v = cb["value"]
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 / v, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "same hot path, 1 pair per step on the host CPU", "pairs_per_step": 1},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=8, help="stereo pairs per GPU per step")
+    ap.add_argument("--filter", choices=["regenerate", "volume"], default="regenerate")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

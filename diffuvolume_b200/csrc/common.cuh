@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <cstdlib>
 #include "../../include/dv_b200.h"
 
 namespace dv {
@@ -12,6 +13,12 @@ extern std::atomic<int64_t> g_launch_count;
 inline int finish_launch(int nlaunches = 1) {
     g_launch_count.fetch_add(nlaunches, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? DV_OK : DV_ERR_LAUNCH;
+}
+
+// Kernel-variant switches for tuning runs (scripts/tune_kernels.py); unset = the shipped default.
+inline int tune_variant(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -56,27 +56,11 @@ concat_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tg
     const int c_end = min(c_begin + chans_per_cta, 2 * C);
 
     if (HAS_ATT) {
-        // softmax over D of att[b,0,:,p] (F.softmax(att_weights, dim=2)): exp(a - max) / sum
-        if (threadIdx.x < kConcatSpan) {
-            const int px = threadIdx.x, p = p0 + px;
-            if (p < HW) {
-                const float *ap = att + static_cast<int64_t>(b) * D * HW + p;
-                float mx = -INFINITY;
-                for (int d = 0; d < D; ++d) {
-                    const float a = ap[static_cast<int64_t>(d) * HW];
-                    sw[d * kConcatSpan + px] = a;
-                    mx = fmaxf(mx, a);
-                }
-                float sum = 0.0f;
-                for (int d = 0; d < D; ++d) {
-                    const float e = expf(sw[d * kConcatSpan + px] - mx);
-                    sw[d * kConcatSpan + px] = e;
-                    sum += e;
-                }
-                for (int d = 0; d < D; ++d) sw[d * kConcatSpan + px] = sw[d * kConcatSpan + px] / sum;
-            } else {
-                for (int d = 0; d < D; ++d) sw[d * kConcatSpan + px] = 0.0f;
-            }
+        // stage the raw attention logits of the span: all threads, coalesced, independent loads
+        for (int e = threadIdx.x; e < D * kConcatSpan; e += kConcatThreads) {
+            const int d = e / kConcatSpan, px = e % kConcatSpan;
+            const int p = p0 + px;
+            sw[e] = p < HW ? __ldg(att + (static_cast<int64_t>(b) * D + d) * HW + p) : 0.0f;
         }
     }
     if (HAS_N) {
@@ -84,6 +68,22 @@ concat_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tg
             fill_filter_factor<double>(sn, static_cast<const double *>(xt), shift, scale, b, D, HW, p0);
         else
             fill_filter_factor<float>(sn, static_cast<const float *>(xt), shift, static_cast<float>(scale), b, D, HW, p0);
+    }
+    if (HAS_ATT) {
+        __syncthreads();
+        // softmax over D of att[b,0,:,p] (F.softmax(att_weights, dim=2)): exp(a - max) / sum, in place
+        if (threadIdx.x < kConcatSpan) {
+            float *col = sw + threadIdx.x;
+            float mx = -INFINITY;
+            for (int d = 0; d < D; ++d) mx = fmaxf(mx, col[d * kConcatSpan]);
+            float sum = 0.0f;
+            for (int d = 0; d < D; ++d) {
+                const float e = expf(col[d * kConcatSpan] - mx);
+                col[d * kConcatSpan] = e;
+                sum += e;
+            }
+            for (int d = 0; d < D; ++d) col[d * kConcatSpan] = col[d * kConcatSpan] / sum;
+        }
     }
     if (HAS_ATT || HAS_N) __syncthreads();
 
@@ -209,7 +209,7 @@ static int launch_concat(const float *ref, const float *tgt, float *out, int B, 
     }
     const int spans = (HW + kConcatSpan - 1) / kConcatSpan;
     // channels per CTA: amortise the per-CTA factor build, keep >= ~8 waves of CTAs
-    int cpc = (HAS_ATT || HAS_N) ? 16 : 8;
+    int cpc = tune_variant("DV_CONCAT_CPC", HAS_N ? 16 : 8);
     while (cpc > 8 && static_cast<int64_t>(spans) * B * ((2 * C + cpc - 1) / cpc) < 8LL * kNumSMs * 4) cpc /= 2;
     dim3 grid(spans, (2 * C + cpc - 1) / cpc, B);
     kern<<<grid, kConcatThreads, smem, st>>>(ref, tgt, out, C, HW, W, D, mask_left, cpc, att, xt, xt_is_f64, shift,

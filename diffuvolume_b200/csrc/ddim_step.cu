@@ -45,31 +45,42 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fm
 // disp_q -> (r, coff): 2-tap hypothesis weights of acv_ddim.py:279-283
 struct TwoTap {
     int r;        // floor(disp_q), clamped to [0, D-1]
-    float coff;   // weight at r;  1 - coff at min(r+1, D-1)
+    float coff;   // weight at r;  1 - coff at r+1
+    bool last;    // r == D-1: the reference forces one-hot(D-1) (acv_ddim.py:289-290)
 };
 __device__ __forceinline__ TwoTap two_tap(float dq, int D) {
+    // The clamp is done in float on purpose: with the integer form max(0, min(int(floor), D-1)) ptxas 12.9
+    // (sm_100a) fused the clamp into VIMNMX.RELU with a predicate output and reused that predicate as
+    // "r == D-1" in one unrolled loop iteration, which produced wrong one-hot planes for d % 4 == 1
+    // (caught by tests/test_gpu_parity.py::test_xstart_golden_and_known_answers).
     TwoTap t;
-    const float rf = floorf(dq);
-    t.r = max(0, min(static_cast<int>(rf), D - 1));
-    t.coff = __fadd_rn(__fsub_rn(static_cast<float>(t.r), dq), 1.0f);  // real - disp + 1
+    const float top = static_cast<float>(D - 1);
+    const float rf = fminf(fmaxf(floorf(dq), 0.0f), top);
+    t.r = static_cast<int>(rf);
+    t.coff = __fadd_rn(__fsub_rn(rf, dq), 1.0f);  // real - disp + 1
+    t.last = rf >= top;
     return t;
 }
 __device__ __forceinline__ float x0_from_tap(const TwoTap &t, int d, int D, float s) {
-    float vol;
-    if (t.r == D - 1)
-        vol = d == D - 1 ? 1.0f : 0.0f;  // where(real == D-1, one_hot(D-1), ...)
-    else
-        vol = d == t.r ? t.coff : (d == t.r + 1 ? __fsub_rn(1.0f, t.coff) : 0.0f);
+    // vol[r] = coff, vol[r+1] = 1 - coff; when r == D-1 the plane is one_hot(D-1)
+    const float w0 = t.last ? 1.0f : t.coff;
+    const float w1 = __fsub_rn(1.0f, t.coff);
+    const float vol = d == t.r ? w0 : ((d == t.r + 1 && !t.last) ? w1 : 0.0f);
     const float x0 = __fmul_rn(s, __fsub_rn(__fmul_rn(vol, 2.0f), 1.0f));  // scale * (x*2 - 1)
     return clampf(x0, -s, s);
 }
 
+constexpr int kDdimPx = 32;   // pixels per CTA (x)
+constexpr int kDdimDg = 8;    // hypothesis groups per CTA (y): thread (px, dg) owns d = dg, dg+8, ...
+
 template <typename XT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kDdimPx * kDdimDg)
 ddim_step_kernel(const dv_ddim_step_args a) {
     const int hw = static_cast<int>(a.h * a.w);
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= hw) return;
+    const int pix_raw = blockIdx.x * kDdimPx + threadIdx.x;
+    const int dg = threadIdx.y;
+    const bool live = pix_raw < hw;              // no early exit: the CTA meets at a barrier below
+    const int pix = live ? pix_raw : hw - 1;
     const int b = blockIdx.y;
     const int D = static_cast<int>(a.D), H = static_cast<int>(a.H), W = static_cast<int>(a.W);
     const int y = pix / static_cast<int>(a.w), x = pix % static_cast<int>(a.w);
@@ -101,8 +112,11 @@ ddim_step_kernel(const dv_ddim_step_args a) {
             v11 = fabsf(d11 - a.used[o11]) < th ? 1.f : 0.f;
         }
         m = clampf(m + bilinear_mix(ty, tx, v00, v01, v10, v11), 0.0f, 1.0f);
-        a.mask[static_cast<int64_t>(b) * hw + pix] = m;
     }
+    // every thread of the pixel has read the old mask before one of them overwrites it
+    __syncthreads();
+    if (a.mask && (a.vote || a.used) && dg == 0 && live) a.mask[static_cast<int64_t>(b) * hw + pix] = m;
+    if (!live) return;
     const bool renoise_px = (a.renoise_mode != 0) && (m == 0.0f);
 
     const float s32 = static_cast<float>(a.scale);
@@ -112,7 +126,7 @@ ddim_step_kernel(const dv_ddim_step_args a) {
     const XT *xt = static_cast<const XT *>(a.xt);
     const XT *sn = static_cast<const XT *>(a.step_noise);
 
-    for (int d = 0; d < D; ++d) {
+    for (int d = dg; d < D; d += kDdimDg) {
         const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
         const float x0 = x0_from_tap(tap, d, D, s32);
         a.x0_out[e] = x0;
@@ -226,11 +240,12 @@ extern "C" int dv_ddim_step(const dv_ddim_step_args *args, void *stream) {
         if (a.renoise_mode != 0 && !a.mask) return DV_ERR_NULL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dim3 grid(static_cast<unsigned>((a.h * a.w + 127) / 128), static_cast<unsigned>(a.B));
+    dim3 grid(static_cast<unsigned>((a.h * a.w + kDdimPx - 1) / kDdimPx), static_cast<unsigned>(a.B));
+    dim3 block(kDdimPx, kDdimDg);
     if (a.xt_is_f64 == 1)
-        ddim_step_kernel<double><<<grid, 128, 0, st>>>(a);
+        ddim_step_kernel<double><<<grid, block, 0, st>>>(a);
     else if (a.xt_is_f64 == 0)
-        ddim_step_kernel<float><<<grid, 128, 0, st>>>(a);
+        ddim_step_kernel<float><<<grid, block, 0, st>>>(a);
     else
         return DV_ERR_BAD_DTYPE;
     return finish_launch();

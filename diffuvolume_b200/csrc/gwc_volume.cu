@@ -23,106 +23,126 @@
 
 namespace dv {
 
-template <int CPG, int DC, int SQ, int NCH>
-__global__ void __launch_bounds__(SQ * NCH)
+template <int CPG, int DC, int SQ, int NCH, int MINB>
+__global__ void __launch_bounds__(SQ * NCH, MINB)
 gwc_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out,
-                  int C, int HW, int W, int D, int G, int Dpad, int Dtot, int dofs) {
+                  int C, int HW, int W, int D, int G, int Dpad, int Dtot, int dofs, int tiles_per_cta) {
     // Dtot = planes per (b,g) in `out`, dofs = slot of shift 0 (plain gwc: Dtot = D, dofs = 0;
-    // two-sided correlation volume: Dtot = 2m+1, dofs = m)
+    // two-sided correlation volume: Dtot = 2m+1, dofs = m).
+    // A CTA walks `tiles_per_cta` consecutive spans of one (b, g) plane with a 2-stage pipeline: the bulk
+    // copies of span i+1 are in flight while span i is being correlated and stored.
     static_assert(DC % 4 == 0, "DC must be a multiple of 4");
     constexpr int SPAN = SQ * 4;
     extern __shared__ __align__(16) float smem[];
-    __shared__ __align__(8) uint64_t bar;
-    float *sL = smem;               // [CPG][SPAN]
-    float *sR = smem + CPG * SPAN;  // [CPG][SPAN + Dpad]; element Dpad of a row is flat index p0
+    __shared__ __align__(8) uint64_t bar[2];
     const int rpitch = SPAN + Dpad;
+    const int stage_floats = CPG * SPAN + CPG * rpitch;  // [CPG][SPAN] ref | [CPG][SPAN + Dpad] tgt window
 
     const int b = blockIdx.z, g = blockIdx.y;
-    const int p0 = blockIdx.x * SPAN;
-    const int len = min(SPAN, HW - p0);  // multiple of 4 (HW % 4 == 0)
+    const int nspans = (HW + SPAN - 1) / SPAN;
+    const int t0 = blockIdx.x * tiles_per_cta;
+    const int nt = min(tiles_per_cta, nspans - t0);
+    const int64_t plane0 = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * CPG) * HW;
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    if (threadIdx.x < 32) {
-        const int64_t plane0 = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * CPG) * HW;
-        // The tgt window starts Dpad floats before the span; only the very first plane of the
-        // tensor can make that negative (those values are never used: x < d there).
-        int64_t roff0 = plane0 + p0 - Dpad;
+    auto issue = [&](int i) {  // called by warp 0 only
+        float *sL = smem + (i & 1) * stage_floats;
+        float *sR = sL + CPG * SPAN;  // element Dpad of a row is flat index p0
+        const int p0 = (t0 + i) * SPAN;
+        const int len = min(SPAN, HW - p0);  // multiple of 4 (HW % 4 == 0)
+        // The tgt window starts Dpad floats before the span; only the very first plane of the tensor can
+        // make that negative (those values are never used: x < d there).
+        const int64_t roff0 = plane0 + p0 - Dpad;
         const int skip0 = roff0 < 0 ? static_cast<int>(-roff0) : 0;
         if (threadIdx.x == 0) {
             const uint32_t bytes = static_cast<uint32_t>(CPG) * (2u * len + Dpad) * 4u - 4u * skip0;
-            mbar_expect_tx(&bar, bytes);
+            mbar_expect_tx(&bar[i & 1], bytes);
         }
         __syncwarp();
         for (int k = threadIdx.x; k < CPG; k += 32) {
-            bulk_g2s(sL + k * SPAN, ref + plane0 + static_cast<int64_t>(k) * HW + p0, 4u * len, &bar);
+            bulk_g2s(sL + k * SPAN, ref + plane0 + static_cast<int64_t>(k) * HW + p0, 4u * len, &bar[i & 1]);
             const int skip = k == 0 ? skip0 : 0;
             bulk_g2s(sR + k * rpitch + skip, tgt + roff0 + static_cast<int64_t>(k) * HW + skip,
-                     4u * (len + Dpad - skip), &bar);
+                     4u * (len + Dpad - skip), &bar[i & 1]);
         }
-    }
-    mbar_wait(&bar, 0);
+    };
+
+    if (threadIdx.x < 32) issue(0);
 
     const int q = threadIdx.x % SQ;
     const int ch0 = threadIdx.x / SQ;
-    const int p = p0 + 4 * q;
-    if (p >= HW) return;
-    int xs[4];
-    xs[0] = p % W;
-#pragma unroll
-    for (int i = 1; i < 4; ++i) {
-        xs[i] = xs[i - 1] + 1;
-        if (xs[i] >= W) xs[i] -= W;
-    }
     constexpr float inv = 1.0f / CPG;  // mean over the group (torch's mean multiplies by 1/n on CUDA)
 
-    for (int ch = ch0; ch * DC < D; ch += NCH) {
-        const int d0 = ch * DC;
-        float acc[DC][4];
-#pragma unroll
-        for (int j = 0; j < DC; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
+    for (int it = 0; it < nt; ++it) {
+        // stage (it+1)&1 was last read in iteration it-1; the barrier at the end of that iteration makes
+        // it safe to refill now
+        if (threadIdx.x < 32 && it + 1 < nt) issue(it + 1);
+        mbar_wait(&bar[it & 1], (it >> 1) & 1);
 
-        const float *lp = sL + 4 * q;
-        const float *rp = sR + Dpad + 4 * q - d0 - DC;  // 16-byte aligned: Dpad, d0, DC % 4 == 0
+        const float *sL = smem + (it & 1) * stage_floats;
+        const float *sR = sL + CPG * SPAN;
+        const int p0 = (t0 + it) * SPAN;
+        const int p = p0 + 4 * q;
+        if (p < HW) {
+            int xs[4];
+            xs[0] = p % W;
 #pragma unroll
-        for (int k = 0; k < CPG; ++k) {
-            const float4 l4 = *reinterpret_cast<const float4 *>(lp + k * SPAN);
-            const float l[4] = {l4.x, l4.y, l4.z, l4.w};
-            float rw[DC + 4];
-#pragma unroll
-            for (int m = 0; m < DC / 4 + 1; ++m) {
-                const float4 r4 = *reinterpret_cast<const float4 *>(rp + k * rpitch + 4 * m);
-                rw[4 * m + 0] = r4.x;
-                rw[4 * m + 1] = r4.y;
-                rw[4 * m + 2] = r4.z;
-                rw[4 * m + 3] = r4.w;
+            for (int i = 1; i < 4; ++i) {
+                xs[i] = xs[i - 1] + 1;
+                if (xs[i] >= W) xs[i] -= W;
             }
-            // out(d0+j, x+i) += ref(x+i) * tgt(x+i-d0-j);  window index = DC + i - j
+            for (int ch = ch0; ch * DC < D; ch += NCH) {
+                const int d0 = ch * DC;
+                float acc[DC][4];
 #pragma unroll
-            for (int j = 0; j < DC; ++j)
+                for (int j = 0; j < DC; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(l[i], rw[DC + i - j], acc[j][i]);
-        }
+                    for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
 
-        float *op = out + ((static_cast<int64_t>(b) * G + g) * Dtot + dofs + d0) * HW + p;
+                const float *lp = sL + 4 * q;
+                const float *rp = sR + Dpad + 4 * q - d0 - DC;  // 16-byte aligned: Dpad, d0, DC % 4 == 0
 #pragma unroll
-        for (int j = 0; j < DC; ++j) {
-            const int d = d0 + j;
-            if (d < D) {
-                float4 v;
-                v.x = xs[0] >= d ? acc[j][0] * inv : 0.0f;
-                v.y = xs[1] >= d ? acc[j][1] * inv : 0.0f;
-                v.z = xs[2] >= d ? acc[j][2] * inv : 0.0f;
-                v.w = xs[3] >= d ? acc[j][3] * inv : 0.0f;
-                stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(j) * HW), v);
+                for (int k = 0; k < CPG; ++k) {
+                    const float4 l4 = *reinterpret_cast<const float4 *>(lp + k * SPAN);
+                    const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+                    float rw[DC + 4];
+#pragma unroll
+                    for (int m = 0; m < DC / 4 + 1; ++m) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(rp + k * rpitch + 4 * m);
+                        rw[4 * m + 0] = r4.x;
+                        rw[4 * m + 1] = r4.y;
+                        rw[4 * m + 2] = r4.z;
+                        rw[4 * m + 3] = r4.w;
+                    }
+                    // out(d0+j, x+i) += ref(x+i) * tgt(x+i-d0-j);  window index = DC + i - j
+#pragma unroll
+                    for (int j = 0; j < DC; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(l[i], rw[DC + i - j], acc[j][i]);
+                }
+
+                float *op = out + ((static_cast<int64_t>(b) * G + g) * Dtot + dofs + d0) * HW + p;
+#pragma unroll
+                for (int j = 0; j < DC; ++j) {
+                    const int d = d0 + j;
+                    if (d < D) {
+                        float4 v;
+                        v.x = xs[0] >= d ? acc[j][0] * inv : 0.0f;
+                        v.y = xs[1] >= d ? acc[j][1] * inv : 0.0f;
+                        v.z = xs[2] >= d ? acc[j][2] * inv : 0.0f;
+                        v.w = xs[3] >= d ? acc[j][3] * inv : 0.0f;
+                        stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(j) * HW), v);
+                    }
+                }
             }
         }
+        if (it + 1 < nt) __syncthreads();
     }
 }
 
@@ -184,20 +204,25 @@ __global__ void corr_negative_kernel(const float *__restrict__ ref, const float 
     }
 }
 
-template <int CPG, int DC, int SQ, int NCH>
+template <int CPG, int DC, int SQ, int NCH, int MINB>
 static int launch_gwc(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int G,
                       int Dtot, int dofs, cudaStream_t st) {
     constexpr int SPAN = SQ * 4;
     const int Dpad = ((D + DC - 1) / DC) * DC;
-    const size_t smem = sizeof(float) * (static_cast<size_t>(CPG) * SPAN + static_cast<size_t>(CPG) * (SPAN + Dpad));
+    const int nspans = (HW + SPAN - 1) / SPAN;
+    // spans per CTA (2-stage pipeline inside the CTA); keep >= ~4 CTAs per SM slot for balance
+    int tpc = tune_variant("DV_GWC_TPC", 8);
+    while (tpc > 1 && static_cast<int64_t>((nspans + tpc - 1) / tpc) * G * B < 4LL * kNumSMs * MINB) tpc /= 2;
+    const int stages = tpc > 1 ? 2 : 1;
+    const size_t smem = sizeof(float) * stages * (static_cast<size_t>(CPG) * SPAN + static_cast<size_t>(CPG) * (SPAN + Dpad));
     if (smem > 200 * 1024) return DV_ERR_UNSUPPORTED;
-    auto kern = gwc_volume_kernel<CPG, DC, SQ, NCH>;
+    auto kern = gwc_volume_kernel<CPG, DC, SQ, NCH, MINB>;
     if (smem > 48 * 1024) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
             return DV_ERR_LAUNCH;
     }
-    dim3 grid((HW + SPAN - 1) / SPAN, G, B);
-    kern<<<grid, SQ * NCH, smem, st>>>(ref, tgt, out, C, HW, W, D, G, Dpad, Dtot, dofs);
+    dim3 grid((nspans + tpc - 1) / tpc, G, B);
+    kern<<<grid, SQ * NCH, smem, st>>>(ref, tgt, out, C, HW, W, D, G, Dpad, Dtot, dofs, tpc);
     return finish_launch();
 }
 
@@ -206,9 +231,13 @@ static int dispatch_gwc(const float *ref, const float *tgt, float *out, int B, i
                         int Dtot, int dofs, cudaStream_t st) {
     constexpr int DC = 12, SQ = 64;
     const int nch = (D + DC - 1) / DC;
-    if (nch >= 4) return launch_gwc<CPG, DC, SQ, 4>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
-    if (nch >= 2) return launch_gwc<CPG, DC, SQ, 2>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
-    return launch_gwc<CPG, DC, SQ, 1>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+    if (nch >= 4) {
+        if (tune_variant("DV_GWC_MINB", 2) == 2)
+            return launch_gwc<CPG, DC, SQ, 4, 2>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+        return launch_gwc<CPG, DC, SQ, 4, 3>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+    }
+    if (nch >= 2) return launch_gwc<CPG, DC, SQ, 2, 4>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+    return launch_gwc<CPG, DC, SQ, 1, 8>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
 }
 
 static int gwc_volume_impl(const float *ref, const float *tgt, float *out, int64_t B, int64_t C, int64_t H, int64_t W,

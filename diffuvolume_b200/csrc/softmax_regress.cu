@@ -19,9 +19,7 @@
 
 namespace dv {
 
-constexpr int kSrSlices = 8;
 constexpr int kSrLanes = 32;
-constexpr int kSrThreads = kSrSlices * kSrLanes;
 
 template <int V>
 struct alignas(V * 4) Vec {
@@ -34,6 +32,10 @@ __device__ __forceinline__ Vec<V> load_vec(const float *p) {
     if constexpr (V == 4) {
         const float4 t = ldg_stream(reinterpret_cast<const float4 *>(p));
         r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else if constexpr (V == 2) {
+        float2 t;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "l"(p));
+        r.v[0] = t.x; r.v[1] = t.y;
     } else {
         r.v[0] = __ldg(p);
     }
@@ -43,17 +45,28 @@ template <int V>
 __device__ __forceinline__ void store_vec(float *p, const Vec<V> &r) {
     if constexpr (V == 4)
         *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    else if constexpr (V == 2)
+        *reinterpret_cast<float2 *>(p) = make_float2(r.v[0], r.v[1]);
     else
         *p = r.v[0];
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    // volatile: under register pressure ptxas otherwise REMATERIALISES the exponentials in the uncertainty
+    // pass instead of keeping them (2x MUFU + FFMA, seen in the ncu source page of round 1)
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // one MUFU.EX2; exp2(-inf) = +0
+    return y;
+}
+
 // cost [B,D,HW];  pixel-vector index pv in [0, HW/V)
-template <int DPT, int V>
-__global__ void __launch_bounds__(kSrThreads)
+template <int DPT, int V, int SL, int MINB, bool FULLD>
+__global__ void __launch_bounds__(SL * kSrLanes, MINB)
 softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__restrict__ disp_out,
                        float *__restrict__ prob_out, const float *__restrict__ used, float *__restrict__ unc_out,
                        float *__restrict__ vote_out, float thr_dif, float thr_unc, float *__restrict__ ens_acc,
                        float ens_coef, int ens_init) {
+    constexpr int kSrSlices = SL;   // disparity slices per CTA; thread (lane, slice) owns d = j*SL + slice
     __shared__ Vec<V> red[3][kSrSlices][kSrLanes];
     const int lane = threadIdx.x % kSrLanes;
     const int slice = threadIdx.x / kSrLanes;
@@ -64,14 +77,18 @@ softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__r
     constexpr float kLog2e = 1.4426950408889634f;
 
     Vec<V> x[DPT];
+    {
+        const float *lp = cp + static_cast<int64_t>(slice) * HW;
+        const int64_t step = static_cast<int64_t>(kSrSlices) * HW;
 #pragma unroll
-    for (int j = 0; j < DPT; ++j) {
-        const int d = j * kSrSlices + slice;
-        if (live && d < D) {
-            x[j] = load_vec<V>(cp + static_cast<int64_t>(d) * HW);
-        } else {
+        for (int j = 0; j < DPT; ++j, lp += step) {
+            const bool ok = FULLD ? live : (live && (j * kSrSlices + slice < D));   // FULLD: D == SL * DPT
+            if (ok) {
+                x[j] = load_vec<V>(lp);
+            } else {
 #pragma unroll
-            for (int i = 0; i < V; ++i) x[j].v[i] = -INFINITY;
+                for (int i = 0; i < V; ++i) x[j].v[i] = -INFINITY;
+            }
         }
     }
     // ---- max over D
@@ -103,7 +120,7 @@ softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__r
         const float df = static_cast<float>(j * kSrSlices + slice);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const float e = exp2f(fmaf(x[j].v[i], kLog2e, -mL.v[i]));  // exp2(-inf) = 0 for d >= D
+            const float e = fast_exp2(fmaf(x[j].v[i], kLog2e, -mL.v[i]));  // exp2(-inf) = 0 for d >= D
             x[j].v[i] = e;
             S.v[i] += e;
             Wd.v[i] = fmaf(df, e, Wd.v[i]);
@@ -137,7 +154,7 @@ softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__r
 #pragma unroll
         for (int j = 0; j < DPT; ++j) {
             const int d = j * kSrSlices + slice;
-            if (d < D) {
+            if (FULLD || d < D) {
                 Vec<V> p;
 #pragma unroll
                 for (int i = 0; i < V; ++i) p.v[i] = x[j].v[i] * rS.v[i];
@@ -254,14 +271,56 @@ disparity_regression_kernel(const float *__restrict__ x, float *__restrict__ out
     store_vec<V>(out + static_cast<int64_t>(b) * HW + pv * V, acc);
 }
 
-template <int DPT, int V>
+// a11 when the disparity is NOT the regression of `prob` (PCWNet: the refined disparity is compared with
+// the pre-refinement distribution, pwcnet_ddim.py:553-570): unc = sum_d |disp - d| * prob[d].
+template <int V>
+__global__ void __launch_bounds__(256)
+uncertainty_vote_kernel(const float *__restrict__ prob, const float *__restrict__ disp, const float *__restrict__ used,
+                        float *__restrict__ unc_out, float *__restrict__ vote_out, float thr_dif, float thr_unc, int D,
+                        int HW) {
+    const int b = blockIdx.y;
+    const int64_t pv = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (pv * V >= HW) return;
+    const int64_t o = static_cast<int64_t>(b) * HW + pv * V;
+    const float *pp = prob + static_cast<int64_t>(b) * D * HW + pv * V;
+    const Vec<V> dsp = load_vec<V>(disp + o);
+    Vec<V> U;
+#pragma unroll
+    for (int i = 0; i < V; ++i) U.v[i] = 0.0f;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) {
+        const Vec<V> t = load_vec<V>(pp + static_cast<int64_t>(d) * HW);
+#pragma unroll
+        for (int i = 0; i < V; ++i) U.v[i] = fmaf(fabsf(dsp.v[i] - static_cast<float>(d)), t.v[i], U.v[i]);
+    }
+    if (unc_out) store_vec<V>(unc_out + o, U);
+    if (vote_out) {
+        Vec<V> vt;
+        if (used) {
+            const Vec<V> u0 = load_vec<V>(used + o);
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                vt.v[i] = (fabsf(dsp.v[i] - u0.v[i]) < thr_dif && U.v[i] < thr_unc) ? 1.0f : 0.0f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) vt.v[i] = U.v[i] < thr_unc ? 1.0f : 0.0f;
+        }
+        store_vec<V>(vote_out + o, vt);
+    }
+}
+
+template <int DPT, int V, int SL, int MINB>
 static void launch_sr(const float *cost, int B, int D, int HW, float *disp_out, float *prob_out, const float *used,
                       float *unc_out, float *vote_out, float thr_dif, float thr_unc, float *ens_acc, float ens_coef,
                       int ens_init, cudaStream_t st) {
     const int pvs = (HW + V - 1) / V;
     dim3 grid((pvs + kSrLanes - 1) / kSrLanes, B);
-    softmax_regress_kernel<DPT, V><<<grid, kSrThreads, 0, st>>>(cost, D, HW, disp_out, prob_out, used, unc_out, vote_out,
-                                                               thr_dif, thr_unc, ens_acc, ens_coef, ens_init);
+    if (D == SL * DPT)
+        softmax_regress_kernel<DPT, V, SL, MINB, true><<<grid, SL * kSrLanes, 0, st>>>(
+            cost, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init);
+    else
+        softmax_regress_kernel<DPT, V, SL, MINB, false><<<grid, SL * kSrLanes, 0, st>>>(
+            cost, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init);
 }
 
 }  // namespace dv
@@ -277,25 +336,31 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
     const int64_t HW = H * W;
     if (HW > INT32_MAX || B > 65535 || D > INT32_MAX) return DV_ERR_BAD_SHAPE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool vec = (HW % 4 == 0) && aligned16(cost) && (!disp_out || aligned16(disp_out)) &&
-                     (!prob_out || aligned16(prob_out)) && (!used || aligned16(used)) &&
-                     (!unc_out || aligned16(unc_out)) && (!vote_out || aligned16(vote_out)) &&
-                     (!ens_acc || aligned16(ens_acc));
-#define DV_SR(DPT)                                                                                                    \
-    do {                                                                                                              \
-        if (vec)                                                                                                      \
-            launch_sr<DPT, 4>(cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, \
-                              ens_coef, ens_init, st);                                                                \
-        else                                                                                                          \
-            launch_sr<DPT, 1>(cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, \
-                              ens_coef, ens_init, st);                                                                \
-    } while (0)
+    auto all_aligned = [&](uintptr_t mask) {
+        auto ok = [mask](const void *p) { return !p || (reinterpret_cast<uintptr_t>(p) & mask) == 0; };
+        return ok(cost) && ok(disp_out) && ok(prob_out) && ok(used) && ok(unc_out) && ok(vote_out) && ok(ens_acc);
+    };
+    const bool vec4 = (HW % 4 == 0) && all_aligned(15);
+    const bool vec2 = (HW % 2 == 0) && all_aligned(7);
+    // D <= 8*DPT.  Tuning switch DV_SR_VARIANT (scripts/tune_kernels.py) selects the D = 192 layout.
+    const int variant = tune_variant("DV_SR_VARIANT", 4);
+#define DV_SR_ARGS cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, st
     if (D <= 48) {
-        DV_SR(6);
+        if (vec4) launch_sr<6, 4, 8, 4>(DV_SR_ARGS);
+        else if (vec2) launch_sr<6, 2, 8, 4>(DV_SR_ARGS);
+        else launch_sr<6, 1, 8, 4>(DV_SR_ARGS);
     } else if (D <= 96) {
-        DV_SR(12);
+        if (vec4) launch_sr<12, 4, 8, 2>(DV_SR_ARGS);
+        else if (vec2) launch_sr<12, 2, 8, 3>(DV_SR_ARGS);
+        else launch_sr<12, 1, 8, 4>(DV_SR_ARGS);
     } else if (D <= 192) {
-        DV_SR(24);
+        if (vec4 && variant == 0) launch_sr<24, 4, 8, 1>(DV_SR_ARGS);
+        else if (vec4 && variant == 1) launch_sr<12, 4, 16, 1>(DV_SR_ARGS);
+        else if (vec4 && variant == 5) launch_sr<12, 4, 16, 2>(DV_SR_ARGS);
+        else if (vec2 && variant == 2) launch_sr<24, 2, 8, 2>(DV_SR_ARGS);
+        else if (vec2 && variant == 3) launch_sr<12, 2, 16, 2>(DV_SR_ARGS);
+        else if (vec2) launch_sr<24, 2, 8, 3>(DV_SR_ARGS);   // measured best of the six layouts (r01 tuning)
+        else launch_sr<24, 1, 8, 4>(DV_SR_ARGS);
     } else {
         const int64_t total = B * HW;
         const int64_t blocks = (total + 255) / 256;
@@ -304,6 +369,7 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
                                                              prob_out, used, unc_out, vote_out, thr_dif, thr_unc,
                                                              ens_acc, ens_coef, ens_init, total);
     }
+#undef DV_SR_ARGS
 #undef DV_SR
     return finish_launch();
 }
@@ -322,6 +388,29 @@ extern "C" int dv_disparity_regression_f32(const float *x, float *out, int64_t B
     } else {
         dim3 grid(static_cast<unsigned>((HW + 255) / 256), static_cast<unsigned>(B));
         disparity_regression_kernel<1><<<grid, 256, 0, st>>>(x, out, static_cast<int>(D), static_cast<int>(HW));
+    }
+    return finish_launch();
+}
+
+extern "C" int dv_uncertainty_vote_f32(const float *prob, const float *disp, const float *used, int64_t B, int64_t D,
+                                       int64_t H, int64_t W, float thr_dif, float thr_unc, float *unc_out,
+                                       float *vote_out, void *stream) {
+    using namespace dv;
+    if (!prob || !disp) return DV_ERR_NULL;
+    if (!unc_out && !vote_out) return DV_ERR_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535) return DV_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto ok16 = [](const void *p) { return !p || aligned16(p); };
+    if ((HW % 4 == 0) && ok16(prob) && ok16(disp) && ok16(used) && ok16(unc_out) && ok16(vote_out)) {
+        dim3 grid(static_cast<unsigned>((HW / 4 + 255) / 256), static_cast<unsigned>(B));
+        uncertainty_vote_kernel<4><<<grid, 256, 0, st>>>(prob, disp, used, unc_out, vote_out, thr_dif, thr_unc,
+                                                         static_cast<int>(D), static_cast<int>(HW));
+    } else {
+        dim3 grid(static_cast<unsigned>((HW + 255) / 256), static_cast<unsigned>(B));
+        uncertainty_vote_kernel<1><<<grid, 256, 0, st>>>(prob, disp, used, unc_out, vote_out, thr_dif, thr_unc,
+                                                         static_cast<int>(D), static_cast<int>(HW));
     }
     return finish_launch();
 }

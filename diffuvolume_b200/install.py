@@ -1,0 +1,103 @@
+"""Bind the sm_100a ops into an imported copy of the reference so its scripts run unchanged.
+
+The reference has no plugin/operator registry: consumers pull the hot-path functions in with
+star-imports (`from models.submodule import *`, SceneFlow/models/acv_ddim.py:7; KITTI12/models/pwcnet_ddim.py:8;
+`from core.submodule import *` + `from core.geometry_ddim import Combined_Geo_Encoding_Volume`,
+KITTI15/core/igev_stereo_ddim.py:7-8).  A star-import copies bindings, so replacing the function in
+`models.submodule` after `models.acv_ddim` was imported changes nothing; `install()` therefore
+rebinds the names on every consumer module that is already in sys.modules (tier 1), and rebinds the
+sampler methods on the reference's model classes (tier 2) so that the unnamed ops between the named
+functions (softmax, the filter multiply, the DDIM arithmetic) are fused too.
+
+    import models                      # the reference, cwd = SceneFlow/
+    import diffuvolume_b200.install as dvi
+    dvi.install("sceneflow")           # or "kitti12", "kitti15"
+    ...                                # run test_sceneflow_ddim.py's code path unchanged
+    dvi.uninstall()
+
+Nothing is added to any nn.Module (no parameters, no buffers): checkpoints load unchanged.
+"""
+from __future__ import annotations
+
+import sys
+from typing import Dict, List, Tuple
+
+from . import kitti12, kitti15, sampler, sceneflow
+
+_TIER1 = {
+    "sceneflow": (sceneflow, ["models.submodule", "models.acv", "models.acv_ddim", "models.temp", "models"]),
+    "kitti12": (kitti12, ["models.submodule", "models.pwcnet", "models.pwcnet_ddim", "models"]),
+    "kitti15": (kitti15, ["core.submodule", "core.geometry", "core.geometry_ddim", "core.igev_stereo",
+                          "core.igev_stereo_ddim", "core.extractor"]),
+}
+
+_TIER2 = {
+    "sceneflow": [("models.acv_ddim", "ACVNet_DDIM", {
+        "q_sample": sampler.q_sample,
+        "predict_noise_from_start": sampler.predict_noise_from_start,
+        "model_predictions": sampler.acv_model_predictions,
+        "ddim_sample": sampler.acv_ddim_sample,
+    })],
+    "kitti12": [("models.pwcnet_ddim", "PWCNet_ddim", {
+        "q_sample": sampler.q_sample,
+        "predict_noise_from_start": sampler.predict_noise_from_start,
+        "ddim_sample": sampler.pcw_ddim_sample,
+    })],
+    "kitti15": [("core.igev_stereo_ddim", "IGEVStereo_ddim", {
+        "q_sample": sampler.q_sample,
+        "predict_noise_from_start": sampler.predict_noise_from_start,
+    })],
+}
+
+_undo: List[Tuple[object, str, object, bool]] = []   # (owner, name, original, existed)
+
+
+def _bind(owner, name, value):
+    existed = hasattr(owner, name) and (name in vars(owner))
+    _undo.append((owner, name, getattr(owner, name, None), existed))
+    setattr(owner, name, value)
+
+
+def install(project: str, tier2: bool = True, modules: Dict[str, object] = None) -> List[str]:
+    """Rebind the hot-path names of `project` ('sceneflow' | 'kitti12' | 'kitti15').  `modules` overrides
+    sys.modules (used by the tests with stand-in modules).  Returns the list of 'module.name' rebound."""
+    if project not in _TIER1:
+        raise ValueError(f"unknown project {project!r}; expected one of {sorted(_TIER1)}")
+    mods = sys.modules if modules is None else modules
+    mirror, consumers = _TIER1[project]
+    done = []
+    for mname in consumers:
+        mod = mods.get(mname)
+        if mod is None:
+            continue
+        for name in mirror.__all__:
+            if hasattr(mod, name):
+                _bind(mod, name, getattr(mirror, name))
+                done.append(f"{mname}.{name}")
+    if tier2:
+        for mname, cname, methods in _TIER2[project]:
+            mod = mods.get(mname)
+            cls = getattr(mod, cname, None) if mod is not None else None
+            if cls is None:
+                continue
+            for name, fn in methods.items():
+                if hasattr(cls, name):
+                    _bind(cls, name, fn)
+                    done.append(f"{mname}.{cname}.{name}")
+    return done
+
+
+def uninstall() -> int:
+    """Restore everything install() rebound (LIFO).  Returns the number of bindings restored."""
+    n = 0
+    while _undo:
+        owner, name, orig, existed = _undo.pop()
+        if existed:
+            setattr(owner, name, orig)
+        else:
+            try:
+                delattr(owner, name)
+            except AttributeError:
+                pass
+        n += 1
+    return n

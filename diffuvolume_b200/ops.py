@@ -79,7 +79,8 @@ def groupwise_correlation(fea1: torch.Tensor, fea2: torch.Tensor, num_groups: in
     return out
 
 
-def gwc_volume(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, num_groups: int) -> torch.Tensor:
+def gwc_volume(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, num_groups: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a2 — build_gwc_volume, SceneFlow/models/submodule.py:228-238 -> [B,G,maxdisp,H,W]."""
     B, Cc, H, W = ref.shape
     assert Cc % num_groups == 0
@@ -87,7 +88,10 @@ def gwc_volume(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, num_groups: i
     ref, tgt = _f32c(ref, "refimg_fea"), _f32c(tgt, "targetimg_fea")
     if tgt.shape != ref.shape:
         raise RuntimeError(f"The size of tensor a {tuple(ref.shape)} must match the size of tensor b {tuple(tgt.shape)}")
-    out = torch.empty((B, num_groups, maxdisp, H, W), dtype=torch.float32, device=ref.device)
+    if out is None:
+        out = torch.empty((B, num_groups, maxdisp, H, W), dtype=torch.float32, device=ref.device)
+    else:
+        assert out.shape == (B, num_groups, maxdisp, H, W) and out.dtype == torch.float32 and out.is_contiguous()
     if out.numel() == 0:
         return out
     with torch.cuda.device(ref.device):
@@ -210,6 +214,25 @@ def softmax_regress(cost: torch.Tensor, *, return_prob: bool = False, used: Opti
                                                 thr_unc, _ptr(ens_acc), float(ens_coef), int(ens_init),
                                                 _stream(cost)), "dv_softmax_regress_f32")
     return res
+
+
+def uncertainty_vote(disp: torch.Tensor, prob: torch.Tensor, used: Optional[torch.Tensor], thr_dif: float,
+                     thr_unc: float, return_unc: bool = False):
+    """a11 — sum_d |disp - d| * prob[d] and the renewal vote for a disparity that is not the regression of
+    `prob` (pwcnet_ddim.py:553-570).  Returns vote [B,H,W] (and unc when return_unc)."""
+    B, D, H, W = prob.shape
+    _need_cuda(disp, prob, used)
+    prob = _f32c(prob, "prob")
+    disp = _f32c(disp.reshape(B, H, W), "disp")
+    if used is not None:
+        used = _f32c(used.reshape(B, H, W), "used")
+    vote = torch.empty((B, H, W), dtype=torch.float32, device=prob.device)
+    unc = torch.empty((B, H, W), dtype=torch.float32, device=prob.device) if return_unc else None
+    with torch.cuda.device(prob.device):
+        check(_lib.lib().dv_uncertainty_vote_f32(_ptr(prob), _ptr(disp), _ptr(used), B, D, H, W, float(thr_dif),
+                                                 float(thr_unc), _ptr(unc), _ptr(vote), _stream(prob)),
+              "dv_uncertainty_vote_f32")
+    return (vote, unc) if return_unc else vote
 
 
 def disparity_regression(x: torch.Tensor, maxdisp: int, keepdim: bool = False) -> torch.Tensor:

@@ -1,0 +1,173 @@
+"""The ACVNet+DiffuVolume hot path as one device-resident kernel sequence.
+
+This is the unit BASELINE.json's metric counts ("volume+DDIM-filter pairs/s"): for a batch of
+stereo pairs, 1x group-wise correlation volume, 1x concat volume with the ACV attention weights
+fused, then T DDIM steps of {filter multiply, softmax + disparity regression + uncertainty + renewal
+vote + ensemble accumulate, fused x_start / pred_noise / DDIM update / re-noise}, i.e. everything
+ACVNet_DDIM.forward (eval) + ddim_sample (SceneFlow/models/acv_ddim.py:372-422, :298-370) do
+outside the 2-D/3-D convolutions.  The convolutions stay on PyTorch and are not part of this
+path: their outputs (features, attention logits, per-step cost logits) are inputs here.
+
+Every op is a hand-written sm_100a kernel reached through the C-ABI (diffuvolume_b200.ops).
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def cosine_alphas_cumprod(timesteps: int = 1000, s: float = 0.008) -> np.ndarray:
+    """Host-side float64 cosine schedule (cosine_beta_schedule, SceneFlow/models/acv_ddim.py:113-119,
+    followed by the cumprod of :134-135).  Host scalars only — nothing here touches the device."""
+    x = np.linspace(0, timesteps, timesteps + 1, dtype=np.float64)
+    ac = np.cos(((x / timesteps) + s) / (1 + s) * math.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = np.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+    return np.cumprod(1.0 - betas)
+
+
+def ddim_time_pairs(num_timesteps: int, sampling_timesteps: int) -> List[Tuple[int, int]]:
+    """acv_ddim.py:306-308 — torch.linspace(-1, T-1, S+1) (float32) truncated to int, reversed, paired."""
+    times = torch.linspace(-1, num_timesteps - 1, steps=sampling_timesteps + 1)
+    times = list(reversed(times.int().tolist()))
+    return list(zip(times[:-1], times[1:]))
+
+
+@dataclass
+class DdimSchedule:
+    """The float64 constants the sampler needs, as host scalars."""
+    num_timesteps: int = 1000
+    sampling_timesteps: int = 5
+    eta: float = 1.0
+    scale: float = 1.0
+    alphas_cumprod: np.ndarray = field(default=None, repr=False)
+
+    def __post_init__(self):
+        if self.alphas_cumprod is None:
+            self.alphas_cumprod = cosine_alphas_cumprod(self.num_timesteps)
+        self.alphas_cumprod = np.asarray(self.alphas_cumprod, dtype=np.float64)
+
+    def time_pairs(self):
+        return ddim_time_pairs(self.num_timesteps, self.sampling_timesteps)
+
+    def sqrt_recip(self, t):
+        return float(np.sqrt(1.0 / self.alphas_cumprod[t]))
+
+    def sqrt_recipm1(self, t):
+        return float(np.sqrt(1.0 / self.alphas_cumprod[t] - 1))
+
+    def sqrt_ac(self, t):
+        return float(np.sqrt(self.alphas_cumprod[t]))
+
+    def sqrt_1m_ac(self, t):
+        return float(np.sqrt(1.0 - self.alphas_cumprod[t]))
+
+    def update_coefficients(self, t, t_next):
+        """acv_ddim.py:347-351 -> (sqrt(alpha_next), c, sigma)."""
+        a, an = self.alphas_cumprod[t], self.alphas_cumprod[t_next]
+        sigma = self.eta * np.sqrt((1 - a / an) * (1 - an) / (1 - a))
+        c = np.sqrt(1 - an - sigma ** 2)
+        return float(np.sqrt(an)), float(c), float(sigma)
+
+
+ACV_ENSEMBLE = (0.5, 0.0, 0.0, 0.0, 0.2, 0.3)   # acv_ddim.py:367
+
+
+class AcvHotPath:
+    """Runs the hot path for a batch on one device.
+
+    filter_mode:
+      'regenerate' — each DDIM step re-produces the filtered volume straight from the 1/4-res concat
+                     features + attention logits + x_t (reads 21 MB, writes 398 MB per pair and step);
+      'volume'     — each step multiplies the materialised ac_volume (reads 404 MB, writes 398 MB):
+                     the reference's own op boundary (acv_ddim.py:260).
+    Both produce bit-identical volumes (same roundings in the same order).
+    """
+
+    def __init__(self, schedule: Optional[DdimSchedule] = None, num_groups: int = 40, maxdisp: int = 192,
+                 filter_mode: str = "regenerate", ensemble: Sequence[float] = ACV_ENSEMBLE,
+                 thr_dif: float = 1.0, thr_unc: float = 3.0):
+        assert filter_mode in ("regenerate", "volume")
+        self.sched = schedule or DdimSchedule()
+        self.G = num_groups
+        self.maxdisp = maxdisp
+        self.D = maxdisp // 4
+        self.filter_mode = filter_mode
+        self.cof = tuple(ensemble)
+        self.thr = (thr_dif, thr_unc)
+        self._buf: Dict[str, torch.Tensor] = {}
+        assert len(self.cof) == self.sched.sampling_timesteps + 1
+
+    def _out(self, name, shape, device):
+        t = self._buf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.device != device:
+            t = torch.empty(shape, dtype=torch.float32, device=device)
+            self._buf[name] = t
+        return t
+
+    def __call__(self, feat_l, feat_r, cfeat_l, cfeat_r, att_logits, costs: Sequence[torch.Tensor], used, disp_q,
+                 shifts: Sequence[torch.Tensor], step_noises: Sequence[torch.Tensor],
+                 renoises: Sequence[torch.Tensor], keep_volumes: bool = False, timer=None):
+        """All arguments are device tensors:
+        feat_* [B,C,h,w] gwc features; cfeat_* [B,Cc,h,w] concat features; att_logits [B,1,D,h,w];
+        costs[i] [B,maxdisp,H,W] logits of step i (len T, or len 1 to reuse one buffer), or a callable
+        i -> tensor invoked when step i needs its logits (e.g. to stage them from the host);
+        used [B,H,W] initial disparity; disp_q [B,h,w] its quarter-res version (/4);
+        shifts[i] [B,D] DynamicHead shift at step i; step_noises[i] / renoises[i] the injected
+        randn_like / rand_like tensors of step i (i < T-1).  `timer(name)` may return a context manager
+        wrapped around each kernel category (bench.py uses CUDA events).  Returns dict(pred, mask, x_last)."""
+        tm = timer if timer is not None else (lambda name: contextlib.nullcontext())
+        dev = feat_l.device
+        B, _, h, w = feat_l.shape
+        D, sched = self.D, self.sched
+        Cc = cfeat_l.shape[1]
+        H, W = used.shape[-2:]
+        with tm("gwc_volume"):
+            gwc = ops.gwc_volume(feat_l, feat_r, D, self.G, out=self._out("gwc", (B, self.G, D, h, w), dev))
+        with tm("concat_acv"):
+            ac = ops.concat_volume(cfeat_l, cfeat_r, D, mask_left=False, att_logits=att_logits,
+                                   out=self._out("ac", (B, 2 * Cc, D, h, w), dev))
+        img = ops.xstart_from_disp(disp_q, D, sched.scale)
+        ens = ops.ensemble([used], [self.cof[0]])
+        mask = torch.zeros((B, h, w), dtype=torch.float32, device=dev)
+        vol_f = self._out("vol_f", (B, 2 * Cc, D, h, w), dev)
+        pairs = sched.time_pairs()
+        for i, (t, t_next) in enumerate(pairs):
+            shift = shifts[i]
+            with tm("filter"):
+                if self.filter_mode == "regenerate":
+                    ops.concat_volume(cfeat_l, cfeat_r, D, mask_left=False, att_logits=att_logits, xt=img,
+                                      shift=shift, scale=sched.scale, out=vol_f)
+                else:
+                    ops.volume_filter(ac, img, shift, sched.scale, out=vol_f)
+            # (3-D conv aggregation of vol_f happens here in the full network — out of scope)
+            cost = costs(i) if callable(costs) else costs[i if len(costs) > 1 else 0]
+            with tm("softmax_regress"):
+                r = ops.softmax_regress(cost, used=used, vote_thresholds=self.thr, ens_acc=ens,
+                                        ens_coef=self.cof[i + 1])
+            last = t_next < 0
+            kw = {}
+            if not last:
+                san, c, sigma = sched.update_coefficients(t, t_next)
+                kw = dict(sqrt_alpha_next=san, c=c, sigma=sigma, step_noise=step_noises[i], renoise=renoises[i])
+            with tm("ddim_step"):
+                st = ops.ddim_step(disp=r["disp"], xt=img, shift=shift, scale=sched.scale,
+                                   sqrt_recip=sched.sqrt_recip(t), sqrt_recipm1=sched.sqrt_recipm1(t),
+                                   last_step=last, disp_clamp_hi=float(self.maxdisp - 1), vote=r["vote"], mask=mask,
+                                   **kw)
+            img = st["x_next"]
+        out = {"pred": ens, "mask": mask, "x_last": img}
+        if keep_volumes:
+            out.update(gwc=gwc, ac=ac, vol_f=vol_f)
+        return out
+
+    def launches_per_call(self) -> int:
+        T = self.sched.sampling_timesteps
+        return 4 + 3 * T

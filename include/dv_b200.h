@@ -111,6 +111,13 @@ int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, int64_t H, i
                            float *ens_acc, float ens_coef, int ens_init,
                            void *stream);
 
+/* ---- a11 alone: uncertainty + renewal vote of a disparity map against a given probability volume
+ *          (KITTI12/models/pwcnet_ddim.py:553-570 — the REFINED disparity vs the pre-refinement softmax)
+ * unc[b,p] = sum_d |disp[b,p] - d| * prob[b,d,p];  vote = (|disp-used| < thr_dif  [if used]) && unc < thr_unc  */
+int dv_uncertainty_vote_f32(const float *prob, const float *disp, const float *used,
+                            int64_t B, int64_t D, int64_t H, int64_t W, float thr_dif, float thr_unc,
+                            float *unc_out, float *vote_out, void *stream);
+
 /* ---- a6 alone: disparity_regression on an already-normalised volume
  *          (SceneFlow/models/submodule.py:173-177)  out[b,p] = sum_d d * x[b,d,p]              */
 int dv_disparity_regression_f32(const float *x, float *out,

@@ -1,0 +1,354 @@
+"""Parity of the CUDA path (through the C-ABI, via diffuvolume_b200.ops) against the oracle and the
+reference-minted golden fixtures.  Runs on the B200 box: `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star): volumes max|a-b|/max|ref| <= 1e-4 in fp32 (we hold 1e-5),
+copies and zero regions bit-exact, disparities within 0.01 px (we hold 1e-3).
+"""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from conftest import rel_max_err
+from golden.make_golden import CONCAT_CASES, GWC_CASES, trace_inputs
+from oracle import dv_oracle as O
+
+pytestmark = pytest.mark.gpu
+VOL_TOL = 1e-5
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from diffuvolume_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------------------------------------
+# a1 / a2
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", list(GWC_CASES))
+def test_gwc_volume_golden(ops, golden, case):
+    B, C, G, D, H, W, seed = GWC_CASES[case]
+    ref, tgt = synth.normal((B, C, H, W), seed), synth.normal((B, C, H, W), seed + 1000)
+    got = host(ops.gwc_volume(cu(ref), cu(tgt), D, G))
+    want = golden[f"sf.gwc.{case}"]
+    assert rel_max_err(got, want) < VOL_TOL
+    for d in range(1, D):  # x < d is exactly +0.0
+        z = got[:, :, d, :, : min(d, W)]
+        assert (z == 0).all() and not np.signbit(z).any()
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 320, 40, 48, 27, 240),    # ACV quarter-res width, 1/5 of the height
+    (1, 320, 40, 24, 48, 156),    # PCWNet 1/8 scale
+    (2, 320, 40, 12, 24, 78),     # PCWNet 1/16 (row stride not 16-byte aligned)
+    (2, 320, 40, 6, 12, 39),      # PCWNet 1/32
+    (1, 96, 8, 48, 24, 312),      # IGEV: 12 channels per group
+    (1, 64, 4, 48, 20, 64),       # 16 channels per group
+    (1, 16, 4, 48, 9, 60),        # 4 channels per group, H*W % 256 != 0 tail span
+    (1, 10, 2, 7, 5, 13),         # cpg = 5, H*W % 4 != 0: shape-agnostic kernel
+    (1, 8, 1, 100, 8, 64),        # D > 48: chunk loop, D > W
+])
+def test_gwc_volume_vs_oracle(ops, shape):
+    B, C, G, D, H, W = shape
+    ref, tgt = synth.normal((B, C, H, W), 5), synth.normal((B, C, H, W), 6)
+    got = host(ops.gwc_volume(cu(ref), cu(tgt), D, G))
+    want = O.build_gwc_volume(ref, tgt, D, G)
+    assert rel_max_err(got, want) < VOL_TOL
+    assert np.array_equal(got == 0, want == 0) or rel_max_err(got, want) < VOL_TOL
+
+
+def test_gwc_nonfinite_features_do_not_leak_into_zero_region(ops):
+    B, C, G, D, H, W = 1, 8, 1, 12, 4, 64
+    ref, tgt = synth.normal((B, C, H, W), 7), synth.normal((B, C, H, W), 8)
+    ref[0, 0, 2, 3] = np.inf
+    tgt[0, 1, 1, 60] = np.nan
+    got = host(ops.gwc_volume(cu(ref), cu(tgt), D, G))
+    for d in range(1, D):
+        assert (got[:, :, d, :, :d] == 0).all()
+
+
+def test_groupwise_correlation(ops, golden):
+    B, C, G, D, H, W, seed = GWC_CASES["cpg12"]
+    ref, tgt = synth.normal((B, C, H, W), seed), synth.normal((B, C, H, W), seed + 1000)
+    got = host(ops.groupwise_correlation(cu(ref), cu(tgt), G))
+    assert rel_max_err(got, golden["sf.groupwise.cpg12"]) < VOL_TOL
+    with pytest.raises(AssertionError):
+        ops.groupwise_correlation(cu(ref), cu(tgt), 5)
+
+
+# ------------------------------------------------------------------------------------------------
+# a3 / a4 / a9
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prefix,mask_left", [("sf", False), ("k12", True)])
+@pytest.mark.parametrize("case", list(CONCAT_CASES))
+def test_concat_volume_bit_exact(ops, golden, prefix, mask_left, case):
+    B, C, D, H, W, seed = CONCAT_CASES[case]
+    ref, tgt = synth.normal((B, C, H, W), seed), synth.normal((B, C, H, W), seed + 1000)
+    got = host(ops.concat_volume(cu(ref), cu(tgt), D, mask_left=mask_left))
+    assert np.array_equal(got, golden[f"{prefix}.concat.{case}"])
+
+
+@pytest.mark.parametrize("mask_left", [False, True])
+@pytest.mark.parametrize("shape", [(2, 32, 48, 27, 240), (1, 12, 24, 48, 156), (2, 12, 6, 12, 39), (1, 12, 12, 24, 78),
+                                   (1, 5, 9, 5, 13)])
+def test_concat_volume_vs_oracle(ops, shape, mask_left):
+    B, C, D, H, W = shape
+    ref, tgt = synth.normal((B, C, H, W), 9), synth.normal((B, C, H, W), 10)
+    got = host(ops.concat_volume(cu(ref), cu(tgt), D, mask_left=mask_left))
+    assert np.array_equal(got, O.build_concat_volume(ref, tgt, D, mask_left))
+
+
+def test_acv_attention_volume_golden(ops, golden):
+    B, C, D, h, w = 1, 4, 48, 4, 56
+    cl, cr = synth.normal((B, C, h, w), 51), synth.normal((B, C, h, w), 1051)
+    att = synth.normal((B, 1, D, h, w), 52) * np.float32(3)
+    got = host(ops.concat_volume(cu(cl), cu(cr), D, mask_left=False, att_logits=cu(att)))
+    assert rel_max_err(got, golden["sf.acv_volume"]) < VOL_TOL
+
+
+@pytest.mark.parametrize("xt_dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(2, 32, 48, 27, 240), (1, 4, 48, 5, 13)])
+def test_fused_concat_att_filter_vs_oracle(ops, shape, xt_dtype):
+    B, C, D, h, w = shape
+    cl, cr = synth.normal((B, C, h, w), 11), synth.normal((B, C, h, w), 12)
+    att = synth.normal((B, 1, D, h, w), 13) * np.float32(2)
+    xt = (synth.normal((B, D, h, w), 14, dtype=np.float64) * 0.8).astype(xt_dtype)
+    shift = synth.normal((B, D), 15) * np.float32(0.2)
+    want = O.volume_filter(O.acv_attention_volume(att, O.build_concat_volume(cl, cr, D, False)), xt, shift, 1.0)
+    got = host(ops.concat_volume(cu(cl), cu(cr), D, mask_left=False, att_logits=cu(att), xt=cu(xt), shift=cu(shift)))
+    assert rel_max_err(got, want) < VOL_TOL
+    # the op-boundary variant: volume in, filtered volume out (+ n itself)
+    vol = cu(O.acv_attention_volume(att, O.build_concat_volume(cl, cr, D, False)))
+    got2, n = ops.volume_filter(vol, cu(xt), cu(shift), 1.0, return_n=True)
+    assert rel_max_err(host(got2), want) < 1e-6
+    assert n.dtype == (torch.float64 if xt_dtype == np.float64 else torch.float32)
+    np.testing.assert_allclose(host(n), O.filter_factor(xt, shift, 1.0), rtol=1e-6 if xt_dtype == np.float32 else 1e-14)
+
+
+# ------------------------------------------------------------------------------------------------
+# a5
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,shape,m,G,seed", [
+    ("k12.corr2.m24", (1, 32, 8, 64), 24, 1, 41),
+    ("k12.corr2.w80_m24", (1, 32, 6, 80), 24, 1, 43),
+    ("sftop.corr2.tiny_m9", (2, 8, 3, 7), 9, 2, 42),
+])
+def test_corr_volume_2sided_golden(ops, golden, key, shape, m, G, seed):
+    ref, tgt = synth.normal(shape, seed), synth.normal(shape, seed + 1000)
+    got = host(ops.corr_volume_2sided(cu(ref), cu(tgt), m, G))
+    want = golden[key]
+    assert rel_max_err(got, want) < VOL_TOL
+    assert np.array_equal(got == 0, want == 0)
+
+
+def test_corr_volume_2sided_fullres_vs_oracle(ops):
+    shape = (1, 32, 48, 1248)
+    ref, tgt = synth.normal(shape, 16), synth.normal(shape, 17)
+    got = host(ops.corr_volume_2sided(cu(ref), cu(tgt), 24, 1))
+    assert rel_max_err(got, O.build_corrleation_volume(ref, tgt, 24, 1)) < VOL_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# a6 / a11 / a13
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 10])
+def test_softmax_regress_golden(ops, golden, k):
+    cost = synth.normal((1, 192, 16, 32), 31) * np.float32(k)
+    r = ops.softmax_regress(cu(cost))
+    assert np.abs(host(r["disp"]) - golden[f"sf.regress.k{k}"]).max() < 1e-3
+    prob = O.softmax(cost, 1)
+    got = host(ops.disparity_regression(cu(prob), 192))
+    assert np.abs(got - golden[f"sf.regress.k{k}"]).max() < 1e-3
+    got4 = host(ops.disparity_regression(cu(prob), 192, keepdim=True))
+    assert got4.shape == (1, 1, 16, 32)
+
+
+@pytest.mark.parametrize("shape", [(2, 192, 36, 64), (1, 48, 24, 312), (1, 192, 5, 13), (2, 96, 8, 20), (1, 300, 6, 16)])
+def test_softmax_regress_full_vs_oracle(ops, shape):
+    B, D, H, W = shape
+    cost = synth.normal(shape, 18) * np.float32(4)
+    disp_o, prob_o = O.softmax_regress(cost, D)
+    unc_o = O.uncertainty(disp_o, prob_o)
+    used = (disp_o + (synth.uniform((B, H, W), 19, dtype=np.float32) - np.float32(0.5)) * np.float32(4)).astype(np.float32)
+    thr_unc = float(np.median(unc_o))
+    ens = cu(synth.normal((B, H, W), 20))
+    ens0 = host(ens).copy()
+    r = ops.softmax_regress(cu(cost), return_prob=True, used=cu(used), want_unc=True, vote_thresholds=(1.0, thr_unc),
+                            ens_acc=ens, ens_coef=0.3, ens_init=False)
+    assert np.abs(host(r["disp"]) - disp_o).max() < 1e-3
+    assert rel_max_err(host(r["prob"]), prob_o) < VOL_TOL
+    assert np.abs(host(r["unc"]) - unc_o).max() < 1e-3
+    vote_o = O.renewal_vote(disp_o, used, unc_o, 1.0, thr_unc)
+    near = (np.abs(np.abs(disp_o - used) - 1.0) < 1e-3) | (np.abs(unc_o - thr_unc) < 1e-3)
+    assert np.array_equal(host(r["vote"])[~near], vote_o[~near])
+    np.testing.assert_allclose(host(ens), ens0 + np.float32(0.3) * disp_o, atol=1e-3)
+
+
+def test_softmax_regress_big_golden(ops, golden):
+    cost = synth.normal((1, 192, 135, 240), 92) * np.float32(4)
+    r = ops.softmax_regress(cu(cost), want_unc=True)
+    assert np.abs(host(r["disp"]) - golden["big.regress.disp"]).max() < 1e-3
+    assert np.abs(host(r["unc"]) - golden["big.regress.unc"]).max() < 1e-3
+
+
+def test_gwc_big_golden(ops, golden):
+    B, C, G, D, H, W = 1, 320, 40, 48, 135, 240
+    ref, tgt = synth.normal((B, C, H, W), 91), synth.normal((B, C, H, W), 1091)
+    v = ops.gwc_volume(cu(ref), cu(tgt), D, G)
+    s = golden["big.gwc.sum"]
+    assert abs(float(v.abs().sum(dtype=torch.float64)) - s[1]) < 1e-6 * s[1]
+    flat = host(v).reshape(-1)
+    idx = np.linspace(0, flat.size - 1, 4096).astype(np.int64)
+    assert np.abs(flat[idx] - golden["big.gwc.sample"]).max() < VOL_TOL * s[2]
+
+
+# ------------------------------------------------------------------------------------------------
+# a7 / a8 / a10 / a12 / a13
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("t", [999, 599, 0])
+def test_q_sample_and_pred_noise_golden(ops, golden, t):
+    s = O.Schedule()
+    x0 = synth.uniform((2, 48, 4, 8), 61, dtype=np.float32) * 2 - 1
+    nz = synth.normal((2, 48, 4, 8), 62)
+    qs = ops.q_sample(cu(x0), cu(nz), s.sqrt_alphas_cumprod[t], s.sqrt_one_minus_alphas_cumprod[t])
+    assert qs.dtype == torch.float64
+    np.testing.assert_allclose(host(qs), golden[f"sf.q_sample.t{t}"], rtol=1e-13, atol=1e-15)
+    pn = ops.predict_noise_from_start(qs, cu(x0), s.sqrt_recip_alphas_cumprod[t], s.sqrt_recipm1_alphas_cumprod[t])
+    np.testing.assert_allclose(host(pn), golden[f"sf.pred_noise.t{t}"], rtol=1e-11, atol=1e-11)
+    pn32 = ops.predict_noise_from_start(cu(nz), cu(x0), s.sqrt_recip_alphas_cumprod[t], s.sqrt_recipm1_alphas_cumprod[t])
+    np.testing.assert_allclose(host(pn32), golden[f"sf.pred_noise_f32.t{t}"], rtol=1e-11, atol=1e-11)
+
+
+def test_xstart_golden_and_known_answers(ops, golden):
+    got = host(ops.xstart_from_disp(cu(golden["trace.disp_q"]), 48, 1.0))
+    assert np.array_equal(got, golden["trace.asd"])
+    dq = np.array([0.0, 0.25, 3.0, 46.5, 47.0, 47.75], dtype=np.float32).reshape(1, 1, 6)
+    vol = (host(ops.xstart_from_disp(cu(dq), 48, 1.0))[0, :, 0, :] + 1) / 2
+    want = [{0: 1.0}, {0: 0.75, 1: 0.25}, {3: 1.0}, {46: 0.5, 47: 0.5}, {47: 1.0}, {47: 1.0}]
+    for j, w in enumerate(want):
+        ref = np.zeros(48, dtype=np.float32)
+        for kk, v in w.items():
+            ref[kk] = v
+        np.testing.assert_allclose(vol[:, j], ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("HW", [(16, 32), (18, 30), (135 * 4, 64)])
+def test_downsample_bilinear_vs_oracle(ops, HW):
+    H, W = HW
+    x = synth.normal((2, H, W), 21) * np.float32(60) + np.float32(90)
+    got = host(ops.downsample_bilinear(cu(x), (H // 4, W // 4), clamp=(0, 191), post_scale=0.25))
+    want = O.disp_to_quarter(x, 192)
+    np.testing.assert_allclose(got, want, atol=2e-5)
+
+
+def test_ensemble(ops):
+    maps = [synth.normal((2, 16, 32), 22 + i) * np.float32(50) for i in range(6)]
+    cof = [0.5, 0.0, 0.0, 0.0, 0.2, 0.3]
+    got = host(ops.ensemble([cu(m) for m in maps], cof))
+    np.testing.assert_array_equal(got, O.ensemble(maps, cof))
+
+
+def test_ddim_trace_golden(ops, golden):
+    """The reference's ddim_sample trace, replayed through the CUDA kernels step by step: fused
+    producer (concat+ACV+filter), softmax-regress (+vote +ensemble) and the fused DDIM step.
+    The stand-in for the conv stack (mean over channels * 2 + bias, trilinear x4) runs in numpy."""
+    B, Cc, D, h, w, H, W = (int(v) for v in golden["trace.shape"])
+    sched = O.Schedule()
+    cl, cr = synth.normal((B, Cc, h, w), 71), synth.normal((B, Cc, h, w), 1071)
+    att = synth.normal((B, 1, D, h, w), 72) * np.float32(2)
+    bias, used = trace_inputs(B, D, h, w, H, W)
+    rn, ru = golden["trace.randn_like_seeds"], golden["trace.rand_like_seeds"]
+    img = ops.xstart_from_disp(cu(golden["trace.disp_q"]), D, 1.0)
+    mask = torch.zeros((B, h, w), dtype=torch.float32, device="cuda")
+    ens = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
+    cof = (0.5, 0.0, 0.0, 0.0, 0.2, 0.3)
+    used_c = cu(used)
+    ens.copy_(used_c * cof[0])
+    pairs = sched.time_pairs()
+    for i, (time, time_next) in enumerate(pairs):
+        np.testing.assert_allclose(host(img), golden[f"trace.img.{i}"], atol=1e-3)
+        assert host(img).dtype == golden[f"trace.img.{i}"].dtype
+        shift = cu(golden[f"trace.shift.t{time}"])
+        vol_f = ops.concat_volume(cu(cl), cu(cr), D, mask_left=False, att_logits=cu(att), xt=img, shift=shift)
+        c = host(vol_f).mean(axis=1, keepdims=True, dtype=np.float32) * np.float32(2.0)
+        cost = O.interpolate_trilinear(c + bias[i], (192, H, W))[:, 0]
+        r = ops.softmax_regress(cu(cost), used=used_c, vote_thresholds=(1.0, 3.0), ens_acc=ens, ens_coef=cof[i + 1])
+        assert np.abs(host(r["disp"]) - golden[f"trace.disp.{i}"]).max() < 1e-3
+        last = time_next < 0
+        kw = {}
+        if not last:
+            san, c_, sigma = sched.ddim_coefficients(time, time_next)
+            seed, is64 = rn[2 * i]
+            sn = synth.normal((B, D, h, w), int(seed), dtype=np.float64).astype(np.float64 if is64 else np.float32)
+            kw = dict(sqrt_alpha_next=san, c=c_, sigma=sigma, step_noise=cu(sn),
+                      renoise=cu(synth.uniform((B, D, h, w), int(ru[i][0]), dtype=np.float64)))
+        st = ops.ddim_step(disp=r["disp"], xt=img, shift=shift, scale=1.0,
+                           sqrt_recip=sched.sqrt_recip_alphas_cumprod[time],
+                           sqrt_recipm1=sched.sqrt_recipm1_alphas_cumprod[time], last_step=last,
+                           vote=r["vote"], mask=mask, want_eps=True, **kw)
+        np.testing.assert_allclose(host(st["x0"]), golden[f"trace.x0.{i}"], atol=2e-4)
+        np.testing.assert_allclose(host(st["eps"]), golden[f"trace.eps.{i}"], rtol=1e-6, atol=1e-3)
+        img = st["x_next"]
+    assert 0.2 < float((mask == 0).float().mean()) < 0.8
+    assert np.abs(host(ens) - golden["trace.pred"]).max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# a14 / a15
+# ------------------------------------------------------------------------------------------------
+def test_corr1d_and_geo_lookup_golden(ops, golden):
+    B, Cf, h, w, Cg, D = 2, 16, 6, 40, 8, 48
+    f1, f2 = synth.normal((B, Cf, h, w), 101), synth.normal((B, Cf, h, w), 102)
+    geo = synth.normal((B, Cg, D, h, w), 103)
+    disp = synth.uniform((B, 1, h, w), 104, dtype=np.float32) * np.float32(50) - np.float32(2)
+    coords = np.broadcast_to(np.arange(w, dtype=np.float32).reshape(1, 1, 1, w), (B, 1, h, w)).copy()
+    noisy = synth.uniform((B, D, h, w), 105, dtype=np.float32)
+    corr = ops.corr1d_allpairs(cu(f1), cu(f2))
+    assert corr.shape == (B, h, w, 1, w)
+    assert rel_max_err(host(corr), golden["k15.corr"]) < VOL_TOL
+    g0 = ops.geo_permute(cu(geo))
+    g1 = ops.avgpool_w2(g0)
+    c0 = corr.reshape(B * h * w, 1, 1, w)
+    c1 = ops.avgpool_w2(c0)
+    assert rel_max_err(host(g1), golden["k15.geo.pyr1"]) < 1e-6
+    assert rel_max_err(host(c1), golden["k15.corr.pyr1"]) < VOL_TOL
+    plain = ops.geo_lookup([g0, g1], [c0, c1], cu(disp), cu(coords), None, 4)
+    assert plain.shape == (B, 162, h, w)
+    assert rel_max_err(host(plain), golden["k15.geo.plain"]) < VOL_TOL
+    ddim = ops.geo_lookup([g0, g1], [c0, c1], cu(disp), cu(coords), cu(noisy), 4)
+    assert rel_max_err(host(ddim), golden["k15.geo.ddim"]) < VOL_TOL
+
+
+def test_geo_lookup_igev_shape_vs_oracle(ops):
+    B, Cf, h, w, Cg, D = 1, 96, 12, 312, 8, 48
+    f1, f2 = synth.normal((B, Cf, h, w), 111), synth.normal((B, Cf, h, w), 112)
+    geo = synth.normal((B, Cg, D, h, w), 113)
+    disp = synth.uniform((B, 1, h, w), 114, dtype=np.float32) * np.float32(47)
+    coords = np.broadcast_to(np.arange(w, dtype=np.float32).reshape(1, 1, 1, w), (B, 1, h, w)).copy()
+    noisy = synth.uniform((B, D, h, w), 115, dtype=np.float32)
+    vol = O.CombinedGeoEncodingVolume(f1, f2, geo, 2, 4)
+    corr = ops.corr1d_allpairs(cu(f1), cu(f2))
+    assert rel_max_err(host(corr), vol.init_corr_pyramid[0].reshape(corr.shape)) < VOL_TOL
+    g0 = ops.geo_permute(cu(geo)); g1 = ops.avgpool_w2(g0)
+    c0 = corr.reshape(B * h * w, 1, 1, w); c1 = ops.avgpool_w2(c0)
+    got = ops.geo_lookup([g0, g1], [c0, c1], cu(disp), cu(coords), cu(noisy), 4)
+    assert rel_max_err(host(got), vol(disp, coords, noisy)) < VOL_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# loud failure on CPU tensors (no fallback)
+# ------------------------------------------------------------------------------------------------
+def test_cpu_tensor_raises(ops):
+    from diffuvolume_b200._lib import DvLibraryError
+    x = torch.zeros(1, 8, 4, 8)
+    with pytest.raises(DvLibraryError):
+        ops.gwc_volume(x, x, 4, 2)

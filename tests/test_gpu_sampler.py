@@ -1,0 +1,141 @@
+"""Tier-2 drop-ins (diffuvolume_b200.sampler) bound onto a stand-in for the reference's ACVNet_DDIM and
+replayed against the trace the REAL ACVNet_DDIM.ddim_sample produced (tests/golden/make_golden.py): same
+stand-in conv stack, same injected noise.  Runs on the GPU box."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import synth
+from golden.make_golden import trace_inputs
+from oracle import dv_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+class ShiftTable(nn.Module):
+    """DynamicHead stand-in: noisy + shift[t] (head.py:74-77), shifts taken from the golden fixture."""
+
+    def __init__(self, golden):
+        super().__init__()
+        self.table = {t: cu(golden[f"trace.shift.t{t}"]) for t in (999, 799, 599, 399, 199)}
+
+    def forward(self, noisy, t):
+        s = self.table[int(t.reshape(-1)[0].item())]
+        return noisy + s[:, :, None, None]
+
+
+class Stand0(nn.Module):
+    def forward(self, v):
+        return v.mean(1, keepdim=True) * 2.0
+
+
+class Zero(nn.Module):
+    def forward(self, v):
+        return torch.zeros_like(v)
+
+
+class Bias(nn.Module):
+    def __init__(self, bias):
+        super().__init__()
+        self.bias, self.n = [cu(b) for b in bias], 0
+
+    def forward(self, v):
+        o = v + self.bias[self.n]
+        self.n += 1
+        return o
+
+
+class MockACVNetDDIM(nn.Module):
+    """Attribute-compatible stand-in for SceneFlow/models/acv_ddim.py:ACVNet_DDIM (sampler-relevant part)."""
+
+    def __init__(self, golden, bias):
+        super().__init__()
+        s = O.Schedule()
+        self.maxdisp, self.scale = 192, 1.0
+        self.num_timesteps, self.sampling_timesteps, self.ddim_sampling_eta = 1000, 5, 1
+        self.renewal, self.use_ensemble = True, True
+        for name in ("alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                     "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod"):
+            self.register_buffer(name, torch.from_numpy(getattr(s, name)))
+        self.time_embedding = ShiftTable(golden)
+        self.dres0, self.dres1, self.dres2, self.dres3, self.classif2 = Stand0(), Zero(), nn.Identity(), nn.Identity(), Bias(bias)
+
+
+@pytest.fixture()
+def bound(golden):
+    from diffuvolume_b200 import ops, sampler
+    B, Cc, D, h, w, H, W = (int(v) for v in golden["trace.shape"])
+    bias, used = trace_inputs(B, D, h, w, H, W)
+    net = MockACVNetDDIM(golden, bias).cuda()
+    for name, fn in (("q_sample", sampler.q_sample), ("predict_noise_from_start", sampler.predict_noise_from_start),
+                     ("model_predictions", sampler.acv_model_predictions), ("ddim_sample", sampler.acv_ddim_sample)):
+        setattr(MockACVNetDDIM, name, fn)
+    cl, cr = synth.normal((B, Cc, h, w), 71), synth.normal((B, Cc, h, w), 1071)
+    att = synth.normal((B, 1, D, h, w), 72) * np.float32(2)
+    volume = ops.concat_volume(cu(cl), cu(cr), D, mask_left=False, att_logits=cu(att))
+    asd = ops.xstart_from_disp(cu(golden["trace.disp_q"]), D, 1.0)
+    return net, volume, cu(used), asd
+
+
+def test_methods_q_sample_and_pred_noise(bound, golden):
+    net = bound[0]
+    x0 = synth.uniform((2, 48, 4, 8), 61, dtype=np.float32) * 2 - 1
+    nz = synth.normal((2, 48, 4, 8), 62)
+    for t in (999, 599, 0):
+        tt = torch.full((1,), t, dtype=torch.long, device="cuda")
+        qs = net.q_sample(cu(x0), tt, cu(nz))
+        np.testing.assert_allclose(qs.cpu().numpy(), golden[f"sf.q_sample.t{t}"], rtol=1e-13, atol=1e-15)
+        pn = net.predict_noise_from_start(qs, tt, cu(x0))
+        np.testing.assert_allclose(pn.cpu().numpy(), golden[f"sf.pred_noise.t{t}"], rtol=1e-11, atol=1e-11)
+
+
+def test_model_predictions_first_step(bound, golden):
+    net, volume, used, asd = bound
+    t = torch.full((volume.shape[0],), 999, dtype=torch.long, device="cuda")
+    pred_noise, x_start, pred, prob = net.model_predictions(volume, asd, t)
+    assert pred_noise.dtype == torch.float64 and x_start.dtype == torch.float32 and prob.shape[1] == 192
+    assert np.abs(pred.cpu().numpy() - golden["trace.disp.0"]).max() < 1e-3
+    np.testing.assert_allclose(x_start.cpu().numpy(), golden["trace.x0.0"], atol=2e-4)
+    np.testing.assert_allclose(pred_noise.cpu().numpy(), golden["trace.eps.0"], rtol=1e-6, atol=1e-3)
+    np.testing.assert_allclose(prob.sum(1).cpu().numpy(), 1.0, atol=1e-5)
+
+
+def test_ddim_sample_replays_the_reference_trace(bound, golden, monkeypatch):
+    net, volume, used, asd = bound
+    k = {"n": 0}
+
+    def randn_like(x, **kw):
+        seed = 2000 + k["n"]; k["n"] += 1
+        return cu(synth.normal(tuple(x.shape), seed, dtype=np.float64)).to(kw.get("dtype", x.dtype))
+
+    def rand_like(x, **kw):
+        seed = 2000 + k["n"]; k["n"] += 1
+        return cu(synth.uniform(tuple(x.shape), seed, dtype=np.float64)).to(kw.get("dtype", x.dtype))
+
+    monkeypatch.setattr(torch, "randn_like", randn_like)
+    monkeypatch.setattr(torch, "rand_like", rand_like)
+    pred, final = net.ddim_sample(volume, used, asd)
+    assert k["n"] == 12                                    # 3 draws per non-final step, like the reference
+    assert final.shape == (6, *used.shape)
+    assert np.abs(final.cpu().numpy() - golden["trace.final"]).max() < 1e-3
+    assert np.abs(pred.cpu().numpy() - golden["trace.pred"]).max() < 1e-3
+
+
+def test_uncertainty_vote_matches_oracle():
+    from diffuvolume_b200 import ops
+    cost = synth.normal((2, 192, 12, 20), 5) * np.float32(4)
+    disp_o, prob_o = O.softmax_regress(cost, 192)
+    refined = disp_o + synth.normal((2, 12, 20), 6) * np.float32(0.7)
+    used = refined + (synth.uniform((2, 12, 20), 7, dtype=np.float32) - np.float32(0.5)) * np.float32(3)
+    unc_o = O.uncertainty(refined, prob_o)
+    thr = float(np.median(unc_o))
+    vote, unc = ops.uncertainty_vote(cu(refined), cu(prob_o), cu(used), 1.0, thr, return_unc=True)
+    np.testing.assert_allclose(unc.cpu().numpy(), unc_o, atol=1e-3)
+    want = O.renewal_vote(refined, used, unc_o, 1.0, thr)
+    near = (np.abs(np.abs(refined - used) - 1.0) < 1e-3) | (np.abs(unc_o - thr) < 1e-3)
+    assert np.array_equal(vote.cpu().numpy()[~near], want[~near])

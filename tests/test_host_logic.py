@@ -1,0 +1,179 @@
+"""Host-side logic that needs no GPU: schedule constants, the installer, error conventions, autograd
+formulas of the drop-in functions, metric sharding."""
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import dv_oracle as O
+from oracle import torch_port as P
+
+REF = Path("/root/reference")
+
+
+def test_schedule_matches_oracle_and_golden(golden):
+    from diffuvolume_b200.pipeline import DdimSchedule
+    s, o = DdimSchedule(), O.Schedule()
+    np.testing.assert_allclose(s.alphas_cumprod, golden["sched.alphas_cumprod"], rtol=1e-12)
+    for S in (5, 3, 2):
+        assert DdimSchedule(sampling_timesteps=S).time_pairs() == O.Schedule(sampling_timesteps=S).time_pairs()
+        assert np.array_equal(np.array(DdimSchedule(sampling_timesteps=S).time_pairs()), golden[f"sched.time_pairs.S{S}"])
+    for t, tn in s.time_pairs()[:-1]:
+        np.testing.assert_allclose(s.update_coefficients(t, tn), o.ddim_coefficients(t, tn), rtol=1e-14)
+        assert s.sqrt_recip(t) == pytest.approx(golden["sched.sqrt_recip_alphas_cumprod"][t], rel=1e-12)
+        assert s.sqrt_recipm1(t) == pytest.approx(golden["sched.sqrt_recipm1_alphas_cumprod"][t], rel=1e-12)
+        assert s.sqrt_ac(t) == pytest.approx(golden["sched.sqrt_alphas_cumprod"][t], rel=1e-12)
+        assert s.sqrt_1m_ac(t) == pytest.approx(golden["sched.sqrt_one_minus_alphas_cumprod"][t], rel=1e-12)
+
+
+def test_reference_error_conventions_on_the_mirrors():
+    from diffuvolume_b200 import kitti12, kitti15, sceneflow
+    from diffuvolume_b200._lib import DvLibraryError
+    x = torch.zeros(1, 10, 4, 8)
+    for m in (sceneflow, kitti12, kitti15):
+        with pytest.raises(AssertionError):          # assert C % num_groups == 0 (submodule.py:211)
+            m.build_gwc_volume(x, x, 4, 3)
+        with pytest.raises(AssertionError):          # assert len(x.shape) == 4 (submodule.py:174)
+            m.disparity_regression(torch.zeros(1, 4, 8), 4)
+        with pytest.raises(DvLibraryError):          # CPU tensors: loud failure, no fallback
+            m.build_gwc_volume(x, x, 4, 2)
+        with pytest.raises(DvLibraryError):
+            m.build_concat_volume(x, x, 4)
+    with pytest.raises(AssertionError):
+        kitti12.build_corrleation_volume(x, x, 2, 3)
+
+
+def test_installer_with_stand_in_modules():
+    import diffuvolume_b200.install as dvi
+    from diffuvolume_b200 import sampler, sceneflow
+    sub = types.ModuleType("models.submodule")
+    sub.build_gwc_volume = lambda *a: "ref-gwc"
+    sub.build_concat_volume = lambda *a: "ref-concat"
+    sub.disparity_regression = lambda *a: "ref-reg"
+    sub.groupwise_correlation = lambda *a: "ref-gc"
+    sub.convbn = "untouched"
+    consumer = types.ModuleType("models.acv_ddim")
+    for k, v in vars(sub).items():            # what `from models.submodule import *` does
+        if not k.startswith("__"):
+            setattr(consumer, k, v)
+
+    class ACVNet_DDIM:
+        def q_sample(self, x, t, noise=None):
+            return "ref"
+
+        def predict_noise_from_start(self, x_t, t, x0):
+            return "ref"
+
+        def model_predictions(self, volume, noise, t):
+            return "ref"
+
+        def ddim_sample(self, volume, used, asd):
+            return "ref"
+
+    consumer.ACVNet_DDIM = ACVNet_DDIM
+    mods = {"models.submodule": sub, "models.acv_ddim": consumer}
+    done = dvi.install("sceneflow", modules=mods)
+    assert "models.acv_ddim.build_gwc_volume" in done and "models.acv_ddim.ACVNet_DDIM.ddim_sample" in done
+    assert consumer.build_gwc_volume is sceneflow.build_gwc_volume
+    assert sub.disparity_regression is sceneflow.disparity_regression
+    assert consumer.convbn == "untouched"
+    assert ACVNet_DDIM.ddim_sample is sampler.acv_ddim_sample
+    n = dvi.uninstall()
+    assert n == len(done)
+    assert consumer.build_gwc_volume() == "ref-gwc" and ACVNet_DDIM().ddim_sample(0, 0, 0) == "ref"
+    with pytest.raises(ValueError):
+        dvi.install("nope")
+
+
+@pytest.mark.skipif(not (REF / "SceneFlow").exists(), reason="reference checkout not present (authoring container only)")
+def test_installer_on_the_real_reference():
+    """Import the reference's SceneFlow package, install, and check that its own consumer modules now hold
+    our functions (calling them with CPU tensors then fails loudly — no silent fallback)."""
+    import subprocess
+    code = r'''
+import sys, torch
+sys.path.insert(0, "/root/reference/SceneFlow"); sys.path.insert(0, "%s")
+import models.acv_ddim as M, models.acv as A
+import diffuvolume_b200.install as dvi
+from diffuvolume_b200 import sceneflow, sampler
+from diffuvolume_b200._lib import DvLibraryError
+done = dvi.install("sceneflow")
+assert M.build_gwc_volume is sceneflow.build_gwc_volume and A.build_concat_volume is sceneflow.build_concat_volume
+assert M.ACVNet_DDIM.ddim_sample is sampler.acv_ddim_sample
+x = torch.zeros(1, 8, 4, 8)
+try:
+    M.build_gwc_volume(x, x, 4, 2)
+    raise SystemExit("expected a loud failure on CPU tensors")
+except DvLibraryError:
+    pass
+dvi.uninstall()
+assert M.build_gwc_volume.__module__ == "models.submodule"
+print("OK", len(done))
+''' % str(Path(__file__).resolve().parent.parent)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_backward_formulas_against_autograd(monkeypatch):
+    """The drop-ins are autograd Functions (training scripts back-propagate through them); their backward
+    formulas are checked against autograd of the op-for-op CPU port, with the CUDA forward swapped for the
+    port in THIS TEST ONLY."""
+    from diffuvolume_b200 import functional as Fn
+    from diffuvolume_b200 import ops
+    monkeypatch.setattr(ops, "gwc_volume", lambda r, t_, D, G, out=None: P.gwc_volume(r, t_, D, G))
+    monkeypatch.setattr(ops, "concat_volume", lambda r, t_, D, mask_left, **k: P.concat_volume(r, t_, D, mask_left))
+    monkeypatch.setattr(ops, "disparity_regression",
+                        lambda x, D, keepdim=False: torch.sum(x * torch.arange(D, dtype=x.dtype).view(1, D, 1, 1), 1, keepdim=keepdim))
+    monkeypatch.setattr(ops, "corr_volume_2sided",
+                        lambda r, t_, m, G: torch.from_numpy(O.build_corrleation_volume(r.detach().numpy(), t_.detach().numpy(), m, G)))
+    monkeypatch.setattr(ops, "groupwise_correlation",
+                        lambda a, b, G: (a * b).view(a.shape[0], G, a.shape[1] // G, *a.shape[2:]).mean(2))
+    tt = lambda a: torch.from_numpy(a.astype(np.float64)).requires_grad_(True)
+    ref, tgt = synth.normal((2, 8, 3, 10), 1), synth.normal((2, 8, 3, 10), 2)
+
+    def check(fn_ours, fn_port, *shape_args):
+        a1, b1 = tt(ref), tt(tgt)
+        a2, b2 = tt(ref), tt(tgt)
+        o1, o2 = fn_ours(a1, b1, *shape_args), fn_port(a2, b2, *shape_args)
+        g = torch.from_numpy(synth.normal(tuple(o2.shape), 9).astype(np.float64))
+        o1.backward(g); o2.backward(g)
+        np.testing.assert_allclose(a1.grad.numpy(), a2.grad.numpy(), atol=1e-5)
+        np.testing.assert_allclose(b1.grad.numpy(), b2.grad.numpy(), atol=1e-5)
+
+    check(Fn.build_gwc_volume, lambda r, t_, D, G: P.gwc_volume(r, t_, D, G), 6, 4)
+    check(Fn.build_concat_volume_m, lambda r, t_, D: P.concat_volume(r, t_, D, False), 6)
+    check(Fn.build_concat_volume_t, lambda r, t_, D: P.concat_volume(r, t_, D, True), 6)
+    check(Fn.groupwise_correlation, lambda a, b, G: (a * b).view(2, G, 8 // G, 3, 10).mean(2), 2)
+
+    # two-sided correlation volume: autograd reference written with slices (KITTI12/models/submodule.py:121-135)
+    def corr_port(r, t_, m, G):
+        B, C, H, W = r.shape
+        vol = r.new_zeros([B, G, 2 * m + 1, H, W])
+        gc = lambda a, b: (a * b).view(B, G, C // G, H, -1).mean(2)
+        for i in range(-m, m + 1):
+            if i > 0:
+                vol[:, :, i + m, :, i:] = gc(r[..., i:], t_[..., :-i])
+            elif i < 0:
+                vol[:, :, i + m, :, :-i] = gc(r[..., :-i], t_[..., i:])
+            else:
+                vol[:, :, m] = gc(r, t_)
+        return vol
+    check(Fn.build_corrleation_volume, corr_port, 3, 2)
+    x = torch.from_numpy(synth.normal((2, 6, 3, 5), 3).astype(np.float64)).requires_grad_(True)
+    Fn.disparity_regression(x, 6, True).sum().backward()
+    np.testing.assert_allclose(x.grad.numpy(), np.broadcast_to(np.arange(6.0).reshape(1, 6, 1, 1), (2, 6, 3, 5)))
+
+
+def test_shard_range_covers_everything():
+    from diffuvolume_b200.distributed import shard_range
+    for n in (0, 1, 7, 8, 4370):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
