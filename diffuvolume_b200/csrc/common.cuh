@@ -1,5 +1,6 @@
 // common.cuh — shared device/host helpers for the DiffuVolume B200 hot-path kernels (sm_100a).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
@@ -88,6 +89,51 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- tensor-map TMA (cp.async.bulk.tensor, SASS: UTMALDG) ------------------------------------
+// The driver's encoder is fetched through the runtime (no link-time dependency on libcuda).
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// Dense fp32 tensor of `rank` dims (dims[0] fastest, contiguous), tile box `box`; no swizzle; OOB reads give 0.
+inline bool make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint32_t *box) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t gdim[5], gstride[5];
+    cuuint32_t bdim[5], estride[5];
+    uint64_t stride = 4;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estride[i] = 1;
+        stride *= dims[i];
+        if (i + 1 < rank) {
+            if (stride % 16 != 0) return false;
+            gstride[i] = stride;   // byte stride of dim i+1
+        }
+    }
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank), const_cast<void *>(base), gdim, gstride,
+               bdim, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+__device__ __forceinline__ void tma_load_3d(void *dst_smem, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // ---- streaming 128-bit global accesses ------------------------------------------------------
 __device__ __forceinline__ void stg_cs(float4 *p, const float4 &v) {
     // evict-first streaming store: the volume is written once and consumed by a later kernel
@@ -110,5 +156,9 @@ __device__ __forceinline__ T filter_n(T xt, float shift, T s) {
     v = v < -s ? -s : (v > s ? s : v);
     return ((v / s) + static_cast<T>(1)) / static_cast<T>(2);
 }
+
+// concat_stream.cu: TMA-fed streaming producer; DV_ERR_UNSUPPORTED when tensor maps cannot be built
+int launch_concat_stream(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int mask_left,
+                         const float *wts, const float *nf, cudaStream_t st);
 
 }  // namespace dv

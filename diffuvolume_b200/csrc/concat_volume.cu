@@ -160,6 +160,225 @@ concat_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tg
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weighted producer (the shipped path of the DDIM loop): the per-(b,d,pixel) factors arrive PRECOMPUTED as
+// fp32 maps — w = softmax_D(att logits) (dv_att_softmax_f32, once per pair) and n = the filter factor
+// (dv_filter_factor_f32 / the n_next output of dv_ddim_step, 6 MB per pair and step) — so the volume-sized
+// pass has no prologue, no shared memory and no barrier: thread = (quad q of a 128-px span, slot) walks
+// d = slot, slot+8, ...; per d it loads w and n once (2 x LDG.128, L2-resident) and produces CG channels
+// (left: the ref quad, held in registers for the whole CTA; right: two aligned LDG.128 of tgt + a warp-uniform
+// select).  Small CTAs (CG x D planes x 512 B) keep the grid >= 25 waves, which the micro-benchmarks
+// (scripts/ubench/ubench_mem.cu) show is what separates 6.4 from 7.3 TB/s on a write-only stream.
+template <int CG, bool HAS_W, bool HAS_N, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+concat_weighted_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out, int C,
+                       int HW, int W, int D, int mask_left, const float *__restrict__ wts,
+                       const float *__restrict__ nf) {
+    const int q = threadIdx.x & 31, slot = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int p = (blockIdx.x * 32 + q) * 4;
+    if (p >= HW) return;
+    const int c0 = blockIdx.y * CG;
+    int xs[4];
+    xs[0] = p % W;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        xs[i] = xs[i - 1] + 1;
+        if (xs[i] >= W) xs[i] -= W;
+    }
+    // left-half channels of this CTA: one quad each, reused for every d
+    float4 lv[CG];
+#pragma unroll
+    for (int k = 0; k < CG; ++k) {
+        const int c = c0 + k;
+        lv[k] = (c < C) ? __ldg(reinterpret_cast<const float4 *>(ref + (static_cast<int64_t>(b) * C + c) * HW + p))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int64_t fbase = static_cast<int64_t>(b) * D * HW + p;
+    for (int d = slot; d < D; d += 8) {
+        float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f), n4 = w4;
+        if (HAS_W) w4 = __ldg(reinterpret_cast<const float4 *>(wts + fbase + static_cast<int64_t>(d) * HW));
+        if (HAS_N) n4 = __ldg(reinterpret_cast<const float4 *>(nf + fbase + static_cast<int64_t>(d) * HW));
+        const bool k0 = xs[0] >= d, k1 = xs[1] >= d, k2 = xs[2] >= d, k3 = xs[3] >= d;
+        const int sh = d & 3;            // warp-uniform
+        const int dal = d - sh;          // aligned part of the shift
+#pragma unroll
+        for (int k = 0; k < CG; ++k) {
+            const int c = c0 + k;
+            if (c >= 2 * C) break;
+            float4 o;
+            if (c < C) {
+                o = lv[k];
+                if (mask_left) {
+                    o.x = k0 ? o.x : 0.0f; o.y = k1 ? o.y : 0.0f; o.z = k2 ? o.z : 0.0f; o.w = k3 ? o.w : 0.0f;
+                }
+            } else {
+                // out = tgt[p-d .. p-d+3] = last `sh` floats of block (p-dal-4) ++ first 4-sh floats of block (p-dal)
+                const int64_t base = (static_cast<int64_t>(b) * C + (c - C)) * HW + p - dal;   // flat index into tgt
+                // only the first rows of the very first plane can reach below 0; x < d there
+                const float4 cur = base >= 0 ? __ldg(reinterpret_cast<const float4 *>(tgt + base)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sh != 0 && base >= 4) prev = __ldg(reinterpret_cast<const float4 *>(tgt + base - 4));
+                if (sh == 0) o = cur;
+                else if (sh == 1) o = make_float4(prev.w, cur.x, cur.y, cur.z);
+                else if (sh == 2) o = make_float4(prev.z, prev.w, cur.x, cur.y);
+                else o = make_float4(prev.y, prev.z, prev.w, cur.x);
+                o.x = k0 ? o.x : 0.0f; o.y = k1 ? o.y : 0.0f; o.z = k2 ? o.z : 0.0f; o.w = k3 ? o.w : 0.0f;
+            }
+            if (HAS_W) { o.x *= w4.x; o.y *= w4.y; o.z *= w4.z; o.w *= w4.w; }
+            if (HAS_N) { o.x *= n4.x; o.y *= n4.y; o.z *= n4.z; o.w *= n4.w; }
+            stg_cs(reinterpret_cast<float4 *>(out + ((static_cast<int64_t>(b) * 2 * C + c) * D + d) * HW + p), o);
+        }
+    }
+}
+
+// Variant with all loads hoisted: thread = (quad q, group ds of 4 consecutive disparities d0 = 4 ds).  The two
+// factor quads of each of its 4 disparities are fetched first (8 independent LDG.128), then per channel the
+// thread needs ONE ref quad (left half) or TWO aligned tgt quads (right half: d0 % 4 == 0 makes the four shifted
+// windows compile-time permutations of {prev, cur}) for FOUR 128-bit stores.
+template <int CG, bool HAS_W, bool HAS_N>
+__global__ void __launch_bounds__(384)
+concat_weighted4_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out, int C,
+                        int HW, int W, int D, int mask_left, const float *__restrict__ wts,
+                        const float *__restrict__ nf) {
+    const int q = threadIdx.x & 31, slot = threadIdx.x >> 5, nslots = blockDim.x >> 5;
+    const int b = blockIdx.z;
+    const int p = (blockIdx.x * 32 + q) * 4;
+    if (p >= HW) return;
+    const int c0 = blockIdx.y * CG;
+    int xs[4];
+    xs[0] = p % W;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        xs[i] = xs[i - 1] + 1;
+        if (xs[i] >= W) xs[i] -= W;
+    }
+    const int64_t fbase = static_cast<int64_t>(b) * D * HW + p;
+    for (int d0 = 4 * slot; d0 < D; d0 += 4 * nslots) {
+        float4 w4[4], n4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            w4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+            n4[j] = w4[j];
+            if (d0 + j < D) {
+                if (HAS_W) w4[j] = __ldg(reinterpret_cast<const float4 *>(wts + fbase + static_cast<int64_t>(d0 + j) * HW));
+                if (HAS_N) n4[j] = __ldg(reinterpret_cast<const float4 *>(nf + fbase + static_cast<int64_t>(d0 + j) * HW));
+            }
+        }
+        float4 cur[CG], prev[CG];
+#pragma unroll
+        for (int k = 0; k < CG; ++k) {
+            const int c = c0 + k;
+            cur[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            prev[k] = cur[k];
+            if (c < C) {
+                cur[k] = __ldg(reinterpret_cast<const float4 *>(ref + (static_cast<int64_t>(b) * C + c) * HW + p));
+            } else if (c < 2 * C) {
+                const int64_t base = (static_cast<int64_t>(b) * C + (c - C)) * HW + p - d0;   // flat index into tgt
+                // only the first rows of the very first plane can reach below 0; x < d there
+                if (base >= 0) cur[k] = __ldg(reinterpret_cast<const float4 *>(tgt + base));
+                if (base >= 4) prev[k] = __ldg(reinterpret_cast<const float4 *>(tgt + base - 4));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CG; ++k) {
+            const int c = c0 + k;
+            if (c >= 2 * C) break;
+            float *op = out + ((static_cast<int64_t>(b) * 2 * C + c) * D + d0) * HW + p;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = d0 + j;
+                if (d >= D) break;
+                float4 o;
+                if (c < C || j == 0) o = cur[k];
+                else if (j == 1) o = make_float4(prev[k].w, cur[k].x, cur[k].y, cur[k].z);
+                else if (j == 2) o = make_float4(prev[k].z, prev[k].w, cur[k].x, cur[k].y);
+                else o = make_float4(prev[k].y, prev[k].z, prev[k].w, cur[k].x);
+                if (c >= C || mask_left) {
+                    o.x = xs[0] >= d ? o.x : 0.0f; o.y = xs[1] >= d ? o.y : 0.0f;
+                    o.z = xs[2] >= d ? o.z : 0.0f; o.w = xs[3] >= d ? o.w : 0.0f;
+                }
+                if (HAS_W) { o.x *= w4[j].x; o.y *= w4[j].y; o.z *= w4[j].z; o.w *= w4[j].w; }
+                if (HAS_N) { o.x *= n4[j].x; o.y *= n4[j].y; o.z *= n4[j].z; o.w *= n4[j].w; }
+                stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(j) * HW), o);
+            }
+        }
+    }
+}
+
+// softmax over D of the attention logits [B,1,D,HW] -> weights [B,D,HW] (F.softmax(att_weights, dim=2),
+// acv_ddim.py:390): thread = one quad of pixels, three passes over D (the 2nd and 3rd hit L1/L2).
+__global__ void __launch_bounds__(128)
+att_softmax_kernel(const float *__restrict__ att, float *__restrict__ wts, int D, int HW) {
+    const int b = blockIdx.y;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (p >= HW) return;
+    const float *ap = att + static_cast<int64_t>(b) * D * HW + p;
+    float *wp = wts + static_cast<int64_t>(b) * D * HW + p;
+    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int d = 0; d < D; ++d) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(ap + static_cast<int64_t>(d) * HW));
+        mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+    }
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 0; d < D; ++d) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(ap + static_cast<int64_t>(d) * HW));
+        sum.x += expf(v.x - mx.x); sum.y += expf(v.y - mx.y); sum.z += expf(v.z - mx.z); sum.w += expf(v.w - mx.w);
+    }
+    for (int d = 0; d < D; ++d) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(ap + static_cast<int64_t>(d) * HW));
+        float4 o;
+        o.x = expf(v.x - mx.x) / sum.x; o.y = expf(v.y - mx.y) / sum.y;
+        o.z = expf(v.z - mx.z) / sum.z; o.w = expf(v.w - mx.w) / sum.w;
+        *reinterpret_cast<float4 *>(wp + static_cast<int64_t>(d) * HW) = o;
+    }
+}
+__global__ void att_softmax_generic_kernel(const float *__restrict__ att, float *__restrict__ wts, int D, int HW,
+                                           int64_t total) {
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t b = idx / HW, p = idx % HW;
+        const float *ap = att + b * D * HW + p;
+        float mx = -INFINITY;
+        for (int d = 0; d < D; ++d) mx = fmaxf(mx, ap[static_cast<int64_t>(d) * HW]);
+        float sum = 0.0f;
+        for (int d = 0; d < D; ++d) sum += expf(ap[static_cast<int64_t>(d) * HW] - mx);
+        for (int d = 0; d < D; ++d)
+            wts[b * D * HW + static_cast<int64_t>(d) * HW + p] = expf(ap[static_cast<int64_t>(d) * HW] - mx) / sum;
+    }
+}
+
+// n[b,d,p] = float(((clamp(xt + shift[b,d], -s, s) / s) + 1) / 2)   (acv_ddim.py:256-258)
+template <typename XT>
+__global__ void filter_factor_kernel(const XT *__restrict__ xt, const float *__restrict__ shift, XT scale,
+                                     float *__restrict__ nf, int HW, int64_t total) {
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t bd = idx / HW;
+        nf[idx] = static_cast<float>(filter_n<XT>(xt[idx], shift ? shift[bd] : 0.0f, scale));
+    }
+}
+
+template <int CG, bool HAS_W, bool HAS_N>
+static int launch_weighted(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D,
+                           int mask_left, const float *wts, const float *nf, cudaStream_t st) {
+    dim3 grid((HW / 4 + 31) / 32, (2 * C + CG - 1) / CG, B);
+    if (tune_variant("DV_CONCAT_V", 0) == 1) {
+        int slots = (D + 3) / 4;
+        if (slots > 12) slots = 12;
+        concat_weighted4_kernel<CG, HAS_W, HAS_N><<<grid, 32 * slots, 0, st>>>(ref, tgt, out, C, HW, W, D, mask_left, wts, nf);
+        return finish_launch();
+    }
+    const int minb = tune_variant("DV_CONCAT_MINB", 4);
+    if (minb == 8)
+        concat_weighted_kernel<CG, HAS_W, HAS_N, 8><<<grid, 256, 0, st>>>(ref, tgt, out, C, HW, W, D, mask_left, wts, nf);
+    else if (minb == 6)
+        concat_weighted_kernel<CG, HAS_W, HAS_N, 6><<<grid, 256, 0, st>>>(ref, tgt, out, C, HW, W, D, mask_left, wts, nf);
+    else
+        concat_weighted_kernel<CG, HAS_W, HAS_N, 4><<<grid, 256, 0, st>>>(ref, tgt, out, C, HW, W, D, mask_left, wts, nf);
+    return finish_launch();
+}
+
 // Shape-agnostic path ((H*W) % 4 != 0 or unaligned pointers): one thread per output element.
 template <typename XT>
 __global__ void concat_volume_generic_kernel(const float *__restrict__ ref, const float *__restrict__ tgt,
@@ -256,4 +475,75 @@ extern "C" int dv_concat_volume_f32(const float *ref, const float *tgt, float *o
             ref, tgt, out, static_cast<int>(C), static_cast<int>(HW), static_cast<int>(W), static_cast<int>(D), mask_left,
             att_logits, static_cast<const float *>(xt), shift, static_cast<float>(scale), total);
     return finish_launch();
+}
+
+extern "C" int dv_att_softmax_f32(const float *att_logits, float *weights, int64_t B, int64_t D, int64_t H, int64_t W,
+                                  void *stream) {
+    using namespace dv;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!att_logits || !weights) return DV_ERR_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || D > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    if ((HW % 4 == 0) && aligned16(att_logits) && aligned16(weights)) {
+        dim3 grid(static_cast<unsigned>((HW / 4 + 127) / 128), static_cast<unsigned>(B));
+        att_softmax_kernel<<<grid, 128, 0, st>>>(att_logits, weights, static_cast<int>(D), static_cast<int>(HW));
+    } else {
+        const int64_t total = B * HW;
+        const int64_t blocks = (total + 255) / 256;
+        const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+        att_softmax_generic_kernel<<<grid, 256, 0, st>>>(att_logits, weights, static_cast<int>(D), static_cast<int>(HW), total);
+    }
+    return finish_launch();
+}
+
+extern "C" int dv_filter_factor_f32(const void *xt, int xt_is_f64, const float *shift, double scale, float *n_out,
+                                    int64_t B, int64_t D, int64_t H, int64_t W, void *stream) {
+    using namespace dv;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!xt || !n_out) return DV_ERR_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || !(scale > 0.0)) return DV_ERR_BAD_SHAPE;
+    if (xt_is_f64 != 0 && xt_is_f64 != 1) return DV_ERR_BAD_DTYPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    const int64_t total = B * D * HW;
+    const int64_t blocks = (total + 255) / 256;
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 16 ? blocks : static_cast<int64_t>(kNumSMs) * 16);
+    if (xt_is_f64)
+        filter_factor_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double *>(xt), shift, scale, n_out,
+                                                           static_cast<int>(HW), total);
+    else
+        filter_factor_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(xt), shift, static_cast<float>(scale),
+                                                          n_out, static_cast<int>(HW), total);
+    return finish_launch();
+}
+
+extern "C" int dv_concat_volume_weighted_f32(const float *ref, const float *tgt, float *out, int64_t B, int64_t C,
+                                             int64_t H, int64_t W, int64_t D, int mask_left, const float *att_weights,
+                                             const float *n, void *stream) {
+    using namespace dv;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!ref || !tgt || !out) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || 2 * C > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    auto ok16 = [](const void *p) { return !p || aligned16(p); };
+    if (!((HW % 4 == 0) && W >= 4 && aligned16(ref) && aligned16(tgt) && aligned16(out) && ok16(att_weights) && ok16(n)))
+        return DV_ERR_MISALIGNED;   // callers fall back to dv_concat_volume_f32 + dv_volume_filter_f32
+    if (tune_variant("DV_CONCAT_STREAM", 1)) {
+        const int rc = launch_concat_stream(ref, tgt, out, static_cast<int>(B), static_cast<int>(C), static_cast<int>(HW),
+                                            static_cast<int>(W), static_cast<int>(D), mask_left, att_weights, n, st);
+        if (rc != DV_ERR_UNSUPPORTED) return rc;
+    }
+    const int cg = tune_variant("DV_CONCAT_CG", 2);
+#define DV_W(CGV)                                                                                                      \
+    (att_weights && n ? launch_weighted<CGV, true, true>(ref, tgt, out, B, C, HW, W, D, mask_left, att_weights, n, st)  \
+     : att_weights   ? launch_weighted<CGV, true, false>(ref, tgt, out, B, C, HW, W, D, mask_left, att_weights, n, st) \
+     : n             ? launch_weighted<CGV, false, true>(ref, tgt, out, B, C, HW, W, D, mask_left, att_weights, n, st) \
+                     : launch_weighted<CGV, false, false>(ref, tgt, out, B, C, HW, W, D, mask_left, att_weights, n, st))
+    if (cg == 1) return DV_W(1);
+    if (cg == 2) return DV_W(2);
+    if (cg == 8) return DV_W(8);
+    return DV_W(4);
+#undef DV_W
 }

@@ -159,6 +159,9 @@ ddim_step_kernel(const dv_ddim_step_args a) {
             if (renoise_px) img = rn;
         }
         static_cast<double *>(a.x_next)[e] = img;
+        // the next step's filter factor from the fp64 state just produced (acv_ddim.py:256-258 of the next iteration)
+        if (a.n_next_out)
+            a.n_next_out[e] = static_cast<float>(filter_n<double>(img, a.shift_next ? a.shift_next[b * D + d] : 0.0f, a.scale));
     }
 }
 

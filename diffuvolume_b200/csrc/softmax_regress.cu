@@ -216,6 +216,237 @@ softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__r
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipelined variant (the shipped path for 16-byte-aligned maps with D <= 192).
+//
+// A persistent CTA (2 per SM) walks tiles of [D x 64 px] of one batch item.  A dedicated producer warp lands
+// each tile in shared memory with one 256-byte bulk copy per disparity row (cp.async.bulk -> SASS UBLKCP,
+// mbarrier transaction count), STAGES tiles deep, so HBM requests stay in flight while the 8 consumer warps
+// do the arithmetic of earlier tiles — the register-resident kernel above alternates between "all loads"
+// and "all math" per warp and reached only 4.5 TB/s.  Consumers copy their slice of the tile to registers
+// (conflict-free LDS.128: a warp reads two adjacent rows = 512 contiguous bytes) and release the stage at
+// once.  Thread (quad q of 16, slice ds of 16) owns d = 16 j + ds; the constant 16 j folds into FFMA/FADD
+// immediates, the per-thread ds enters once per tile.  Cross-slice reductions: one shuffle + 8-way shared
+// memory combine behind a 256-thread named barrier (the producer warp never joins it).
+template <int NJ, int STAGES, int SPAN, bool TMAP>
+__global__ void __launch_bounds__(288, SPAN == 64 ? 2 : 1)
+softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ cost, int D, int HW,
+                           int spans_per_b, int ntiles,
+                           float *__restrict__ disp_out, float *__restrict__ prob_out, const float *__restrict__ used,
+                           float *__restrict__ unc_out, float *__restrict__ vote_out, float thr_dif, float thr_unc,
+                           float *__restrict__ ens_acc, float ens_coef, int ens_init) {
+    constexpr int SQ = SPAN / 4, NW = 8, NDS = 256 / SQ;   // quads per span, consumer warps, disparity slices
+    extern __shared__ __align__(128) float smem[];              // [STAGES][D][SPAN]
+    __shared__ float4 red[4][NW][SQ];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
+    const int stage_floats = D * SPAN;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ---------------- producer warp
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int s = it % STAGES, k = it / STAGES;
+            if (k > 0) mbar_wait(&empty_bar[s], (k & 1) ^ 1);
+            const int b = t / spans_per_b;
+            const int p0 = (t - b * spans_per_b) * SPAN;
+            float *dst = smem + s * stage_floats;
+            if (TMAP) {
+                // one tensor-map TMA per tile: box [64 px, D rows, 1] of the [HW, D, B] view (OOB px read as 0)
+                if (lane == 0) {
+                    mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(D) * SPAN * 4u);
+                    tma_load_3d(dst, &tmap, p0, 0, b, &full_bar[s]);
+                }
+            } else {
+                const int len = min(SPAN, HW - p0);   // multiple of 4
+                if (lane == 0) mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(D) * len * 4u);
+                __syncwarp();
+                const float *src = cost + static_cast<int64_t>(b) * D * HW + p0;
+                for (int r = lane; r < D; r += 32)
+                    bulk_g2s(dst + r * SPAN, src + static_cast<int64_t>(r) * HW, 4u * len, &full_bar[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps
+    const int q = threadIdx.x & (SQ - 1);
+    const int ds = threadIdx.x / SQ;           // 0..NDS-1
+    const float dsf = static_cast<float>(ds);
+    constexpr float kLog2e = 1.4426950408889634f;
+    const bool fin = ds == 0;                  // lanes 0..15 of warp 0 write the span's outputs
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % STAGES, k = it / STAGES;
+        const int b = t / spans_per_b;
+        const int p0 = (t - b * spans_per_b) * SPAN;
+        const int p = p0 + 4 * q;
+        const bool live = p < HW;
+        const int64_t o = static_cast<int64_t>(b) * HW + p;
+        float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fin && live) {   // issue the small map reads before waiting for the tile
+            if (vote_out) u4 = ldg_stream(reinterpret_cast<const float4 *>(used + o));
+            if (ens_acc && !ens_init) a4 = *reinterpret_cast<const float4 *>(ens_acc + o);
+        }
+        mbar_wait(&full_bar[s], k & 1);
+        float4 x[NJ];
+        {
+            const float *st = smem + s * stage_floats + ds * SPAN + 4 * q;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (NDS * j + ds < D)
+                    x[j] = *reinterpret_cast<const float4 *>(st + NDS * j * SPAN);
+                else
+                    x[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);   // the tile now lives in registers
+
+        // ---- max over D
+        float4 m = x[0];
+#pragma unroll
+        for (int j = 1; j < NJ; ++j) {
+            m.x = fmaxf(m.x, x[j].x); m.y = fmaxf(m.y, x[j].y); m.z = fmaxf(m.z, x[j].z); m.w = fmaxf(m.w, x[j].w);
+        }
+        if (SQ < 32) {
+        m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, 16));
+        m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, 16));
+        m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, 16));
+        m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, 16));
+        }
+        if (SQ == 32 || lane < SQ) red[0][warp][q] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float4 v = red[0][w][q];
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+        // ---- e = exp(x - max), S = sum e, Wd = sum d e   (d = 16 j + ds)
+        const float4 mL = make_float4(m.x * kLog2e, m.y * kLog2e, m.z * kLog2e, m.w * kLog2e);
+        float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Wj = S;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float dj = static_cast<float>(NDS * j);
+            x[j].x = fast_exp2(fmaf(x[j].x, kLog2e, -mL.x)); S.x += x[j].x; Wj.x = fmaf(dj, x[j].x, Wj.x);
+            x[j].y = fast_exp2(fmaf(x[j].y, kLog2e, -mL.y)); S.y += x[j].y; Wj.y = fmaf(dj, x[j].y, Wj.y);
+            x[j].z = fast_exp2(fmaf(x[j].z, kLog2e, -mL.z)); S.z += x[j].z; Wj.z = fmaf(dj, x[j].z, Wj.z);
+            x[j].w = fast_exp2(fmaf(x[j].w, kLog2e, -mL.w)); S.w += x[j].w; Wj.w = fmaf(dj, x[j].w, Wj.w);
+        }
+        float4 Wd = make_float4(fmaf(dsf, S.x, Wj.x), fmaf(dsf, S.y, Wj.y), fmaf(dsf, S.z, Wj.z), fmaf(dsf, S.w, Wj.w));
+        if (SQ < 32) {
+        S.x += __shfl_xor_sync(0xffffffffu, S.x, 16); S.y += __shfl_xor_sync(0xffffffffu, S.y, 16);
+        S.z += __shfl_xor_sync(0xffffffffu, S.z, 16); S.w += __shfl_xor_sync(0xffffffffu, S.w, 16);
+        Wd.x += __shfl_xor_sync(0xffffffffu, Wd.x, 16); Wd.y += __shfl_xor_sync(0xffffffffu, Wd.y, 16);
+        Wd.z += __shfl_xor_sync(0xffffffffu, Wd.z, 16); Wd.w += __shfl_xor_sync(0xffffffffu, Wd.w, 16);
+        }
+        if (SQ == 32 || lane < SQ) {
+            red[1][warp][q] = S;
+            red[2][warp][q] = Wd;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        S = make_float4(0.f, 0.f, 0.f, 0.f);
+        Wd = S;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float4 a = red[1][w][q], c = red[2][w][q];
+            S.x += a.x; S.y += a.y; S.z += a.z; S.w += a.w;
+            Wd.x += c.x; Wd.y += c.y; Wd.z += c.z; Wd.w += c.w;
+        }
+        const float4 rS = make_float4(1.0f / S.x, 1.0f / S.y, 1.0f / S.z, 1.0f / S.w);
+        const float4 disp = make_float4(Wd.x * rS.x, Wd.y * rS.y, Wd.z * rS.z, Wd.w * rS.w);
+        if (prob_out && live) {
+            float *pp = prob_out + static_cast<int64_t>(b) * D * HW + p + static_cast<int64_t>(ds) * HW;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+                if (NDS * j + ds < D)
+                    *reinterpret_cast<float4 *>(pp + static_cast<int64_t>(NDS * j) * HW) =
+                        make_float4(x[j].x * rS.x, x[j].y * rS.y, x[j].z * rS.z, x[j].w * rS.w);
+        }
+        float4 U = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (unc_out || vote_out) {   // uniform across the grid
+            const float4 t0 = make_float4(disp.x - dsf, disp.y - dsf, disp.z - dsf, disp.w - dsf);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const float dj = static_cast<float>(NDS * j);
+                U.x = fmaf(fabsf(t0.x - dj), x[j].x, U.x);
+                U.y = fmaf(fabsf(t0.y - dj), x[j].y, U.y);
+                U.z = fmaf(fabsf(t0.z - dj), x[j].z, U.z);
+                U.w = fmaf(fabsf(t0.w - dj), x[j].w, U.w);
+            }
+            if (SQ < 32) {
+            U.x += __shfl_xor_sync(0xffffffffu, U.x, 16); U.y += __shfl_xor_sync(0xffffffffu, U.y, 16);
+            U.z += __shfl_xor_sync(0xffffffffu, U.z, 16); U.w += __shfl_xor_sync(0xffffffffu, U.w, 16);
+            }
+            if (SQ == 32 || lane < SQ) red[3][warp][q] = U;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (fin) {
+                U = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const float4 a = red[3][w][q];
+                    U.x += a.x; U.y += a.y; U.z += a.z; U.w += a.w;
+                }
+                U.x *= rS.x; U.y *= rS.y; U.z *= rS.z; U.w *= rS.w;
+            }
+        }
+        if (fin && live) {
+            if (disp_out) *reinterpret_cast<float4 *>(disp_out + o) = disp;
+            if (unc_out) *reinterpret_cast<float4 *>(unc_out + o) = U;
+            if (vote_out) {
+                float4 vt;
+                vt.x = (fabsf(disp.x - u4.x) < thr_dif && U.x < thr_unc) ? 1.0f : 0.0f;
+                vt.y = (fabsf(disp.y - u4.y) < thr_dif && U.y < thr_unc) ? 1.0f : 0.0f;
+                vt.z = (fabsf(disp.z - u4.z) < thr_dif && U.z < thr_unc) ? 1.0f : 0.0f;
+                vt.w = (fabsf(disp.w - u4.w) < thr_dif && U.w < thr_unc) ? 1.0f : 0.0f;
+                *reinterpret_cast<float4 *>(vote_out + o) = vt;
+            }
+            if (ens_acc) {
+                a4.x = fmaf(ens_coef, disp.x, a4.x); a4.y = fmaf(ens_coef, disp.y, a4.y);
+                a4.z = fmaf(ens_coef, disp.z, a4.z); a4.w = fmaf(ens_coef, disp.w, a4.w);
+                *reinterpret_cast<float4 *>(ens_acc + o) = a4;
+            }
+        }
+    }
+}
+
+template <int NJ, int STAGES, int SPAN>
+static int launch_sr_tma(const float *cost, int B, int D, int HW, float *disp_out, float *prob_out, const float *used,
+                         float *unc_out, float *vote_out, float thr_dif, float thr_unc, float *ens_acc,
+                         float ens_coef, int ens_init, cudaStream_t st) {
+    const size_t smem = sizeof(float) * STAGES * static_cast<size_t>(D) * SPAN;
+    const int spans = (HW + SPAN - 1) / SPAN;
+    constexpr int kCtasPerSm = SPAN == 64 ? 2 : 1;
+    const int64_t ntiles = static_cast<int64_t>(spans) * B;
+    const int grid = static_cast<int>(ntiles < 1LL * kCtasPerSm * kNumSMs ? ntiles : 1LL * kCtasPerSm * kNumSMs);
+    CUtensorMap tmap;
+    const uint64_t dims[3] = {static_cast<uint64_t>(HW), static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
+    const uint32_t box[3] = {static_cast<uint32_t>(SPAN), static_cast<uint32_t>(D), 1u};
+    const bool have_map = tune_variant("DV_SR_TMAP", 1) && make_tensor_map_f32(&tmap, cost, 3, dims, box);
+#define DV_LAUNCH(TM)                                                                                                  \
+    {                                                                                                                  \
+        auto kern = softmax_regress_tma_kernel<NJ, STAGES, SPAN, TM>;                                                        \
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=         \
+            cudaSuccess)                                                                                               \
+            return DV_ERR_LAUNCH;                                                                                      \
+        kern<<<grid, 288, smem, st>>>(tmap, cost, D, HW, spans, static_cast<int>(ntiles), disp_out, prob_out, used,    \
+                                      unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init);               \
+    }
+    if (have_map) DV_LAUNCH(true) else DV_LAUNCH(false)
+#undef DV_LAUNCH
+    return DV_OK;
+}
+
 // Any D: one thread per pixel, three passes over D (the re-reads hit L2).
 __global__ void softmax_regress_generic_kernel(const float *__restrict__ cost, int D, int HW,
                                                float *__restrict__ disp_out, float *__restrict__ prob_out,
@@ -344,6 +575,18 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
     const bool vec2 = (HW % 2 == 0) && all_aligned(7);
     // D <= 8*DPT.  Tuning switch DV_SR_VARIANT (scripts/tune_kernels.py) selects the D = 192 layout.
     const int variant = tune_variant("DV_SR_VARIANT", 4);
+    if (vec4 && D <= 192 && tune_variant("DV_SR_TMA", 1) && static_cast<int64_t>((HW + 63) / 64) * B <= INT32_MAX) {
+        int rc;
+#define DV_SR_TMA_ARGS cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, st
+        const int span = tune_variant("DV_SR_SPAN", 64);
+        if (D <= 48) rc = launch_sr_tma<3, 4, 64>(DV_SR_TMA_ARGS);
+        else if (D <= 96) rc = launch_sr_tma<6, 4, 64>(DV_SR_TMA_ARGS);
+        else if (span == 128) rc = launch_sr_tma<24, 2, 128>(DV_SR_TMA_ARGS);
+        else rc = launch_sr_tma<12, 2, 64>(DV_SR_TMA_ARGS);
+#undef DV_SR_TMA_ARGS
+        if (rc != DV_OK) return rc;
+        return finish_launch();
+    }
 #define DV_SR_ARGS cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, st
     if (D <= 48) {
         if (vec4) launch_sr<6, 4, 8, 4>(DV_SR_ARGS);

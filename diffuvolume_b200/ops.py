@@ -141,6 +141,68 @@ def concat_volume(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, *, mask_le
     return out
 
 
+def att_softmax(att_logits: torch.Tensor) -> torch.Tensor:
+    """a4 factor — softmax over D of the attention logits [B,1,D,H,W] -> fp32 weights [B,D,H,W]
+    (F.softmax(att_weights, dim=2), acv_ddim.py:390)."""
+    _need_cuda(att_logits)
+    att_logits = _f32c(att_logits, "att_logits")
+    if att_logits.dim() == 5:
+        assert att_logits.shape[1] == 1
+        B, _, D, H, W = att_logits.shape
+    else:
+        B, D, H, W = att_logits.shape
+    out = torch.empty((B, D, H, W), dtype=torch.float32, device=att_logits.device)
+    if out.numel():
+        with torch.cuda.device(out.device):
+            check(_lib.lib().dv_att_softmax_f32(_ptr(att_logits), _ptr(out), B, D, H, W, _stream(out)), "dv_att_softmax_f32")
+    return out
+
+
+def filter_factor(xt: torch.Tensor, shift: Optional[torch.Tensor] = None, scale: float = 1.0,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a9 factor — n = float(((clamp(xt + shift[b,d], -s, s)/s)+1)/2) as an fp32 map [B,D,H,W] (acv_ddim.py:256-258)."""
+    _need_cuda(xt, shift)
+    B, D, H, W = xt.shape
+    f64 = _is_f64(xt, "xt")
+    xt = xt.contiguous()
+    if shift is not None:
+        shift = _f32c(shift.reshape(B, D), "shift")
+    if out is None:
+        out = torch.empty((B, D, H, W), dtype=torch.float32, device=xt.device)
+    if out.numel():
+        with torch.cuda.device(out.device):
+            check(_lib.lib().dv_filter_factor_f32(_ptr(xt), f64, _ptr(shift), float(scale), _ptr(out), B, D, H, W,
+                                                  _stream(out)), "dv_filter_factor_f32")
+    return out
+
+
+def concat_volume_weighted(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, *, mask_left: bool,
+                           att_weights: Optional[torch.Tensor] = None, n: Optional[torch.Tensor] = None,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a3 (+a4 +a9) with PRECOMPUTED fp32 factor maps (`att_softmax`, `filter_factor` / ddim_step's n_next):
+    out = (concat * att_weights) * n — the same values as `concat_volume(att_logits=..., xt=...)`.
+    Needs H*W % 4 == 0 (every reference shape); raises DvLibraryError(DV_ERR_MISALIGNED) otherwise."""
+    B, Cc, H, W = ref.shape
+    _need_cuda(ref, tgt, att_weights, n)
+    ref, tgt = _f32c(ref, "refimg_fea"), _f32c(tgt, "targetimg_fea")
+    if tgt.shape != ref.shape:
+        raise RuntimeError(f"The size of tensor a {tuple(ref.shape)} must match the size of tensor b {tuple(tgt.shape)}")
+    for name, t in (("att_weights", att_weights), ("n", n)):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != B * maxdisp * H * W):
+            raise RuntimeError(f"{name} must be a contiguous float32 [B,{maxdisp},{H},{W}] map")
+    if out is None:
+        out = torch.empty((B, 2 * Cc, maxdisp, H, W), dtype=torch.float32, device=ref.device)
+    else:
+        assert out.shape == (B, 2 * Cc, maxdisp, H, W) and out.dtype == torch.float32 and out.is_contiguous()
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(ref.device):
+        check(_lib.lib().dv_concat_volume_weighted_f32(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp,
+                                                       int(mask_left), _ptr(att_weights), _ptr(n), _stream(ref)),
+              "dv_concat_volume_weighted_f32")
+    return out
+
+
 def volume_filter(vol: torch.Tensor, xt: torch.Tensor, shift: Optional[torch.Tensor] = None, scale: float = 1.0, *,
                   out: Optional[torch.Tensor] = None, return_n: bool = False):
     """a9 — `volume * ((clamp(xt + shift, -s, s)/s + 1)/2).unsqueeze(1).float()` (acv_ddim.py:254-260)."""
@@ -335,11 +397,11 @@ def ddim_step(*, disp: torch.Tensor, xt: torch.Tensor, shift: Optional[torch.Ten
               renoise: Optional[torch.Tensor] = None,
               asd: Optional[torch.Tensor] = None, q_noise: Optional[torch.Tensor] = None,
               sqrt_ac: float = 0.0, sqrt_1m_ac: float = 0.0, want_asd_out: bool = False,
-              want_eps: bool = False):
+              want_eps: bool = False, shift_next: Optional[torch.Tensor] = None, want_n_next: bool = False):
     """a8+a10+a11+a12 — one fused DDIM sampler step (see dv_ddim_step_args in include/dv_b200.h).
 
     Returns dict(x0=[B,D,h,w] fp32, x_next=[B,D,h,w] fp64 (fp32 when last_step), eps=fp64 or None,
-    asd_out=fp64 or None).  `mask` is updated in place.
+    asd_out=fp64 or None, n_next=fp32 filter factor of the NEXT step when want_n_next).  `mask` is updated in place.
     """
     _need_cuda(disp, xt, shift, coords0, vote, used, mask, step_noise, renoise, asd, q_noise)
     B, D, h, w = xt.shape
@@ -414,10 +476,17 @@ def ddim_step(*, disp: torch.Tensor, xt: torch.Tensor, shift: Optional[torch.Ten
     eps = torch.empty((B, D, h, w), dtype=torch.float64, device=dev) if want_eps else None
     x_next = torch.empty((B, D, h, w), dtype=torch.float32 if last_step else torch.float64, device=dev)
     a.x0_out, a.eps_out, a.x_next = _ptr(x0), _ptr(eps), _ptr(x_next)
+    n_next = None
+    if want_n_next and not last_step:
+        if shift_next is not None:
+            shift_next = _f32c(shift_next.reshape(B, D), "shift_next")
+            keep.append(shift_next)
+        n_next = torch.empty((B, D, h, w), dtype=torch.float32, device=dev)
+        a.shift_next, a.n_next_out = _ptr(shift_next), _ptr(n_next)
     with torch.cuda.device(dev):
         check(_lib.lib().dv_ddim_step(C.byref(a), _stream(xt)), "dv_ddim_step")
     del keep
-    return {"x0": x0, "x_next": x_next, "eps": eps, "asd_out": asd_out}
+    return {"x0": x0, "x_next": x_next, "eps": eps, "asd_out": asd_out, "n_next": n_next}
 
 
 # --------------------------------------------------------------------------------------------

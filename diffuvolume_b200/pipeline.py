@@ -85,7 +85,9 @@ class AcvHotPath:
 
     filter_mode:
       'regenerate' — each DDIM step re-produces the filtered volume straight from the 1/4-res concat
-                     features + attention logits + x_t (reads 21 MB, writes 398 MB per pair and step);
+                     features and two precomputed fp32 factor maps (softmax of the attention logits, once per
+                     pair; the filter factor n, emitted by the previous fused DDIM step): reads 21 MB, writes
+                     398 MB per pair and step;
       'volume'     — each step multiplies the materialised ac_volume (reads 404 MB, writes 398 MB):
                      the reference's own op boundary (acv_ddim.py:260).
     Both produce bit-identical volumes (same roundings in the same order).
@@ -131,20 +133,27 @@ class AcvHotPath:
         H, W = used.shape[-2:]
         with tm("gwc_volume"):
             gwc = ops.gwc_volume(feat_l, feat_r, D, self.G, out=self._out("gwc", (B, self.G, D, h, w), dev))
+        regen = self.filter_mode == "regenerate"
         with tm("concat_acv"):
-            ac = ops.concat_volume(cfeat_l, cfeat_r, D, mask_left=False, att_logits=att_logits,
-                                   out=self._out("ac", (B, 2 * Cc, D, h, w), dev))
+            if regen:
+                # softmax over D of the attention logits: once per pair, reused by all T filter passes
+                att_w = ops.att_softmax(att_logits)
+                ac = ops.concat_volume_weighted(cfeat_l, cfeat_r, D, mask_left=False, att_weights=att_w,
+                                                out=self._out("ac", (B, 2 * Cc, D, h, w), dev))
+            else:
+                ac = ops.concat_volume(cfeat_l, cfeat_r, D, mask_left=False, att_logits=att_logits,
+                                       out=self._out("ac", (B, 2 * Cc, D, h, w), dev))
         img = ops.xstart_from_disp(disp_q, D, sched.scale)
         ens = ops.ensemble([used], [self.cof[0]])
         mask = torch.zeros((B, h, w), dtype=torch.float32, device=dev)
         vol_f = self._out("vol_f", (B, 2 * Cc, D, h, w), dev)
         pairs = sched.time_pairs()
+        n = ops.filter_factor(img, shifts[0], sched.scale) if regen else None
         for i, (t, t_next) in enumerate(pairs):
             shift = shifts[i]
             with tm("filter"):
-                if self.filter_mode == "regenerate":
-                    ops.concat_volume(cfeat_l, cfeat_r, D, mask_left=False, att_logits=att_logits, xt=img,
-                                      shift=shift, scale=sched.scale, out=vol_f)
+                if regen:
+                    ops.concat_volume_weighted(cfeat_l, cfeat_r, D, mask_left=False, att_weights=att_w, n=n, out=vol_f)
                 else:
                     ops.volume_filter(ac, img, shift, sched.scale, out=vol_f)
             # (3-D conv aggregation of vol_f happens here in the full network — out of scope)
@@ -156,13 +165,15 @@ class AcvHotPath:
             kw = {}
             if not last:
                 san, c, sigma = sched.update_coefficients(t, t_next)
-                kw = dict(sqrt_alpha_next=san, c=c, sigma=sigma, step_noise=step_noises[i], renoise=renoises[i])
+                kw = dict(sqrt_alpha_next=san, c=c, sigma=sigma, step_noise=step_noises[i], renoise=renoises[i],
+                          shift_next=shifts[i + 1], want_n_next=regen)
             with tm("ddim_step"):
                 st = ops.ddim_step(disp=r["disp"], xt=img, shift=shift, scale=sched.scale,
                                    sqrt_recip=sched.sqrt_recip(t), sqrt_recipm1=sched.sqrt_recipm1(t),
                                    last_step=last, disp_clamp_hi=float(self.maxdisp - 1), vote=r["vote"], mask=mask,
                                    **kw)
             img = st["x_next"]
+            n = st["n_next"]
         out = {"pred": ens, "mask": mask, "x_last": img}
         if keep_volumes:
             out.update(gwc=gwc, ac=ac, vol_f=vol_f)
@@ -170,4 +181,4 @@ class AcvHotPath:
 
     def launches_per_call(self) -> int:
         T = self.sched.sampling_timesteps
-        return 4 + 3 * T
+        return (6 if self.filter_mode == "regenerate" else 4) + 3 * T

@@ -75,6 +75,23 @@ int dv_concat_volume_f32(const float *ref, const float *tgt, float *out,
                          const void *xt, int xt_is_f64, const float *shift, double scale,
                          void *stream);
 
+/* ---- a4 / a9 factors as stand-alone fp32 maps, and the volume producer that consumes them.
+ * The DDIM loop re-produces the filtered volume T times from the same 1/4-res features; its per-(b,d,pixel)
+ * factors are therefore computed once, outside the volume-sized pass:
+ *   dv_att_softmax_f32   : weights[b,d,p] = softmax_d(att_logits[b,0,:,p])          (acv_ddim.py:390, acv.py:203)
+ *   dv_filter_factor_f32 : n[b,d,p] = float(((clamp(xt + shift[b,d], -s, s)/s)+1)/2)  (acv_ddim.py:256-258)
+ *                          (dv_ddim_step can emit the next step's n itself: n_next_out)
+ *   dv_concat_volume_weighted_f32 : out = ((concat * att_weights) * n), either factor may be NULL (= 1);
+ *                          same values, in the same rounding order, as dv_concat_volume_f32 with att_logits / xt.
+ *                          Needs H*W % 4 == 0 and 16-byte aligned pointers (else DV_ERR_MISALIGNED).        */
+int dv_att_softmax_f32(const float *att_logits, float *weights, int64_t B, int64_t D, int64_t H, int64_t W,
+                       void *stream);
+int dv_filter_factor_f32(const void *xt, int xt_is_f64, const float *shift, double scale, float *n_out,
+                         int64_t B, int64_t D, int64_t H, int64_t W, void *stream);
+int dv_concat_volume_weighted_f32(const float *ref, const float *tgt, float *out,
+                                  int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int mask_left,
+                                  const float *att_weights, const float *n, void *stream);
+
 /* ---- a9 at the op boundary: the DDIM filter multiply on an existing volume
  *          (SceneFlow/models/acv_ddim.py:254-260; KITTI12/models/pwcnet_ddim.py:466-472)
  * out[b,c,d,p] = vol[b,c,d,p] * float(n[b,d,p]);  n as above.  out may alias vol.
@@ -192,6 +209,9 @@ typedef struct {
     float *x0_out;             /* [B,D,h,w] fp32 x_start                                          */
     double *eps_out;           /* [B,D,h,w] fp64 pred_noise, optional                             */
     void *x_next;              /* [B,D,h,w]: fp64 normally; fp32 x0 copy when last_step           */
+    /* optional: the NEXT step's filter factor, n_next = float(filter_n(x_next + shift_next[b,d])) */
+    const float *shift_next;   /* [B,D] time-embedding shift of the next timestep, or NULL (= 0)   */
+    float *n_next_out;         /* [B,D,h,w] fp32, or NULL                                          */
 } dv_ddim_step_args;
 
 int dv_ddim_step(const dv_ddim_step_args *args, void *stream);

@@ -32,13 +32,19 @@ cost = rn(B, 192, H, W) * 4
 used = torch.rand(B, H, W, device=dev) * 191
 ens = torch.zeros(B, H, W, device=dev)
 gb = B*(192*H*W*4 + 5*H*W*4)/1e9
-for v in (0, 1, 2, 3, 4, 5):
+for tma in (1, 0):
+    os.environ["DV_SR_TMA"] = str(tma)
+    ms = timeit(lambda: ops.softmax_regress(cost, used=used, vote_thresholds=(1.0, 3.0), ens_acc=ens, ens_coef=0.2))
+    report("softmax_regress", f"tma{tma}", ms, gb)
+    ms = timeit(lambda: ops.softmax_regress(cost))
+    report("softmax_regress_disp_only", f"tma{tma}", ms, B*(192*H*W*4 + H*W*4)/1e9)
+for v in (() if os.environ.get("DV_TUNE_ALL") is None else (0, 1, 2, 3, 4, 5)):
     os.environ["DV_SR_VARIANT"] = str(v)
     ms = timeit(lambda: ops.softmax_regress(cost, used=used, vote_thresholds=(1.0, 3.0), ens_acc=ens, ens_coef=0.2))
     report("softmax_regress", v, ms, gb)
     ms = timeit(lambda: ops.softmax_regress(cost))
     report("softmax_regress_disp_only", v, ms, B*(192*H*W*4 + H*W*4)/1e9)
-os.environ.pop("DV_SR_VARIANT")
+os.environ.pop("DV_SR_VARIANT", None); os.environ.pop("DV_SR_TMA", None)
 del cost
 # ---- gwc
 fl, fr = rn(B, 320, h, w), rn(B, 320, h, w)
@@ -66,6 +72,16 @@ for cpc in (8, 16, 32):
     report("filter_regen_f64", cpc, timeit(lambda: ops.concat_volume(cl, cr, D, mask_left=False, att_logits=att, xt=xt64, shift=shift, out=volf)), B*(64*hw*4 + D*hw*12 + gvol)/1e9)
     report("filter_regen_f32", cpc, timeit(lambda: ops.concat_volume(cl, cr, D, mask_left=False, att_logits=att, xt=xt32, shift=shift, out=volf)), B*(64*hw*4 + D*hw*8 + gvol)/1e9)
 os.environ.pop("DV_CONCAT_CPC")
+att_w = ops.att_softmax(att)
+nf = ops.filter_factor(xt64, shift, 1.0)
+report("att_softmax", 0, timeit(lambda: ops.att_softmax(att)), B*2*D*hw*4/1e9)
+report("filter_factor_f64", 0, timeit(lambda: ops.filter_factor(xt64, shift, 1.0)), B*D*hw*12/1e9)
+for cg, ver, bar in ((8, 31, 0), (8, 31, 1), (16, 31, 0), (16, 31, 1), (8, 21, 0), (8, 21, 1), (8, 22, 0), (8, 22, 1), (4, 22, 1), (4, 31, 1)):
+    os.environ["DV_CS_CGT"] = str(cg); os.environ["DV_CS_SHAPE"] = str(ver); os.environ["DV_CS_BAR"] = str(bar); cg = f"cgt{cg}_shape{ver}_bar{bar}"
+    report("weighted_plain", cg, timeit(lambda: ops.concat_volume_weighted(cl, cr, D, mask_left=False, out=vol)), B*(64*hw*4 + gvol)/1e9)
+    report("weighted_acv", cg, timeit(lambda: ops.concat_volume_weighted(cl, cr, D, mask_left=False, att_weights=att_w, out=vol)), B*(64*hw*4 + D*hw*4 + gvol)/1e9)
+    report("weighted_filter", cg, timeit(lambda: ops.concat_volume_weighted(cl, cr, D, mask_left=False, att_weights=att_w, n=nf, out=volf)), B*(64*hw*4 + D*hw*8 + gvol)/1e9)
+os.environ.pop("DV_CONCAT_CG"); os.environ.pop("DV_CS_CGT"); os.environ.pop("DV_CS_SHAPE"); os.environ.pop("DV_CS_BAR")
 report("filter_volume_f64", 0, timeit(lambda: ops.volume_filter(vol, xt64, shift, 1.0, out=volf)), B*(2*gvol + D*hw*8)/1e9)
 # plain device copy of the same size for reference
 report("torch_copy_3.2GB", 0, timeit(lambda: volf.copy_(vol)), 2*B*gvol/1e9)

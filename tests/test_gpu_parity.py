@@ -134,6 +134,43 @@ def test_fused_concat_att_filter_vs_oracle(ops, shape, xt_dtype):
     np.testing.assert_allclose(host(n), O.filter_factor(xt, shift, 1.0), rtol=1e-6 if xt_dtype == np.float32 else 1e-14)
 
 
+@pytest.mark.parametrize("xt_dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mask_left", [False, True])
+@pytest.mark.parametrize("shape", [(2, 32, 48, 27, 240), (1, 5, 48, 6, 14), (1, 12, 24, 48, 156), (2, 3, 7, 4, 9)])
+def test_weighted_producer_vs_oracle_and_fused_kernel(ops, shape, mask_left, xt_dtype):
+    """dv_att_softmax_f32 + dv_filter_factor_f32 + dv_concat_volume_weighted_f32 (the DDIM loop's producer)
+    against the oracle, and BIT-identical to the single-kernel fused path (same roundings, same order)."""
+    B, C, D, h, w = shape
+    cl, cr = synth.normal((B, C, h, w), 21), synth.normal((B, C, h, w), 22)
+    att = synth.normal((B, 1, D, h, w), 23) * np.float32(2)
+    xt = (synth.normal((B, D, h, w), 24, dtype=np.float64) * 0.8).astype(xt_dtype)
+    shift = synth.normal((B, D), 25) * np.float32(0.2)
+    att_w = ops.att_softmax(cu(att))
+    np.testing.assert_allclose(host(att_w), O.softmax(att[:, 0], axis=1), rtol=2e-6, atol=1e-9)
+    n = ops.filter_factor(cu(xt), cu(shift), 1.0)
+    np.testing.assert_allclose(host(n), O.filter_factor(xt, shift, 1.0).astype(np.float32), rtol=1e-6, atol=1e-7)
+    concat = O.build_concat_volume(cl, cr, D, mask_left)
+    # plain, att only, n only, both
+    got = host(ops.concat_volume_weighted(cu(cl), cu(cr), D, mask_left=mask_left))
+    np.testing.assert_array_equal(got, concat)
+    got = host(ops.concat_volume_weighted(cu(cl), cu(cr), D, mask_left=mask_left, att_weights=att_w))
+    assert rel_max_err(got, O.acv_attention_volume(att, concat)) < VOL_TOL
+    np.testing.assert_array_equal(got, host(ops.concat_volume(cu(cl), cu(cr), D, mask_left=mask_left, att_logits=cu(att))))
+    got = host(ops.concat_volume_weighted(cu(cl), cu(cr), D, mask_left=mask_left, n=n))
+    assert rel_max_err(got, O.volume_filter(concat, xt, shift, 1.0)) < VOL_TOL
+    want = O.volume_filter(O.acv_attention_volume(att, concat), xt, shift, 1.0)
+    got = host(ops.concat_volume_weighted(cu(cl), cu(cr), D, mask_left=mask_left, att_weights=att_w, n=n))
+    assert rel_max_err(got, want) < VOL_TOL
+    fused = host(ops.concat_volume(cu(cl), cu(cr), D, mask_left=mask_left, att_logits=cu(att), xt=cu(xt), shift=cu(shift)))
+    np.testing.assert_array_equal(got, fused)
+
+
+def test_weighted_producer_rejects_unaligned_plane(ops):
+    cl = cu(synth.normal((1, 2, 3, 7), 1))
+    with pytest.raises(RuntimeError, match="MISALIGNED"):
+        ops.concat_volume_weighted(cl, cl, 4, mask_left=False)
+
+
 # ------------------------------------------------------------------------------------------------
 # a5
 # ------------------------------------------------------------------------------------------------
@@ -274,11 +311,15 @@ def test_ddim_trace_golden(ops, golden):
     used_c = cu(used)
     ens.copy_(used_c * cof[0])
     pairs = sched.time_pairs()
+    n_next = None
     for i, (time, time_next) in enumerate(pairs):
         np.testing.assert_allclose(host(img), golden[f"trace.img.{i}"], atol=1e-3)
         assert host(img).dtype == golden[f"trace.img.{i}"].dtype
         shift = cu(golden[f"trace.shift.t{time}"])
         vol_f = ops.concat_volume(cu(cl), cu(cr), D, mask_left=False, att_logits=cu(att), xt=img, shift=shift)
+        if n_next is not None:   # the factor emitted by the previous fused step drives the weighted producer
+            vol_w = ops.concat_volume_weighted(cu(cl), cu(cr), D, mask_left=False, att_weights=ops.att_softmax(cu(att)), n=n_next)
+            assert torch.equal(vol_w, vol_f)
         c = host(vol_f).mean(axis=1, keepdims=True, dtype=np.float32) * np.float32(2.0)
         cost = O.interpolate_trilinear(c + bias[i], (192, H, W))[:, 0]
         r = ops.softmax_regress(cu(cost), used=used_c, vote_thresholds=(1.0, 3.0), ens_acc=ens, ens_coef=cof[i + 1])
@@ -290,7 +331,8 @@ def test_ddim_trace_golden(ops, golden):
             seed, is64 = rn[2 * i]
             sn = synth.normal((B, D, h, w), int(seed), dtype=np.float64).astype(np.float64 if is64 else np.float32)
             kw = dict(sqrt_alpha_next=san, c=c_, sigma=sigma, step_noise=cu(sn),
-                      renoise=cu(synth.uniform((B, D, h, w), int(ru[i][0]), dtype=np.float64)))
+                      renoise=cu(synth.uniform((B, D, h, w), int(ru[i][0]), dtype=np.float64)),
+                      shift_next=cu(golden[f"trace.shift.t{pairs[i + 1][0]}"]), want_n_next=True)
         st = ops.ddim_step(disp=r["disp"], xt=img, shift=shift, scale=1.0,
                            sqrt_recip=sched.sqrt_recip_alphas_cumprod[time],
                            sqrt_recipm1=sched.sqrt_recipm1_alphas_cumprod[time], last_step=last,
@@ -298,6 +340,7 @@ def test_ddim_trace_golden(ops, golden):
         np.testing.assert_allclose(host(st["x0"]), golden[f"trace.x0.{i}"], atol=2e-4)
         np.testing.assert_allclose(host(st["eps"]), golden[f"trace.eps.{i}"], rtol=1e-6, atol=1e-3)
         img = st["x_next"]
+        n_next = st["n_next"]
     assert 0.2 < float((mask == 0).float().mean()) < 0.8
     assert np.abs(host(ens) - golden["trace.pred"]).max() < 1e-3
 
