@@ -150,12 +150,16 @@ def algorithmic_bytes(B: int, filter_mode: str):
     hw, HW, D = (H // 4) * (W // 4), H * W, MAXDISP // 4
     vol = 2 * C_CAT * D * hw * 4
     state64 = D * hw * 8
+    fmap = D * hw * 4                       # one fp32 [D,h,w] factor map
     per_pair = {
         "gwc_volume": 2 * C_GWC * hw * 4 + G * D * hw * 4,
-        "concat_acv": 2 * C_CAT * hw * 4 + D * hw * 4 + vol,
-        "filter": (2 * C_CAT * hw * 4 + D * hw * 4 + state64 + vol) if filter_mode == "regenerate" else (2 * vol + state64),
+        "concat_acv": 2 * C_CAT * hw * 4 + D * hw * 4 + vol,            # op boundary: features + att logits in, volume out
+        # regenerate: features + the two fp32 factor maps (softmax(att), n) in, volume out; volume: ac_volume + x_t in
+        "filter": (2 * C_CAT * hw * 4 + 2 * fmap + vol) if filter_mode == "regenerate" else (2 * vol + state64),
+        "filter_factor": 2 * fmap,                                      # first step only: x_start (fp32) -> n
         "softmax_regress": MAXDISP * HW * 4 + 5 * HW * 4,      # cost read; used read; disp, vote written; ens read+write
-        "ddim_step": 4 * HW * 2 + D * hw * (8 + 8 + 8 + 4 + 8),  # disp+vote taps; xt, noise, renoise read; x0, x_next written
+        # disp+vote taps; xt, noise, renoise read; x0, x_next (+ next step's n in regenerate mode) written
+        "ddim_step": 4 * HW * 2 + D * hw * (8 + 8 + 8 + 4 + 8) + (fmap if filter_mode == "regenerate" else 0),
     }
     return {k: v * B for k, v in per_pair.items()}
 

@@ -219,19 +219,24 @@ softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__r
 // ---------------------------------------------------------------------------------------------
 // Pipelined variant (the shipped path for 16-byte-aligned maps with D <= 192).
 //
-// A persistent CTA (2 per SM) walks tiles of [D x 64 px] of one batch item.  A dedicated producer warp lands
-// each tile in shared memory with one 256-byte bulk copy per disparity row (cp.async.bulk -> SASS UBLKCP,
-// mbarrier transaction count), STAGES tiles deep, so HBM requests stay in flight while the 8 consumer warps
-// do the arithmetic of earlier tiles — the register-resident kernel above alternates between "all loads"
-// and "all math" per warp and reached only 4.5 TB/s.  Consumers copy their slice of the tile to registers
-// (conflict-free LDS.128: a warp reads two adjacent rows = 512 contiguous bytes) and release the stage at
-// once.  Thread (quad q of 16, slice ds of 16) owns d = 16 j + ds; the constant 16 j folds into FFMA/FADD
-// immediates, the per-thread ds enters once per tile.  Cross-slice reductions: one shuffle + 8-way shared
-// memory combine behind a 256-thread named barrier (the producer warp never joins it).
-template <int NJ, int STAGES, int SPAN, bool TMAP>
+// A persistent CTA (2 per SM) walks tiles of [D x 64 px] of one batch item.  A dedicated producer warp lands each
+// tile in shared memory with ONE tensor-map TMA load (cp.async.bulk.tensor.3d -> SASS UTMALDG, mbarrier
+// transaction count), STAGES tiles deep, so HBM requests stay in flight while the 8 consumer warps do the
+// arithmetic of earlier tiles — the register-resident kernel above alternates between "all loads" and "all math"
+// per warp and reached 4.5 TB/s; per-row 1-D bulk copies (UBLKCP, 256-512 B each) were measured at 2.3 TB/s and
+// dropped.  Consumers copy their slice of the tile to registers (conflict-free LDS.128: a warp reads two adjacent
+// rows = 512 contiguous bytes) and release the stage at once.  Thread (quad q of 16, slice ds of 16) owns
+// d = 16 j + ds; the constant 16 j folds into FFMA/FADD immediates, the per-thread ds enters once per tile.
+// Cross-slice reductions: one shuffle + 8-way shared memory combine behind a 256-thread named barrier (the
+// producer warp never joins it).
+constexpr int kSrSlots = 256;
+static __device__ int g_sr_next[kSrSlots];
+static __device__ int g_sr_done[kSrSlots];
+static std::atomic<unsigned> g_sr_slot{0};
+
+template <int NJ, int STAGES, int SPAN, bool DYN>
 __global__ void __launch_bounds__(288, SPAN == 64 ? 2 : 1)
-softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ cost, int D, int HW,
-                           int spans_per_b, int ntiles,
+softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int HW, int spans_per_b, int ntiles, int slot,
                            float *__restrict__ disp_out, float *__restrict__ prob_out, const float *__restrict__ used,
                            float *__restrict__ unc_out, float *__restrict__ vote_out, float thr_dif, float thr_unc,
                            float *__restrict__ ens_acc, float ens_coef, int ens_init) {
@@ -239,6 +244,7 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float
     extern __shared__ __align__(128) float smem[];              // [STAGES][D][SPAN]
     __shared__ float4 red[4][NW][SQ];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
+    __shared__ int tile_id[STAGES];
     const int stage_floats = D * SPAN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -253,30 +259,31 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float
     __syncthreads();
 
     if (warp == NW) {
-        // ---------------- producer warp
-        int it = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        // ---------------- producer warp (lane 0): one tensor-map TMA per tile, box [SPAN px, D rows, 1] of the
+        // [HW, D, B] view (OOB px read as 0).  Tiles are handed out IN ORDER by an atomic counter (DYN) so that the
+        // spans being read at any moment stay a compact window of the volume (DRAM page locality; the statically
+        // strided assignment lets CTAs drift apart).
+        if (lane != 0) return;
+        for (int it = 0;; ++it) {
             const int s = it % STAGES, k = it / STAGES;
             if (k > 0) mbar_wait(&empty_bar[s], (k & 1) ^ 1);
+            const int t = DYN ? atomicAdd(&g_sr_next[slot], 1) : static_cast<int>(blockIdx.x + it * gridDim.x);
+            if (t >= ntiles) {
+                tile_id[s] = -1;
+                mbar_arrive(&full_bar[s]);
+                if (DYN && atomicAdd(&g_sr_done[slot], 1) == static_cast<int>(gridDim.x) - 1) {
+                    g_sr_next[slot] = 0;   // last CTA out re-arms the counter pair
+                    g_sr_done[slot] = 0;
+                    __threadfence();
+                }
+                return;
+            }
+            tile_id[s] = t;
             const int b = t / spans_per_b;
             const int p0 = (t - b * spans_per_b) * SPAN;
-            float *dst = smem + s * stage_floats;
-            if (TMAP) {
-                // one tensor-map TMA per tile: box [64 px, D rows, 1] of the [HW, D, B] view (OOB px read as 0)
-                if (lane == 0) {
-                    mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(D) * SPAN * 4u);
-                    tma_load_3d(dst, &tmap, p0, 0, b, &full_bar[s]);
-                }
-            } else {
-                const int len = min(SPAN, HW - p0);   // multiple of 4
-                if (lane == 0) mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(D) * len * 4u);
-                __syncwarp();
-                const float *src = cost + static_cast<int64_t>(b) * D * HW + p0;
-                for (int r = lane; r < D; r += 32)
-                    bulk_g2s(dst + r * SPAN, src + static_cast<int64_t>(r) * HW, 4u * len, &full_bar[s]);
-            }
+            mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(D) * SPAN * 4u);
+            tma_load_3d(smem + s * stage_floats, &tmap, p0, 0, b, &full_bar[s]);
         }
-        return;
     }
 
     // ---------------- consumer warps
@@ -285,9 +292,11 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float
     const float dsf = static_cast<float>(ds);
     constexpr float kLog2e = 1.4426950408889634f;
     const bool fin = ds == 0;                  // lanes 0..15 of warp 0 write the span's outputs
-    int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (int it = 0;; ++it) {
         const int s = it % STAGES, k = it / STAGES;
+        mbar_wait(&full_bar[s], k & 1);
+        const int t = tile_id[s];
+        if (t < 0) return;
         const int b = t / spans_per_b;
         const int p0 = (t - b * spans_per_b) * SPAN;
         const int p = p0 + 4 * q;
@@ -298,7 +307,6 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float
             if (vote_out) u4 = ldg_stream(reinterpret_cast<const float4 *>(used + o));
             if (ens_acc && !ens_init) a4 = *reinterpret_cast<const float4 *>(ens_acc + o);
         }
-        mbar_wait(&full_bar[s], k & 1);
         float4 x[NJ];
         {
             const float *st = smem + s * stage_floats + ds * SPAN + 4 * q;
@@ -432,17 +440,18 @@ static int launch_sr_tma(const float *cost, int B, int D, int HW, float *disp_ou
     CUtensorMap tmap;
     const uint64_t dims[3] = {static_cast<uint64_t>(HW), static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
     const uint32_t box[3] = {static_cast<uint32_t>(SPAN), static_cast<uint32_t>(D), 1u};
-    const bool have_map = tune_variant("DV_SR_TMAP", 1) && make_tensor_map_f32(&tmap, cost, 3, dims, box);
-#define DV_LAUNCH(TM)                                                                                                  \
+    if (!make_tensor_map_f32(&tmap, cost, 3, dims, box)) return DV_ERR_UNSUPPORTED;
+    const int slot = static_cast<int>(g_sr_slot.fetch_add(1, std::memory_order_relaxed) % kSrSlots);
+#define DV_LAUNCH(DYN)                                                                                                 \
     {                                                                                                                  \
-        auto kern = softmax_regress_tma_kernel<NJ, STAGES, SPAN, TM>;                                                        \
+        auto kern = softmax_regress_tma_kernel<NJ, STAGES, SPAN, DYN>;                                                 \
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=         \
             cudaSuccess)                                                                                               \
             return DV_ERR_LAUNCH;                                                                                      \
-        kern<<<grid, 288, smem, st>>>(tmap, cost, D, HW, spans, static_cast<int>(ntiles), disp_out, prob_out, used,    \
+        kern<<<grid, 288, smem, st>>>(tmap, D, HW, spans, static_cast<int>(ntiles), slot, disp_out, prob_out, used,    \
                                       unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init);               \
     }
-    if (have_map) DV_LAUNCH(true) else DV_LAUNCH(false)
+    if (tune_variant("DV_SR_DYN", 1)) DV_LAUNCH(true) else DV_LAUNCH(false)
 #undef DV_LAUNCH
     return DV_OK;
 }
@@ -584,8 +593,8 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
         else if (span == 128) rc = launch_sr_tma<24, 2, 128>(DV_SR_TMA_ARGS);
         else rc = launch_sr_tma<12, 2, 64>(DV_SR_TMA_ARGS);
 #undef DV_SR_TMA_ARGS
-        if (rc != DV_OK) return rc;
-        return finish_launch();
+        if (rc == DV_OK) return finish_launch();
+        if (rc != DV_ERR_UNSUPPORTED) return rc;   // no tensor-map encoder: fall through to the register kernel
     }
 #define DV_SR_ARGS cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, st
     if (D <= 48) {

@@ -148,7 +148,10 @@ class AcvHotPath:
         mask = torch.zeros((B, h, w), dtype=torch.float32, device=dev)
         vol_f = self._out("vol_f", (B, 2 * Cc, D, h, w), dev)
         pairs = sched.time_pairs()
-        n = ops.filter_factor(img, shifts[0], sched.scale) if regen else None
+        n = None
+        if regen:
+            with tm("filter_factor"):
+                n = ops.filter_factor(img, shifts[0], sched.scale)
         for i, (t, t_next) in enumerate(pairs):
             shift = shifts[i]
             with tm("filter"):
