@@ -124,7 +124,7 @@ class KernelTimer:
 
 
 # ------------------------------------------------------------------------------------------------
-def make_inputs(B: int, device, seed: int):
+def make_inputs(B: int, device, seed: int, regress: str = "logits"):
     """Synthetic inputs of SURVEY.md §8d, generated on the device with a seeded torch generator."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -135,7 +135,8 @@ def make_inputs(B: int, device, seed: int):
         feat_l=rn(B, C_GWC, h, w), feat_r=rn(B, C_GWC, h, w),
         cfeat_l=rn(B, C_CAT, h, w), cfeat_r=rn(B, C_CAT, h, w),
         att_logits=rn(B, 1, D, h, w),
-        costs=[rn(B, MAXDISP, H, W) * 4.0],            # one 3.2 GB logits buffer, re-read by every step (>> L2)
+        # logits: one 3.2 GB [B,192,H,W] buffer, re-read by every step (>> L2); fused: the quarter-res conv output
+        costs=[rn(B, MAXDISP, H, W) * 4.0] if regress == "logits" else [rn(B, 1, D, h, w) * 4.0],
         used=ru(B, H, W) * 191.0,
         disp_q=ru(B, h, w) * 47.75,
         shifts=[rn(B, D) * 0.1 for _ in range(T_STEPS)],
@@ -145,7 +146,7 @@ def make_inputs(B: int, device, seed: int):
     return inp
 
 
-def algorithmic_bytes(B: int, filter_mode: str):
+def algorithmic_bytes(B: int, filter_mode: str, regress: str = "logits"):
     """Compulsory unique reads + writes per launch, fp32, for a batch of B pairs."""
     hw, HW, D = (H // 4) * (W // 4), H * W, MAXDISP // 4
     vol = 2 * C_CAT * D * hw * 4
@@ -157,7 +158,9 @@ def algorithmic_bytes(B: int, filter_mode: str):
         # regenerate: features + the two fp32 factor maps (softmax(att), n) in, volume out; volume: ac_volume + x_t in
         "filter": (2 * C_CAT * hw * 4 + 2 * fmap + vol) if filter_mode == "regenerate" else (2 * vol + state64),
         "filter_factor": 2 * fmap,                                      # first step only: x_start (fp32) -> n
-        "softmax_regress": MAXDISP * HW * 4 + 5 * HW * 4,      # cost read; used read; disp, vote written; ens read+write
+        # cost read (full-res logits, or the quarter-res conv output when the upsample is fused); used read; disp, vote
+        # written; ens read+write
+        "softmax_regress": (MAXDISP * HW * 4 if regress == "logits" else D * hw * 4) + 5 * HW * 4,
         # disp+vote taps; xt, noise, renoise read; x0, x_next (+ next step's n in regenerate mode) written
         "ddim_step": 4 * HW * 2 + D * hw * (8 + 8 + 8 + 4 + 8) + (fmap if filter_mode == "regenerate" else 0),
     }
@@ -188,8 +191,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     B = args.batch
-    inp = make_inputs(B, dev, seed=1234 + rank)   # rank-offset seeds: every rank owns different pairs
-    path = AcvHotPath(filter_mode=args.filter)
+    regress = "logits" if args.regress == "logits" else "fused_upsample"
+    inp = make_inputs(B, dev, seed=1234 + rank, regress=args.regress)   # rank-offset seeds: every rank owns different pairs
+    path = AcvHotPath(filter_mode=args.filter, regress_mode=regress)
     timer = KernelTimer()
 
     def step(t=None):
@@ -225,7 +229,7 @@ def run_ours(args):
     result = None
     if rank == 0:
         kt = timer.resolve()
-        ab = algorithmic_bytes(B, args.filter)
+        ab = algorithmic_bytes(B, args.filter, args.regress)
         peak, peak_src = measured_peak_gbs()
         kernels = {}
         for name, times in kt.items():
@@ -248,8 +252,10 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]/[4]: gwc G=40 D=48 @135x240 + concat/ACV + T=5 DDIM filter + "
-                                   "softmax/regression over [B,192,540,960]", "pairs_per_gpu": B, "global_batch": B * world,
-                       "filter_mode": args.filter, "l2": "inputs larger than L2 (3.2 GB logits, 3.2 GB volumes per step)",
+                                   + ("softmax/regression over [B,192,540,960]" if args.regress == "logits" else
+                                      "trilinear x4 upsample fused into softmax/regression (input [B,1,48,135,240])"),
+                       "pairs_per_gpu": B, "global_batch": B * world, "filter_mode": args.filter, "regress": args.regress,
+                       "l2": "inputs larger than L2 (3.2 GB logits, 3.2 GB volumes per step)",
                        "parallelism": f"batch-sharded x{world}"},
             "clocks": clk.summary(),
             "gpu_launches": launches,
@@ -262,10 +268,39 @@ def run_ours(args):
         }
     # ---- e2e: the same step through the public API with HOST buffers ------------------------
     e2e = None if args.no_e2e else run_e2e(args, path, inp, dev, barrier, dist, world)
+    # ---- SURVEY.md §8f row f2, reported beside the headline: the same step with F.upsample(trilinear) fused into the
+    # regression kernel (its input is the quarter-res conv output; the full-res logits never exist)
+    fused = None
+    if args.regress == "logits" and not args.no_fused:
+        del inp, path, out
+        torch.cuda.empty_cache()
+        finp = make_inputs(B, dev, seed=1234 + rank, regress="fused")
+        fpath = AcvHotPath(filter_mode=args.filter, regress_mode="fused_upsample")
+        for _ in range(args.warmup):
+            fpath(**finp)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            fpath(**finp)
+        f1.record()
+        barrier()
+        fms = f0.elapsed_time(f1)
+        if dist is not None:
+            tt = torch.tensor([fms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            fms = float(tt.item())
+        fe2e = None if args.no_e2e else run_e2e(args, fpath, finp, dev, barrier, dist, world)
+        fused = {"value": round(B * world / (fms / args.steps / 1e3), 2), "unit": "pairs/s",
+                 "ms_per_step": round(fms / args.steps, 4), "e2e": fe2e,
+                 "note": "same step with the trilinear x4 upsample fused into softmax/regression (SURVEY.md 8f row f2): "
+                         "per-step input [B,1,48,135,240] instead of [B,192,540,960]"}
     if rank == 0:
         result["e2e"] = e2e
+        if fused is not None:
+            result["fused_upsample"] = fused
         if world == 1 and not args.no_cpu_baseline:
-            result["cpu_baseline"] = cpu_reference(steps=args.cpu_steps, warmup=1)
+            result["cpu_baseline"] = cpu_reference(steps=args.cpu_steps, warmup=1, regress=args.regress)
         print(json.dumps(result))
     if dist is not None:
         dist.destroy_process_group()
@@ -282,7 +317,7 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
         host[k] = [t.cpu().pin_memory() for t in inp[k]]
     pred_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
     h2d = sum(host[k].numel() * host[k].element_size() for k in names)
-    h2d += T_STEPS * host["costs"][0].numel() * 4      # the logits of each of the T steps are step inputs
+    h2d += T_STEPS * host["costs"][0].numel() * 4      # the cost tensor of each of the T steps is a step input
     h2d += sum(t.numel() * t.element_size() for k in ("shifts", "step_noises", "renoises") for t in host[k])
     d2h = pred_host.numel() * 4
     dst = {k: torch.empty_like(inp[k]) for k in names}
@@ -323,11 +358,11 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
         ms = float(tt.item())
     return {"value": round(B * world * steps / (ms / 1e3), 2), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": round(ms / steps, 3),
-            "note": "pinned host inputs incl. the T=5 per-step [B,192,540,960] logits; PCIe-bound"}
+            "note": f"pinned host inputs incl. the T=5 per-step {list(host['costs'][0].shape)} cost tensors; PCIe-bound"}
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(steps: int, warmup: int):
+def cpu_reference(steps: int, warmup: int, regress: str = "logits"):
     """The reference's op sequence on the host CPU (oracle/torch_port.py), one pair (B=1) per step."""
     from oracle import dv_oracle as O
     from oracle import torch_port as P
@@ -338,24 +373,26 @@ def cpu_reference(steps: int, warmup: int):
     rn = lambda *s, dt=torch.float32: torch.randn(*s, generator=g, dtype=dt)
     sched = O.Schedule()
     a = dict(feat_l=rn(1, C_GWC, h, w), feat_r=rn(1, C_GWC, h, w), cfeat_l=rn(1, C_CAT, h, w), cfeat_r=rn(1, C_CAT, h, w),
-             att_logits=rn(1, 1, D, h, w), costs=[rn(1, MAXDISP, H, W) * 4.0] * T_STEPS,
+             att_logits=rn(1, 1, D, h, w),
+             costs=([rn(1, MAXDISP, H, W) * 4.0] if regress == "logits" else [rn(1, 1, D, h, w) * 4.0]) * T_STEPS,
              used=torch.rand(1, H, W, generator=g) * 191.0,
              asd=P.xstart_from_pred(torch.rand(1, H, W, generator=g) * 191.0),
              shifts=[rn(1, D) * 0.1 for _ in range(T_STEPS)],
              step_noises=[rn(1, D, h, w, dt=torch.float32 if i == 0 else torch.float64) for i in range(T_STEPS - 1)],
              renoises=[torch.rand(1, D, h, w, generator=g, dtype=torch.float64) for _ in range(T_STEPS - 1)])
+    up = None if regress == "logits" else (MAXDISP, H, W)
     with torch.no_grad():
         for _ in range(warmup):
-            P.hot_path_pair(**a, sched=sched)
+            P.hot_path_pair(**a, sched=sched, upsample_to=up)
         ts = []
         for _ in range(steps):
             t0 = time.perf_counter()
-            P.hot_path_pair(**a, sched=sched)
+            P.hot_path_pair(**a, sched=sched, upsample_to=up)
             ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
     return {"value": round(1.0 / sec, 4), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} x 1 pair (B=1, all T=5 steps, 540x960 D=192), torch CPU op-for-op port of the reference "
-                      f"(oracle/torch_port.py), {sec:.2f} s/pair",
+            "sample": f"{steps} x 1 pair (B=1, all T=5 steps, 540x960 D=192{'' if regress == 'logits' else ', incl. F.upsample trilinear per step'}), "
+                      f"torch CPU op-for-op port of the reference (oracle/torch_port.py), {sec:.2f} s/pair",
             "seconds_per_pair": round(sec, 3)}
 
 
@@ -363,13 +400,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_reference(steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+    cb = cpu_reference(steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)), regress=args.regress)
     v = cb["value"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 / v, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "same hot path, 1 pair per step on the host CPU", "pairs_per_step": 1},
+        "config": {"workload": "same hot path, 1 pair per step on the host CPU", "pairs_per_step": 1, "regress": args.regress},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -384,6 +421,10 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=8, help="stereo pairs per GPU per step")
     ap.add_argument("--filter", choices=["regenerate", "volume"], default="regenerate")
+    ap.add_argument("--regress", choices=["logits", "fused"], default="logits",
+                    help="logits: softmax/regression reads the full-res [B,192,H,W] logits (the metric's op boundary); "
+                         "fused: trilinear x4 upsample fused in, input [B,1,48,h,w] (SURVEY.md 8f row f2)")
+    ap.add_argument("--no-fused", action="store_true", help="skip the extra fused-upsample measurement")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -278,6 +278,43 @@ def softmax_regress(cost: torch.Tensor, *, return_prob: bool = False, used: Opti
     return res
 
 
+def upsample_softmax_regress(cost_q: torch.Tensor, size: Sequence[int], *, align_corners: bool = False,
+                             used: Optional[torch.Tensor] = None, want_unc: bool = False,
+                             vote_thresholds: Optional[Sequence[float]] = None,
+                             ens_acc: Optional[torch.Tensor] = None, ens_coef: float = 0.0, ens_init: bool = False):
+    """f2 — `F.upsample(cost_q, size, mode='trilinear')` + softmax over D + disparity regression (+ uncertainty, vote,
+    ensemble accumulate) without materialising the [B,D,H,W] logits (acv_ddim.py:267-270, pwcnet_ddim.py:480-484).
+    cost_q is [B,1,Dq,h,w] or [B,Dq,h,w]; size = (D, H, W).  Returns the same dict as `softmax_regress` (no 'prob')."""
+    if cost_q.dim() == 5:
+        assert cost_q.shape[1] == 1
+        cost_q = cost_q[:, 0]
+    assert cost_q.dim() == 4 and len(size) == 3
+    B, Dq, h, w = cost_q.shape
+    D, H, W = (int(v) for v in size)
+    _need_cuda(cost_q, used, ens_acc)
+    cost_q = _f32c(cost_q, "cost_q")
+    dev = cost_q.device
+    res = {"disp": torch.empty((B, H, W), dtype=torch.float32, device=dev)}
+    if want_unc:
+        res["unc"] = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    thr_dif = thr_unc = 0.0
+    if vote_thresholds is not None:
+        if used is None:
+            raise DvLibraryError("vote needs `used`")
+        used = _f32c(used.reshape(B, H, W), "used")
+        thr_dif, thr_unc = float(vote_thresholds[0]), float(vote_thresholds[1])
+        res["vote"] = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    if ens_acc is not None:
+        assert ens_acc.dtype == torch.float32 and ens_acc.is_contiguous() and ens_acc.numel() == B * H * W
+    with torch.cuda.device(dev):
+        check(_lib.lib().dv_upsample_softmax_regress_f32(_ptr(cost_q), B, Dq, h, w, D, H, W, int(align_corners),
+                                                         _ptr(res["disp"]), _ptr(used), _ptr(res.get("unc")),
+                                                         _ptr(res.get("vote")), thr_dif, thr_unc, _ptr(ens_acc),
+                                                         float(ens_coef), int(ens_init), _stream(cost_q)),
+              "dv_upsample_softmax_regress_f32")
+    return res
+
+
 def uncertainty_vote(disp: torch.Tensor, prob: torch.Tensor, used: Optional[torch.Tensor], thr_dif: float,
                      thr_unc: float, return_unc: bool = False):
     """a11 — sum_d |disp - d| * prob[d] and the renewal vote for a disparity that is not the regression of

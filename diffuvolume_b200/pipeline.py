@@ -91,12 +91,20 @@ class AcvHotPath:
       'volume'     — each step multiplies the materialised ac_volume (reads 404 MB, writes 398 MB):
                      the reference's own op boundary (acv_ddim.py:260).
     Both produce bit-identical volumes (same roundings in the same order).
+
+    regress_mode:
+      'logits'         — costs[i] are the full-resolution logits [B,maxdisp,H,W] (the output of F.upsample in
+                         acv_ddim.py:267): the op boundary BASELINE.json's metric is defined on;
+      'fused_upsample' — costs[i] are the quarter-resolution outputs [B,1,D,h,w] of the last 3-D conv and the
+                         trilinear x4 upsample is fused into the regression kernel.
     """
 
     def __init__(self, schedule: Optional[DdimSchedule] = None, num_groups: int = 40, maxdisp: int = 192,
                  filter_mode: str = "regenerate", ensemble: Sequence[float] = ACV_ENSEMBLE,
-                 thr_dif: float = 1.0, thr_unc: float = 3.0):
+                 thr_dif: float = 1.0, thr_unc: float = 3.0, regress_mode: str = "logits"):
         assert filter_mode in ("regenerate", "volume")
+        assert regress_mode in ("logits", "fused_upsample")
+        self.regress_mode = regress_mode
         self.sched = schedule or DdimSchedule()
         self.G = num_groups
         self.maxdisp = maxdisp
@@ -162,8 +170,12 @@ class AcvHotPath:
             # (3-D conv aggregation of vol_f happens here in the full network — out of scope)
             cost = costs(i) if callable(costs) else costs[i if len(costs) > 1 else 0]
             with tm("softmax_regress"):
-                r = ops.softmax_regress(cost, used=used, vote_thresholds=self.thr, ens_acc=ens,
-                                        ens_coef=self.cof[i + 1])
+                if self.regress_mode == "fused_upsample":
+                    r = ops.upsample_softmax_regress(cost, (self.maxdisp, H, W), used=used, vote_thresholds=self.thr,
+                                                     ens_acc=ens, ens_coef=self.cof[i + 1])
+                else:
+                    r = ops.softmax_regress(cost, used=used, vote_thresholds=self.thr, ens_acc=ens,
+                                            ens_coef=self.cof[i + 1])
             last = t_next < 0
             kw = {}
             if not last:

@@ -92,14 +92,18 @@ def predict_noise_from_start(self, x_t, t, x0):
 # ------------------------------------------------------------------------------------------------
 # ACVNet_DDIM
 # ------------------------------------------------------------------------------------------------
-def _acv_aggregate(self, volume_f, h, w):
-    """The reference's 3-D conv stack + trilinear upsample (acv_ddim.py:261-268) — unchanged PyTorch."""
+def _acv_convs(self, volume_f):
+    """The reference's 3-D conv stack (acv_ddim.py:261-266) — unchanged PyTorch; returns classif2's [B,1,D,h,w]."""
     cost0 = self.dres0(volume_f)
     cost0 = self.dres1(cost0) + cost0
     out1 = self.dres2(cost0)
     out2 = self.dres3(out1)
-    cost_v = self.classif2(out2)
-    cost2 = F.interpolate(cost_v, [self.maxdisp, h * 4, w * 4], mode="trilinear")
+    return self.classif2(out2)
+
+
+def _acv_aggregate(self, volume_f, h, w):
+    """Conv stack + trilinear upsample to the full-resolution logits (acv_ddim.py:261-268)."""
+    cost2 = F.interpolate(_acv_convs(self, volume_f), [self.maxdisp, h * 4, w * 4], mode="trilinear")
     return torch.squeeze(cost2, 1)
 
 
@@ -144,11 +148,13 @@ def acv_ddim_sample(self, volume, used, asd):
         time_cond = torch.full((batch,), time, device=dev, dtype=torch.long)
         shift = _time_shift(self, time_cond, batch, depth, dev)
         vol_f = ops.volume_filter(volume, img, shift, self.scale)
-        cost2 = _acv_aggregate(self, vol_f, h, w)
+        cost_v = _acv_convs(self, vol_f)
         del vol_f
-        r = ops.softmax_regress(cost2, used=used if self.renewal else None,
-                                vote_thresholds=(1.0, 3.0) if self.renewal else None,
-                                ens_acc=ens, ens_coef=cof[i + 1] if ens is not None else 0.0)
+        # F.upsample(trilinear) + softmax + regression + uncertainty + vote in one kernel: the [B,192,H,W] logits and
+        # the probability volume of acv_ddim.py:267-270, :324-329 are never materialised (ddim_sample does not return them)
+        r = ops.upsample_softmax_regress(cost_v, (self.maxdisp, h * 4, w * 4), used=used if self.renewal else None,
+                                         vote_thresholds=(1.0, 3.0) if self.renewal else None,
+                                         ens_acc=ens, ens_coef=cof[i + 1] if ens is not None else 0.0)
         disp = r["disp"]
         disps.append(disp)
         last = time_next < 0

@@ -128,6 +128,17 @@ int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, int64_t H, i
                            float *ens_acc, float ens_coef, int ens_init,
                            void *stream);
 
+/* ---- f2: F.upsample(..., mode='trilinear') fused into a6 (+a11 +a13)
+ *          (SceneFlow/models/acv_ddim.py:267-270 align_corners=False; KITTI12/models/pwcnet_ddim.py:480-484 True)
+ * cost_q [B,Dq,h,w] (the squeezed [B,1,Dq,h,w] output of the last 3-D conv) is interpolated to [B,D,H,W] on the fly
+ * (ATen upsample_trilinear3d index/lambda rules) and reduced exactly like dv_softmax_regress_f32: the
+ * full-resolution logits are never materialised.  Optional outputs as above (no prob_out: that IS the volume).      */
+int dv_upsample_softmax_regress_f32(const float *cost_q, int64_t B, int64_t Dq, int64_t h, int64_t w,
+                                    int64_t D, int64_t H, int64_t W, int align_corners,
+                                    float *disp_out, const float *used, float *unc_out, float *vote_out,
+                                    float thr_dif, float thr_unc,
+                                    float *ens_acc, float ens_coef, int ens_init, void *stream);
+
 /* ---- a11 alone: uncertainty + renewal vote of a disparity map against a given probability volume
  *          (KITTI12/models/pwcnet_ddim.py:553-570 — the REFINED disparity vs the pre-refinement softmax)
  * unc[b,p] = sum_d |disp[b,p] - d| * prob[b,d,p];  vote = (|disp-used| < thr_dif  [if used]) && unc < thr_unc  */

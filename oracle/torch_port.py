@@ -96,11 +96,12 @@ def xstart_from_pred(pred: torch.Tensor, maxdisp: int = 192, D: int = 48, scale:
 def hot_path_pair(feat_l, feat_r, cfeat_l, cfeat_r, att_logits, costs: Sequence[torch.Tensor], used, asd,
                   shifts: Sequence[torch.Tensor], step_noises: Sequence[torch.Tensor],
                   renoises: Sequence[torch.Tensor], sched, cof=(0.5, 0.0, 0.0, 0.0, 0.2, 0.3),
-                  D: int = 48, G: int = 40) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+                  D: int = 48, G: int = 40, upsample_to=None) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """One "pair" of BASELINE.json's metric with the reference's op sequence: 1x gwc volume, 1x concat + ACV
     multiply, then T x {filter multiply, softmax + regression, uncertainty + vote, x_start, pred_noise,
     DDIM update, re-noise}, and the ensemble.  The conv stack is replaced by nothing:
-    `costs[i]` are the synthetic logits standing in for its output at step i.  `sched` is an
+    `costs[i]` are the synthetic logits standing in for its output at step i (or, with `upsample_to`, the quarter-res
+    conv output that the reference upsamples first).  `sched` is an
     oracle.dv_oracle.Schedule (host-side float64 constants)."""
     gwc = gwc_volume(feat_l, feat_r, D, G)
     ac = acv_volume(att_logits, concat_volume(cfeat_l, cfeat_r, D, mask_left=False))
@@ -112,8 +113,11 @@ def hot_path_pair(feat_l, feat_r, cfeat_l, cfeat_r, att_logits, costs: Sequence[
     for i, (t, t_next) in enumerate(pairs):
         vol_f, n = filter_volume(ac, img, shifts[i], sched.scale)
         del vol_f  # consumed by the (out-of-scope) 3-D convs
-        disp, prob = softmax_regress(costs[i])
-        x0 = xstart_from_pred(disp, costs[i].shape[1], D, sched.scale)
+        cost = costs[i]
+        if upsample_to is not None:   # acv_ddim.py:267-268: F.upsample(cost_v, [maxdisp, 4h, 4w], mode='trilinear'), squeeze
+            cost = torch.squeeze(F.interpolate(cost, list(upsample_to), mode="trilinear"), 1)
+        disp, prob = softmax_regress(cost)
+        x0 = xstart_from_pred(disp, cost.shape[1], D, sched.scale)
         eps = (float(sched.sqrt_recip_alphas_cumprod[t]) * n.double() - x0) / float(sched.sqrt_recipm1_alphas_cumprod[t])
         final.append(disp)
         vote = renewal_vote(disp, used, prob)

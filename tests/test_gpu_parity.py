@@ -230,6 +230,38 @@ def test_softmax_regress_full_vs_oracle(ops, shape):
     np.testing.assert_allclose(host(ens), ens0 + np.float32(0.3) * disp_o, atol=1e-3)
 
 
+@pytest.mark.parametrize("case", [
+    # (B, Dq, h, w, D, H, W, align_corners)
+    (2, 48, 9, 20, 192, 36, 80, False),      # the ACVNet call: x4 in every axis -> register fast path
+    (1, 48, 7, 13, 192, 28, 52, False),      # fast path, ragged CTA tiles
+    (1, 48, 9, 20, 192, 36, 80, True),       # PCWNet: align_corners=True (pwcnet_ddim.py:480) -> table path
+    (1, 12, 5, 9, 48, 20, 36, False),        # other Dq
+    (1, 48, 6, 10, 192, 22, 39, False),      # sizes that are not multiples (F.upsample accepts any size)
+    (2, 7, 3, 5, 19, 11, 17, True),
+])
+def test_upsample_softmax_regress_vs_oracle(ops, case):
+    B, Dq, h, w, D, H, W, ac = case
+    cq = synth.normal((B, 1, Dq, h, w), 91) * np.float32(5)
+    used = synth.uniform((B, H, W), 92, dtype=np.float32) * np.float32(D - 1)
+    cost = O.interpolate_trilinear(cq, (D, H, W), align_corners=ac)[:, 0]
+    disp, prob = O.softmax_regress(cost)
+    unc = O.uncertainty(disp, prob)
+    ens0 = synth.normal((B, H, W), 93)
+    ens = cu(ens0.copy())
+    r = ops.upsample_softmax_regress(cu(cq), (D, H, W), align_corners=ac, used=cu(used), want_unc=True,
+                                     vote_thresholds=(1.0, 3.0), ens_acc=ens, ens_coef=0.3)
+    assert np.abs(host(r["disp"]) - disp).max() < 1e-3
+    assert np.abs(host(r["unc"]) - unc).max() < 1e-3
+    vote = O.renewal_vote(disp, used, unc, 1.0, 3.0)
+    borderline = (np.abs(np.abs(disp - used) - 1.0) < 2e-3) | (np.abs(unc - 3.0) < 2e-3)
+    assert np.array_equal(host(r["vote"])[~borderline], vote[~borderline])
+    assert np.abs(host(ens) - (ens0 + np.float32(0.3) * disp)).max() < 1e-3
+    # disparity only, and agreement with the unfused CUDA path on the materialised logits
+    r2 = ops.upsample_softmax_regress(cu(cq), (D, H, W), align_corners=ac)
+    r3 = ops.softmax_regress(cu(cost))
+    assert np.abs(host(r2["disp"]) - host(r3["disp"])).max() < 1e-3
+
+
 def test_softmax_regress_big_golden(ops, golden):
     cost = synth.normal((1, 192, 135, 240), 92) * np.float32(4)
     r = ops.softmax_regress(cu(cost), want_unc=True)

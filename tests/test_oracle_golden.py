@@ -209,3 +209,18 @@ def test_big_shape_checksums(golden):
     disp, prob = O.softmax_regress(cost, 192)
     assert np.abs(disp - golden["big.regress.disp"]).max() < 5e-4
     assert np.abs(O.uncertainty(disp, prob) - golden["big.regress.unc"]).max() < 5e-4
+
+
+@pytest.mark.parametrize("align_corners", [False, True])
+@pytest.mark.parametrize("shape,size", [((1, 1, 48, 9, 20), (192, 36, 80)), ((2, 1, 7, 3, 5), (19, 11, 17)),
+                                        ((1, 1, 12, 6, 10), (48, 22, 39))])
+def test_oracle_trilinear_matches_torch(shape, size, align_corners):
+    """F.upsample(..., mode='trilinear') lives in PyTorch (torch 2.11 here; the reference pins 2.0 — README.md:25):
+    the oracle's restatement of upsample_trilinear3d is pinned against torch itself on CPU (acv_ddim.py:267,
+    pwcnet_ddim.py:480)."""
+    import torch
+    import torch.nn.functional as F
+    x = synth.normal(shape, 77) * np.float32(3)
+    want = F.interpolate(torch.from_numpy(x), size=size, mode="trilinear", align_corners=align_corners).numpy()
+    got = O.interpolate_trilinear(x, size, align_corners=align_corners)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
