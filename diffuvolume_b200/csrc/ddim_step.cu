@@ -126,42 +126,72 @@ ddim_step_kernel(const dv_ddim_step_args a) {
     const XT *xt = static_cast<const XT *>(a.xt);
     const XT *sn = static_cast<const XT *>(a.step_noise);
 
-    for (int d = dg; d < D; d += kDdimDg) {
-        const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
-        const float x0 = x0_from_tap(tap, d, D, s32);
-        a.x0_out[e] = x0;
-        // a8: pred_noise from the time-embedded, clamped, renormalised state (fp64)
-        const XT n = filter_n<XT>(xt[e], a.shift ? a.shift[b * D + d] : 0.0f, sX);
-        const double eps = (a.sqrt_recip * static_cast<double>(n) - static_cast<double>(x0)) / a.sqrt_recipm1;
-        if (a.eps_out) a.eps_out[e] = eps;
-        if (a.last_step) {
-            static_cast<float *>(a.x_next)[e] = x0;  // img = x_start (fp32)
-            continue;
+    // UN hypotheses per pass: every global load of the pass is issued before its first store (the output pointers
+    // are not provably distinct from the inputs, so without the explicit batching each iteration would serialise
+    // load -> math -> store and the kernel is latency-bound: ncu r01, long-scoreboard 20 cycles per issue)
+    constexpr int UN = 3;
+    for (int d0 = dg; d0 < D; d0 += UN * kDdimDg) {
+        XT xv[UN], snv[UN];
+        double rzv[UN], asv[UN], qnv[UN];
+        float shv[UN], shn[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int d = d0 + u * kDdimDg;
+            xv[u] = static_cast<XT>(0); snv[u] = static_cast<XT>(0); rzv[u] = 0.0; asv[u] = 0.0; qnv[u] = 0.0;
+            shv[u] = 0.0f; shn[u] = 0.0f;
+            if (d < D) {
+                const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
+                xv[u] = xt[e];
+                if (a.shift) shv[u] = a.shift[b * D + d];
+                if (!a.last_step) {
+                    snv[u] = sn[e];
+                    if (a.n_next_out && a.shift_next) shn[u] = a.shift_next[b * D + d];
+                    if (a.renoise_mode == 1) {
+                        if (renoise_px) rzv[u] = static_cast<const double *>(a.renoise)[e];
+                    } else if (a.renoise_mode == 2) {
+                        asv[u] = a.asd_is_f64 ? static_cast<const double *>(a.asd)[e]
+                                              : static_cast<double>(static_cast<const float *>(a.asd)[e]);
+                        qnv[u] = a.q_noise_is_f64 ? static_cast<const double *>(a.q_noise)[e]
+                                                  : static_cast<double>(static_cast<const float *>(a.q_noise)[e]);
+                    }
+                }
+            }
         }
-        // a12: img = x0 * sqrt(alpha_next) + c * eps + sigma * noise
-        const float t1 = __fmul_rn(x0, san32);
-        const double t2 = a.c * eps;
-        double t3;
-        if constexpr (sizeof(XT) == 4)
-            t3 = static_cast<double>(__fmul_rn(sig32, static_cast<float>(sn[e])));
-        else
-            t3 = a.sigma * static_cast<double>(sn[e]);
-        double img = (static_cast<double>(t1) + t2) + t3;
-        if (a.renoise_mode == 1) {
-            if (renoise_px) img = static_cast<const double *>(a.renoise)[e];
-        } else if (a.renoise_mode == 2) {
-            const double as = a.asd_is_f64 ? static_cast<const double *>(a.asd)[e]
-                                           : static_cast<double>(static_cast<const float *>(a.asd)[e]);
-            const double qn = a.q_noise_is_f64 ? static_cast<const double *>(a.q_noise)[e]
-                                               : static_cast<double>(static_cast<const float *>(a.q_noise)[e]);
-            const double rn = a.sqrt_ac * as + a.sqrt_1m_ac * qn;   // q_sample(asd, t)
-            if (a.asd_out) a.asd_out[e] = rn;
-            if (renoise_px) img = rn;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int d = d0 + u * kDdimDg;
+            if (d >= D) break;
+            const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
+            const float x0 = x0_from_tap(tap, d, D, s32);
+            a.x0_out[e] = x0;
+            // a8: pred_noise from the time-embedded, clamped, renormalised state (fp64)
+            const XT n = filter_n<XT>(xv[u], shv[u], sX);
+            const double eps = (a.sqrt_recip * static_cast<double>(n) - static_cast<double>(x0)) / a.sqrt_recipm1;
+            if (a.eps_out) a.eps_out[e] = eps;
+            if (a.last_step) {
+                static_cast<float *>(a.x_next)[e] = x0;  // img = x_start (fp32)
+                continue;
+            }
+            // a12: img = x0 * sqrt(alpha_next) + c * eps + sigma * noise
+            const float t1 = __fmul_rn(x0, san32);
+            const double t2 = a.c * eps;
+            double t3;
+            if constexpr (sizeof(XT) == 4)
+                t3 = static_cast<double>(__fmul_rn(sig32, static_cast<float>(snv[u])));
+            else
+                t3 = a.sigma * static_cast<double>(snv[u]);
+            double img = (static_cast<double>(t1) + t2) + t3;
+            if (a.renoise_mode == 1) {
+                if (renoise_px) img = rzv[u];
+            } else if (a.renoise_mode == 2) {
+                const double rn = a.sqrt_ac * asv[u] + a.sqrt_1m_ac * qnv[u];   // q_sample(asd, t)
+                if (a.asd_out) a.asd_out[e] = rn;
+                if (renoise_px) img = rn;
+            }
+            static_cast<double *>(a.x_next)[e] = img;
+            // the next step's filter factor from the fp64 state just produced (acv_ddim.py:256-258 of the next iteration)
+            if (a.n_next_out) a.n_next_out[e] = static_cast<float>(filter_n<double>(img, shn[u], a.scale));
         }
-        static_cast<double *>(a.x_next)[e] = img;
-        // the next step's filter factor from the fp64 state just produced (acv_ddim.py:256-258 of the next iteration)
-        if (a.n_next_out)
-            a.n_next_out[e] = static_cast<float>(filter_n<double>(img, a.shift_next ? a.shift_next[b * D + d] : 0.0f, a.scale));
     }
 }
 

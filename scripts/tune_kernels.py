@@ -81,7 +81,7 @@ for cg, ver, bar in ((8, 31, 0), (8, 31, 1), (16, 31, 0), (16, 31, 1), (8, 21, 0
     report("weighted_plain", cg, timeit(lambda: ops.concat_volume_weighted(cl, cr, D, mask_left=False, out=vol)), B*(64*hw*4 + gvol)/1e9)
     report("weighted_acv", cg, timeit(lambda: ops.concat_volume_weighted(cl, cr, D, mask_left=False, att_weights=att_w, out=vol)), B*(64*hw*4 + D*hw*4 + gvol)/1e9)
     report("weighted_filter", cg, timeit(lambda: ops.concat_volume_weighted(cl, cr, D, mask_left=False, att_weights=att_w, n=nf, out=volf)), B*(64*hw*4 + D*hw*8 + gvol)/1e9)
-os.environ.pop("DV_CONCAT_CG"); os.environ.pop("DV_CS_CGT"); os.environ.pop("DV_CS_SHAPE"); os.environ.pop("DV_CS_BAR")
+[os.environ.pop(k, None) for k in ("DV_CONCAT_CG", "DV_CS_CGT", "DV_CS_SHAPE", "DV_CS_BAR")]
 report("filter_volume_f64", 0, timeit(lambda: ops.volume_filter(vol, xt64, shift, 1.0, out=volf)), B*(2*gvol + D*hw*8)/1e9)
 # plain device copy of the same size for reference
 report("torch_copy_3.2GB", 0, timeit(lambda: volf.copy_(vol)), 2*B*gvol/1e9)
