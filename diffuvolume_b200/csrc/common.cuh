@@ -148,6 +148,12 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
     return v;
 }
 
+__device__ __forceinline__ float ldg_stream_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // n = ((clamp(xt + shift, -s, s) / s) + 1) / 2 in the dtype of xt, then float()
 // (SceneFlow/models/acv_ddim.py:256-260)
 template <typename T>

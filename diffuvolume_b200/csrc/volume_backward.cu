@@ -1,0 +1,277 @@
+// volume_backward.cu — backward passes of the volume ops for sm_100a.
+//
+// The reference's training scripts differentiate through build_gwc_volume / build_concat_volume /
+// build_corrleation_volume / groupwise_correlation / disparity_regression (SceneFlow/main.py:154 ->
+// SceneFlow/models/acv_ddim.py:424-482; KITTI12/main.py, KITTI15/train_stereo.py); autograd runs their backward as
+// D x {slice, mul, sum, index_put} chains over [B,C,H,W-d] temporaries.  Here each gradient is ONE pass:
+//
+//   gwc  : d_ref[c,p] = 1/cpg * sum_d  g[grp,d,p]   * tgt[c,p-d]   (x(p) >= d)
+//          d_tgt[c,p] = 1/cpg * sum_d  g[grp,d,p+d] * ref[c,p+d]   (x(p)+d < W)
+//          thread = (b, group, pixel) keeps the 2 x cpg channel accumulators in registers, so the gradient volume is
+//          read exactly twice (once per operand; coalesced along x), the features come from L1/L2.
+//   concat: d_ref[c,p] = sum_d g[c,d,p] (x >= d when the left half is masked); d_tgt[c,p] = sum_d g[C+c,d,p+d]
+//          every gradient element is read exactly once (pure HBM read stream, D independent loads per thread).
+//   regression: d_x[b,d,p] = d * g[b,p]   (pure 128-bit write stream).
+//
+// All planes are addressed flattened (p = y*W + x); a shift that leaves the row is a masked term, exactly mirroring the
+// forward kernels (gwc_volume.cu, concat_volume.cu).  No atomics: every output element has one owner thread.
+#include "common.cuh"
+
+namespace dv {
+
+// grad_out [B,G,Dtot,HW]; non-negative shifts d in [0,D) live at planes dofs+d; when mneg > 0 the planes [0,mneg)
+// hold the negative shifts of build_corrleation_volume (slot s <-> k = mneg - s; only columns x < k are live and pair
+// ref[x] with tgt[x + max(W-k,0)], KITTI12/models/submodule.py:128-131).
+template <int CPG>
+__global__ void __launch_bounds__(128)
+gwc_bwd_kernel(const float *__restrict__ go, const float *__restrict__ ref, const float *__restrict__ tgt,
+               float *__restrict__ gref, float *__restrict__ gtgt, int C, int HW, int W, int D, int G, int Dtot, int dofs,
+               int mneg) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int g = blockIdx.y, b = blockIdx.z;
+    const int x = p % W;
+    const float *gp = go + (static_cast<int64_t>(b) * G + g) * Dtot * HW;
+    const int64_t fb = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * CPG) * HW;
+    const float *rp = ref + fb, *tp = tgt + fb;
+    float ar[CPG], at[CPG];
+#pragma unroll
+    for (int k = 0; k < CPG; ++k) ar[k] = at[k] = 0.0f;
+    const int dmax_r = min(D - 1, x);            // x >= d
+    const int dmax_t = min(D - 1, W - 1 - x);    // x + d < W
+    if (gref) {
+#pragma unroll 4
+        for (int d = 0; d <= dmax_r; ++d) {
+            const float gv = __ldg(gp + static_cast<int64_t>(dofs + d) * HW + p);
+#pragma unroll
+            for (int k = 0; k < CPG; ++k) ar[k] = fmaf(gv, __ldg(tp + static_cast<int64_t>(k) * HW + p - d), ar[k]);
+        }
+        for (int s = 0; s < mneg; ++s) {
+            const int kk = mneg - s;
+            if (x < kk) {
+                const int off = max(W - kk, 0);
+                const float gv = __ldg(gp + static_cast<int64_t>(s) * HW + p);
+#pragma unroll
+                for (int k = 0; k < CPG; ++k) ar[k] = fmaf(gv, __ldg(tp + static_cast<int64_t>(k) * HW + p + off), ar[k]);
+            }
+        }
+    }
+    if (gtgt) {
+#pragma unroll 4
+        for (int d = 0; d <= dmax_t; ++d) {
+            const float gv = __ldg(gp + static_cast<int64_t>(dofs + d) * HW + p + d);
+#pragma unroll
+            for (int k = 0; k < CPG; ++k) at[k] = fmaf(gv, __ldg(rp + static_cast<int64_t>(k) * HW + p + d), at[k]);
+        }
+        for (int s = 0; s < mneg; ++s) {
+            const int kk = mneg - s;
+            const int off = max(W - kk, 0);
+            const int xs = x - off;              // the ref column paired with this tgt column
+            if (xs >= 0 && xs < kk) {
+                const float gv = __ldg(gp + static_cast<int64_t>(s) * HW + p - off);
+#pragma unroll
+                for (int k = 0; k < CPG; ++k) at[k] = fmaf(gv, __ldg(rp + static_cast<int64_t>(k) * HW + p - off), at[k]);
+            }
+        }
+    }
+    constexpr float inv = 1.0f / CPG;
+#pragma unroll
+    for (int k = 0; k < CPG; ++k) {
+        if (gref) gref[fb + static_cast<int64_t>(k) * HW + p] = ar[k] * inv;
+        if (gtgt) gtgt[fb + static_cast<int64_t>(k) * HW + p] = at[k] * inv;
+    }
+}
+
+// any channels-per-group: thread = (b, channel, pixel)
+__global__ void gwc_bwd_generic_kernel(const float *__restrict__ go, const float *__restrict__ ref,
+                                       const float *__restrict__ tgt, float *__restrict__ gref, float *__restrict__ gtgt,
+                                       int C, int HW, int W, int D, int G, int cpg, int Dtot, int dofs, int mneg,
+                                       int64_t total) {
+    const float inv = 1.0f / static_cast<float>(cpg);
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(idx % HW);
+        const int64_t bc = idx / HW;
+        const int c = static_cast<int>(bc % C);
+        const int64_t b = bc / C;
+        const int g = c / cpg, x = p % W;
+        const float *gp = go + (b * G + g) * Dtot * HW;
+        const float *rp = ref + bc * HW, *tp = tgt + bc * HW;
+        float ar = 0.0f, at = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            if (x >= d) ar = fmaf(gp[static_cast<int64_t>(dofs + d) * HW + p], tp[p - d], ar);
+            if (x + d < W) at = fmaf(gp[static_cast<int64_t>(dofs + d) * HW + p + d], rp[p + d], at);
+        }
+        for (int s = 0; s < mneg; ++s) {
+            const int kk = mneg - s, off = max(W - kk, 0), xs = x - off;
+            if (x < kk) ar = fmaf(gp[static_cast<int64_t>(s) * HW + p], tp[p + off], ar);
+            if (xs >= 0 && xs < kk) at = fmaf(gp[static_cast<int64_t>(s) * HW + p - off], rp[p - off], at);
+        }
+        if (gref) gref[idx] = ar * inv;
+        if (gtgt) gtgt[idx] = at * inv;
+    }
+}
+
+static int gwc_bwd_impl(const float *go, const float *ref, const float *tgt, float *gref, float *gtgt, int64_t B, int64_t C,
+                        int64_t H, int64_t W, int64_t D, int64_t G, int64_t Dtot, int64_t dofs, int64_t mneg,
+                        cudaStream_t st) {
+    if (!go || !ref || !tgt) return DV_ERR_NULL;
+    if (!gref && !gtgt) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0 || G <= 0 || C % G != 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || G > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    const int cpg = static_cast<int>(C / G);
+    dim3 grid(static_cast<unsigned>((HW + 127) / 128), static_cast<unsigned>(G), static_cast<unsigned>(B));
+#define DV_GB(CPGV)                                                                                                   \
+    gwc_bwd_kernel<CPGV><<<grid, 128, 0, st>>>(go, ref, tgt, gref, gtgt, static_cast<int>(C), static_cast<int>(HW),   \
+                                               static_cast<int>(W), static_cast<int>(D), static_cast<int>(G),         \
+                                               static_cast<int>(Dtot), static_cast<int>(dofs), static_cast<int>(mneg))
+    switch (cpg) {
+        case 1: DV_GB(1); break;
+        case 2: DV_GB(2); break;
+        case 4: DV_GB(4); break;
+        case 8: DV_GB(8); break;
+        case 12: DV_GB(12); break;
+        case 16: DV_GB(16); break;
+        case 32: DV_GB(32); break;
+        default: {
+            const int64_t total = B * C * HW;
+            const int64_t blocks = (total + 255) / 256;
+            const int gsz = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+            gwc_bwd_generic_kernel<<<gsz, 256, 0, st>>>(go, ref, tgt, gref, gtgt, static_cast<int>(C), static_cast<int>(HW),
+                                                        static_cast<int>(W), static_cast<int>(D), static_cast<int>(G), cpg,
+                                                        static_cast<int>(Dtot), static_cast<int>(dofs),
+                                                        static_cast<int>(mneg), total);
+        }
+    }
+#undef DV_GB
+    return finish_launch();
+}
+
+// concat backward: thread = (b, c, pixel); D independent loads per output
+__global__ void __launch_bounds__(256)
+concat_bwd_kernel(const float *__restrict__ go, float *__restrict__ gref, float *__restrict__ gtgt, int C, int HW, int W,
+                  int D, int mask_left) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int c = blockIdx.y, b = blockIdx.z;      // c in [0, 2C)
+    const int x = p % W;
+    const float *gp = go + ((static_cast<int64_t>(b) * 2 * C + c) * D) * HW;
+    float acc = 0.0f;
+    if (c < C) {
+        if (!gref) return;
+        const int dmax = mask_left ? min(D - 1, x) : D - 1;
+#pragma unroll 8
+        for (int d = 0; d <= dmax; ++d) acc += ldg_stream_f32(gp + static_cast<int64_t>(d) * HW + p);
+        gref[(static_cast<int64_t>(b) * C + c) * HW + p] = acc;
+    } else {
+        if (!gtgt) return;
+        const int dmax = min(D - 1, W - 1 - x);
+#pragma unroll 8
+        for (int d = 0; d <= dmax; ++d) acc += ldg_stream_f32(gp + static_cast<int64_t>(d) * HW + p + d);
+        gtgt[(static_cast<int64_t>(b) * C + (c - C)) * HW + p] = acc;
+    }
+}
+
+// disparity_regression backward: d_x[b,d,p] = d * g[b,p]
+template <int V>
+__global__ void __launch_bounds__(256)
+regression_bwd_kernel(const float *__restrict__ g, float *__restrict__ gx, int D, int HW) {
+    const int b = blockIdx.z;
+    const int64_t pv = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * V;
+    if (pv >= HW) return;
+    float gv[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) gv[i] = g[static_cast<int64_t>(b) * HW + pv + i];
+    // blockIdx.y walks chunks of 8 disparities so that the grid stays many short CTAs (write-stream locality)
+    const int d0 = blockIdx.y * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = d0 + j;
+        if (d >= D) break;
+        float *o = gx + (static_cast<int64_t>(b) * D + d) * HW + pv;
+        if constexpr (V == 4) {
+            stg_cs(reinterpret_cast<float4 *>(o), make_float4(gv[0] * d, gv[1] * d, gv[2] * d, gv[3] * d));
+        } else {
+            o[0] = gv[0] * static_cast<float>(d);
+        }
+    }
+}
+
+__global__ void groupwise_bwd_kernel(const float *__restrict__ go, const float *__restrict__ f1, const float *__restrict__ f2,
+                                     float *__restrict__ g1, float *__restrict__ g2, int C, int HW, int G, int cpg,
+                                     int64_t total) {
+    const float inv = 1.0f / static_cast<float>(cpg);
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t p = idx % HW, bc = idx / HW;
+        const int64_t c = bc % C, b = bc / C;
+        const float ge = go[(b * G + c / cpg) * HW + p] * inv;
+        if (g1) g1[idx] = ge * f2[idx];
+        if (g2) g2[idx] = ge * f1[idx];
+    }
+}
+
+}  // namespace dv
+
+extern "C" int dv_gwc_volume_bwd_f32(const float *grad_out, const float *ref, const float *tgt, float *grad_ref,
+                                     float *grad_tgt, int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int64_t G,
+                                     void *stream) {
+    return dv::gwc_bwd_impl(grad_out, ref, tgt, grad_ref, grad_tgt, B, C, H, W, D, G, D, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dv_corr_volume_2sided_bwd_f32(const float *grad_out, const float *ref, const float *tgt, float *grad_ref,
+                                             float *grad_tgt, int64_t B, int64_t C, int64_t H, int64_t W,
+                                             int64_t maxdisp, int64_t G, void *stream) {
+    if (maxdisp < 0) return DV_ERR_BAD_SHAPE;
+    return dv::gwc_bwd_impl(grad_out, ref, tgt, grad_ref, grad_tgt, B, C, H, W, maxdisp + 1, G, 2 * maxdisp + 1, maxdisp,
+                            maxdisp, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dv_groupwise_correlation_bwd_f32(const float *grad_out, const float *fea1, const float *fea2, float *grad1,
+                                                float *grad2, int64_t B, int64_t C, int64_t H, int64_t W, int64_t G,
+                                                void *stream) {
+    using namespace dv;
+    if (!grad_out || !fea1 || !fea2 || (!grad1 && !grad2)) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || G <= 0 || C % G != 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W, total = B * C * HW;
+    if (HW > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    const int64_t blocks = (total + 255) / 256;
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+    groupwise_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, fea1, fea2, grad1, grad2,
+                                                                            static_cast<int>(C), static_cast<int>(HW),
+                                                                            static_cast<int>(G), static_cast<int>(C / G), total);
+    return finish_launch();
+}
+
+extern "C" int dv_concat_volume_bwd_f32(const float *grad_out, float *grad_ref, float *grad_tgt, int64_t B, int64_t C,
+                                        int64_t H, int64_t W, int64_t D, int mask_left, void *stream) {
+    using namespace dv;
+    if (!grad_out || (!grad_ref && !grad_tgt)) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || 2 * C > 65535) return DV_ERR_BAD_SHAPE;
+    dim3 grid(static_cast<unsigned>((HW + 255) / 256), static_cast<unsigned>(2 * C), static_cast<unsigned>(B));
+    concat_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, grad_ref, grad_tgt, static_cast<int>(C),
+                                                                         static_cast<int>(HW), static_cast<int>(W),
+                                                                         static_cast<int>(D), mask_left);
+    return finish_launch();
+}
+
+extern "C" int dv_disparity_regression_bwd_f32(const float *grad_out, float *grad_x, int64_t B, int64_t D, int64_t H,
+                                               int64_t W, void *stream) {
+    using namespace dv;
+    if (!grad_out || !grad_x) return DV_ERR_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || (D + 7) / 8 > 65535) return DV_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((HW % 4 == 0) && aligned16(grad_out) && aligned16(grad_x)) {
+        dim3 grid(static_cast<unsigned>((HW / 4 + 255) / 256), static_cast<unsigned>((D + 7) / 8), static_cast<unsigned>(B));
+        regression_bwd_kernel<4><<<grid, 256, 0, st>>>(grad_out, grad_x, static_cast<int>(D), static_cast<int>(HW));
+    } else {
+        dim3 grid(static_cast<unsigned>((HW + 255) / 256), static_cast<unsigned>((D + 7) / 8), static_cast<unsigned>(B));
+        regression_bwd_kernel<1><<<grid, 256, 0, st>>>(grad_out, grad_x, static_cast<int>(D), static_cast<int>(HW));
+    }
+    return finish_launch();
+}

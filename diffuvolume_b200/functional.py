@@ -3,8 +3,8 @@
 
 Forward passes are the sm_100a kernels (diffuvolume_b200.ops).  The reference's training scripts
 back-propagate through these functions (SceneFlow/main.py:154), so each one is a
-torch.autograd.Function; the backward formulas are composed from PyTorch ops for now (SURVEY.md §8f
-row f1 — dedicated backward kernels are the next row, inference never takes this path).
+torch.autograd.Function whose backward is a dedicated kernel too (SURVEY.md §8f row f1,
+csrc/volume_backward.cu): one pass over the gradient volume instead of autograd's D x {slice, mul, sum, index_put}.
 
 dtype handling follows the reference's `new_zeros`: the result has the input's dtype.  Inputs that
 are not float32 (IGEV runs these under autocast, KITTI15/core/igev_stereo_ddim.py:366) are computed in
@@ -31,19 +31,9 @@ class _GwcVolume(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         ref, tgt = ctx.saved_tensors
-        D, G = ctx.cfg
-        B, C, H, W = ref.shape
-        cpg = C // G
-        g = g.float()
-        r32, t32 = ref.float(), tgt.float()
-        gref = torch.zeros_like(r32) if ctx.needs_input_grad[0] else None
-        gtgt = torch.zeros_like(t32) if ctx.needs_input_grad[1] else None
-        for d in range(min(D, W)):
-            gd = g[:, :, d, :, d:].repeat_interleave(cpg, dim=1) / cpg      # [B,C,H,W-d]
-            if gref is not None:
-                gref[..., d:] += gd * t32[..., : W - d]
-            if gtgt is not None:
-                gtgt[..., : W - d] += gd * r32[..., d:]
+        _, G = ctx.cfg
+        gref, gtgt = ops.gwc_volume_bwd(g.float().contiguous(), ref.float(), tgt.float(), G,
+                                        need_ref=ctx.needs_input_grad[0], need_tgt=ctx.needs_input_grad[1])
         return (None if gref is None else gref.to(ref.dtype), None if gtgt is None else gtgt.to(tgt.dtype), None, None)
 
 
@@ -55,26 +45,10 @@ class _ConcatVolume(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        D, mask_left, dt_r, dt_t = ctx.cfg
-        C = g.shape[1] // 2
-        W = g.shape[-1]
-        g = g.float()
-        gl, gr = g[:, :C], g[:, C:]
-        gref = gtgt = None
-        if ctx.needs_input_grad[0]:
-            if mask_left:
-                gref = torch.zeros_like(gl[:, :, 0])
-                for d in range(min(D, W)):
-                    gref[..., d:] += gl[:, :, d, :, d:]
-            else:
-                gref = gl.sum(dim=2)
-            gref = gref.to(dt_r)
-        if ctx.needs_input_grad[1]:
-            gtgt = torch.zeros_like(gr[:, :, 0])
-            for d in range(min(D, W)):
-                gtgt[..., : W - d] += gr[:, :, d, :, d:]
-            gtgt = gtgt.to(dt_t)
-        return gref, gtgt, None, None
+        _, mask_left, dt_r, dt_t = ctx.cfg
+        gref, gtgt = ops.concat_volume_bwd(g.float().contiguous(), mask_left, need_ref=ctx.needs_input_grad[0],
+                                           need_tgt=ctx.needs_input_grad[1])
+        return (None if gref is None else gref.to(dt_r), None if gtgt is None else gtgt.to(dt_t), None, None)
 
 
 class _CorrVolume2Sided(torch.autograd.Function):
@@ -88,22 +62,9 @@ class _CorrVolume2Sided(torch.autograd.Function):
     def backward(ctx, g):
         ref, tgt = ctx.saved_tensors
         m, G = ctx.cfg
-        B, C, H, W = ref.shape
-        cpg = C // G
-        g = g.float()
-        r32, t32 = ref.float(), tgt.float()
-        gref, gtgt = torch.zeros_like(r32), torch.zeros_like(t32)
-        for i in range(-m, m + 1):
-            gi = g[:, :, i + m].repeat_interleave(cpg, dim=1) / cpg
-            if i >= 0:
-                if i < W:
-                    gref[..., i:] += gi[..., i:] * t32[..., : W - i]
-                    gtgt[..., : W - i] += gi[..., i:] * r32[..., i:]
-            else:
-                k = min(-i, W)
-                gref[..., :k] += gi[..., :k] * t32[..., W - k:]
-                gtgt[..., W - k:] += gi[..., :k] * r32[..., :k]
-        return gref.to(ref.dtype), gtgt.to(tgt.dtype), None, None
+        gref, gtgt = ops.gwc_volume_bwd(g.float().contiguous(), ref.float(), tgt.float(), G, two_sided_maxdisp=m,
+                                        need_ref=ctx.needs_input_grad[0], need_tgt=ctx.needs_input_grad[1])
+        return (None if gref is None else gref.to(ref.dtype), None if gtgt is None else gtgt.to(tgt.dtype), None, None)
 
 
 class _GroupwiseCorrelation(torch.autograd.Function):
@@ -116,9 +77,8 @@ class _GroupwiseCorrelation(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         f1, f2 = ctx.saved_tensors
-        cpg = f1.shape[1] // ctx.G
-        ge = g.float().repeat_interleave(cpg, dim=1) / cpg
-        return (ge * f2.float()).to(f1.dtype), (ge * f1.float()).to(f2.dtype), None
+        g1, g2 = ops.groupwise_correlation_bwd(g.float().contiguous(), f1.float(), f2.float(), ctx.G)
+        return g1.to(f1.dtype), g2.to(f2.dtype), None
 
 
 class _DisparityRegression(torch.autograd.Function):
@@ -130,10 +90,7 @@ class _DisparityRegression(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         maxdisp, keepdim, dt = ctx.cfg
-        if not keepdim:
-            g = g.unsqueeze(1)
-        dv = torch.arange(0, maxdisp, dtype=torch.float32, device=g.device).view(1, maxdisp, 1, 1)
-        return (g.float() * dv).to(dt), None, None
+        return ops.disparity_regression_bwd(g.float().contiguous(), maxdisp).to(dt), None, None
 
 
 def groupwise_correlation(fea1, fea2, num_groups):

@@ -527,6 +527,75 @@ def ddim_step(*, disp: torch.Tensor, xt: torch.Tensor, shift: Optional[torch.Ten
 
 
 # --------------------------------------------------------------------------------------------
+# backward passes
+# --------------------------------------------------------------------------------------------
+def gwc_volume_bwd(grad_out: torch.Tensor, ref: torch.Tensor, tgt: torch.Tensor, num_groups: int, *,
+                   need_ref: bool = True, need_tgt: bool = True, two_sided_maxdisp: Optional[int] = None):
+    """Gradients of build_gwc_volume (or, with two_sided_maxdisp=m, build_corrleation_volume) w.r.t. (ref, tgt)."""
+    B, C, H, W = ref.shape
+    _need_cuda(grad_out, ref, tgt)
+    grad_out, ref, tgt = _f32c(grad_out, "grad_out"), _f32c(ref, "ref"), _f32c(tgt, "tgt")
+    gref = torch.empty_like(ref) if need_ref else None
+    gtgt = torch.empty_like(tgt) if need_tgt else None
+    if ref.numel() == 0 or not (need_ref or need_tgt):
+        return gref, gtgt
+    with torch.cuda.device(ref.device):
+        if two_sided_maxdisp is None:
+            D = grad_out.shape[2]
+            assert tuple(grad_out.shape) == (B, num_groups, D, H, W)
+            check(_lib.lib().dv_gwc_volume_bwd_f32(_ptr(grad_out), _ptr(ref), _ptr(tgt), _ptr(gref), _ptr(gtgt), B, C, H, W,
+                                                   D, num_groups, _stream(ref)), "dv_gwc_volume_bwd_f32")
+        else:
+            m = int(two_sided_maxdisp)
+            assert tuple(grad_out.shape) == (B, num_groups, 2 * m + 1, H, W)
+            check(_lib.lib().dv_corr_volume_2sided_bwd_f32(_ptr(grad_out), _ptr(ref), _ptr(tgt), _ptr(gref), _ptr(gtgt), B,
+                                                           C, H, W, m, num_groups, _stream(ref)),
+                  "dv_corr_volume_2sided_bwd_f32")
+    return gref, gtgt
+
+
+def groupwise_correlation_bwd(grad_out: torch.Tensor, fea1: torch.Tensor, fea2: torch.Tensor, num_groups: int):
+    B, C, H, W = fea1.shape
+    _need_cuda(grad_out, fea1, fea2)
+    grad_out, fea1, fea2 = _f32c(grad_out, "grad_out"), _f32c(fea1, "fea1"), _f32c(fea2, "fea2")
+    g1, g2 = torch.empty_like(fea1), torch.empty_like(fea2)
+    if fea1.numel():
+        with torch.cuda.device(fea1.device):
+            check(_lib.lib().dv_groupwise_correlation_bwd_f32(_ptr(grad_out), _ptr(fea1), _ptr(fea2), _ptr(g1), _ptr(g2), B, C,
+                                                              H, W, num_groups, _stream(fea1)),
+                  "dv_groupwise_correlation_bwd_f32")
+    return g1, g2
+
+
+def concat_volume_bwd(grad_out: torch.Tensor, mask_left: bool, *, need_ref: bool = True, need_tgt: bool = True):
+    """Gradients of build_concat_volume w.r.t. (ref, tgt): grad_out is [B,2C,D,H,W]."""
+    B, C2, D, H, W = grad_out.shape
+    C = C2 // 2
+    _need_cuda(grad_out)
+    grad_out = _f32c(grad_out, "grad_out")
+    gref = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device) if need_ref else None
+    gtgt = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device) if need_tgt else None
+    if grad_out.numel() and (need_ref or need_tgt):
+        with torch.cuda.device(grad_out.device):
+            check(_lib.lib().dv_concat_volume_bwd_f32(_ptr(grad_out), _ptr(gref), _ptr(gtgt), B, C, H, W, D, int(mask_left),
+                                                      _stream(grad_out)), "dv_concat_volume_bwd_f32")
+    return gref, gtgt
+
+
+def disparity_regression_bwd(grad_out: torch.Tensor, maxdisp: int) -> torch.Tensor:
+    """Gradient of disparity_regression w.r.t. x: [B,H,W] (or [B,1,H,W]) -> [B,maxdisp,H,W]."""
+    _need_cuda(grad_out)
+    grad_out = _f32c(grad_out, "grad_out")
+    B, H, W = grad_out.shape[0], grad_out.shape[-2], grad_out.shape[-1]
+    gx = torch.empty((B, maxdisp, H, W), dtype=torch.float32, device=grad_out.device)
+    if gx.numel():
+        with torch.cuda.device(gx.device):
+            check(_lib.lib().dv_disparity_regression_bwd_f32(_ptr(grad_out), _ptr(gx), B, maxdisp, H, W, _stream(gx)),
+                  "dv_disparity_regression_bwd_f32")
+    return gx
+
+
+# --------------------------------------------------------------------------------------------
 # IGEV geometry
 # --------------------------------------------------------------------------------------------
 def corr1d_allpairs(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:

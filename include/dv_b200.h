@@ -255,6 +255,27 @@ int dv_geo_lookup_f32(const float *const *geo_pyr, const float *const *corr_pyr,
                       int64_t B, int64_t C, int64_t D, int64_t h, int64_t w, int64_t W2,
                       int num_levels, int radius, void *stream);
 
+/* ---- f1: backward passes of the volume ops — the reference's training scripts differentiate through them
+ *          (SceneFlow/main.py:154 -> models/acv_ddim.py:424-482; KITTI12/main.py; KITTI15/train_stereo.py).
+ * Gradients of the functions above with respect to their feature inputs; grad_out has the forward output's shape.
+ * Either gradient pointer may be NULL (not needed); every other convention as in the forward entry points.
+ *   gwc    : grad_ref[c,y,x] = 1/cpg sum_{d<=x}   grad_out[g,d,y,x]   * tgt[c,y,x-d]
+ *            grad_tgt[c,y,x] = 1/cpg sum_{x+d<W}  grad_out[g,d,y,x+d] * ref[c,y,x+d]
+ *   corr2  : the same over slots [m, 2m] plus the first-k-columns terms of slots [0, m) (KITTI12/models/submodule.py:128-131)
+ *   concat : grad_ref[c,y,x] = sum_d grad_out[c,d,y,x] (x >= d when mask_left); grad_tgt[c,y,x] = sum_{x+d<W} grad_out[C+c,d,y,x+d]
+ *   regression : grad_x[b,d,y,x] = d * grad_out[b,y,x]                                                          */
+int dv_gwc_volume_bwd_f32(const float *grad_out, const float *ref, const float *tgt, float *grad_ref, float *grad_tgt,
+                          int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int64_t G, void *stream);
+int dv_corr_volume_2sided_bwd_f32(const float *grad_out, const float *ref, const float *tgt, float *grad_ref,
+                                  float *grad_tgt, int64_t B, int64_t C, int64_t H, int64_t W, int64_t maxdisp,
+                                  int64_t G, void *stream);
+int dv_groupwise_correlation_bwd_f32(const float *grad_out, const float *fea1, const float *fea2, float *grad1,
+                                     float *grad2, int64_t B, int64_t C, int64_t H, int64_t W, int64_t G, void *stream);
+int dv_concat_volume_bwd_f32(const float *grad_out, float *grad_ref, float *grad_tgt,
+                             int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int mask_left, void *stream);
+int dv_disparity_regression_bwd_f32(const float *grad_out, float *grad_x, int64_t B, int64_t D, int64_t H, int64_t W,
+                                    void *stream);
+
 /* ---- a13: ensemble (acv_ddim.py:365-369): out[p] = sum_i cof[i] * maps[i][p], i < n_maps <= 8
  * `maps` is a HOST array of n_maps device pointers, `cof` a HOST array of n_maps floats.          */
 int dv_ensemble_f32(const float *const *maps, const float *cof, int n_maps, float *out,

@@ -1,0 +1,110 @@
+"""Backward kernels (csrc/volume_backward.cu) through the reference-named autograd Functions
+(diffuvolume_b200.functional) against torch autograd of the reference's own op sequence on the CPU (oracle/torch_port.py
+restates it; float64 there, so the comparison tolerance is the float32 accumulation error of the kernels).
+"""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import torch_port as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _leaf(a, dev, dtype):
+    return torch.from_numpy(a).to(device=dev, dtype=dtype).requires_grad_(True)
+
+
+def _check(fn_ours, fn_port, shape, args, seed, tol=2e-5):
+    ref, tgt = synth.normal(shape, seed), synth.normal(shape, seed + 1)
+    a1, b1 = _leaf(ref, "cuda", torch.float32), _leaf(tgt, "cuda", torch.float32)
+    a2, b2 = _leaf(ref, "cpu", torch.float64), _leaf(tgt, "cpu", torch.float64)
+    o1, o2 = fn_ours(a1, b1, *args), fn_port(a2, b2, *args)
+    assert tuple(o1.shape) == tuple(o2.shape)
+    g = synth.normal(tuple(o2.shape), seed + 2)
+    o1.backward(torch.from_numpy(g).cuda())
+    o2.backward(torch.from_numpy(g).double())
+    for got, want in ((a1.grad, a2.grad), (b1.grad, b2.grad)):
+        want = want.numpy()
+        err = np.abs(got.cpu().numpy().astype(np.float64) - want).max() / max(np.abs(want).max(), 1e-30)
+        assert err < tol, err
+
+
+def _corr_port(r, t_, m, G):
+    """KITTI12/models/submodule.py:121-135 written with the reference's slices (autograd reference)."""
+    B, C, H, W = r.shape
+    vol = r.new_zeros([B, G, 2 * m + 1, H, W])
+    gc = lambda a, b: (a * b).view(B, G, C // G, H, -1).mean(2)
+    for i in range(-m, m + 1):
+        if i > 0:
+            vol[:, :, i + m, :, i:] = gc(r[..., i:], t_[..., :-i])
+        elif i < 0:
+            vol[:, :, i + m, :, :-i] = gc(r[..., :-i], t_[..., i:])
+        else:
+            vol[:, :, m] = gc(r, t_)
+    return vol
+
+
+@pytest.mark.parametrize("shape,D,G", [((2, 64, 9, 40), 48, 8), ((1, 24, 5, 20), 12, 2), ((2, 8, 3, 7), 9, 4),
+                                       ((1, 15, 4, 11), 6, 3), ((1, 320, 6, 24), 12, 40)])
+def test_gwc_volume_backward(shape, D, G):
+    from diffuvolume_b200 import functional as Fn
+    _check(Fn.build_gwc_volume, lambda r, t_, D_, G_: P.gwc_volume(r, t_, D_, G_), shape, (D, G), 201)
+
+
+@pytest.mark.parametrize("mask_left", [False, True])
+@pytest.mark.parametrize("shape,D", [((2, 32, 9, 40), 48), ((1, 12, 5, 13), 6), ((1, 3, 2, 5), 9)])
+def test_concat_volume_backward(shape, D, mask_left):
+    from diffuvolume_b200 import functional as Fn
+    fn = Fn.build_concat_volume_t if mask_left else Fn.build_concat_volume_m
+    _check(fn, lambda r, t_, D_: P.concat_volume(r, t_, D_, mask_left), shape, (D,), 211)
+
+
+@pytest.mark.parametrize("shape,m,G", [((1, 32, 6, 64), 24, 1), ((2, 8, 3, 7), 9, 2), ((1, 8, 2, 20), 3, 4)])
+def test_corr_volume_2sided_backward(shape, m, G):
+    from diffuvolume_b200 import functional as Fn
+    _check(Fn.build_corrleation_volume, _corr_port, shape, (m, G), 221)
+
+
+def test_groupwise_correlation_and_regression_backward():
+    from diffuvolume_b200 import functional as Fn
+    _check(Fn.groupwise_correlation, lambda a, b, G: (a * b).view(a.shape[0], G, a.shape[1] // G, *a.shape[2:]).mean(2),
+           (2, 24, 5, 12), (4,), 231)
+    for keepdim, shape in ((False, (2, 48, 6, 20)), (True, (1, 192, 5, 13))):
+        x = synth.normal(shape, 241)
+        g = synth.normal((shape[0], 1, *shape[2:]) if keepdim else (shape[0], *shape[2:]), 242)
+        x1 = _leaf(x, "cuda", torch.float32)
+        Fn.disparity_regression(x1, shape[1], keepdim).backward(torch.from_numpy(g).cuda())
+        want = np.arange(shape[1], dtype=np.float32).reshape(1, -1, 1, 1) * g.reshape(shape[0], 1, *shape[2:])
+        np.testing.assert_array_equal(x1.grad.cpu().numpy(), want)
+
+
+def test_training_style_graph_matches_cpu_autograd():
+    """gwc -> concat -> ACV multiply -> filter multiply -> softmax -> regression, differentiated end to end
+    (the op chain of ACVNet_DDIM.forward's training branch, acv_ddim.py:375-390, :446-480, minus the convolutions)."""
+    from diffuvolume_b200 import functional as Fn
+    B, C, Cc, G, D, h, w = 1, 16, 4, 2, 8, 5, 12
+    fl, fr = synth.normal((B, C, h, w), 301), synth.normal((B, C, h, w), 302)
+    cl, cr = synth.normal((B, Cc, h, w), 303), synth.normal((B, Cc, h, w), 304)
+    n = synth.uniform((B, D, h, w), 305, dtype=np.float32)
+
+    def graph(fl_, fr_, cl_, cr_, n_, gwc, concat, regress):
+        att = gwc(fl_, fr_, D, G).mean(1, keepdim=True)
+        vol = torch.softmax(att, dim=2) * concat(cl_, cr_, D)
+        vol = vol * n_.unsqueeze(1)
+        cost = vol.sum(1)
+        return regress(torch.softmax(cost, dim=1), D)
+
+    leaves_gpu = [_leaf(a, "cuda", torch.float32) for a in (fl, fr, cl, cr)]
+    leaves_cpu = [_leaf(a, "cpu", torch.float64) for a in (fl, fr, cl, cr)]
+    out_gpu = graph(*leaves_gpu, torch.from_numpy(n).cuda(), Fn.build_gwc_volume, Fn.build_concat_volume_m,
+                    lambda x, D_: Fn.disparity_regression(x, D_, False))
+    out_cpu = graph(*leaves_cpu, torch.from_numpy(n).double(), P.gwc_volume, lambda r, t_, D_: P.concat_volume(r, t_, D_, False),
+                    lambda x, D_: torch.sum(x * torch.arange(D_, dtype=x.dtype).view(1, D_, 1, 1), 1))
+    gsum = synth.normal(tuple(out_cpu.shape), 306)
+    out_gpu.backward(torch.from_numpy(gsum).cuda())
+    out_cpu.backward(torch.from_numpy(gsum).double())
+    for a, b in zip(leaves_gpu, leaves_cpu):
+        want = b.grad.numpy()
+        assert np.abs(a.grad.cpu().numpy() - want).max() / np.abs(want).max() < 1e-4

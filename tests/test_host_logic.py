@@ -118,56 +118,6 @@ print("OK", len(done))
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
 
 
-def test_backward_formulas_against_autograd(monkeypatch):
-    """The drop-ins are autograd Functions (training scripts back-propagate through them); their backward
-    formulas are checked against autograd of the op-for-op CPU port, with the CUDA forward swapped for the
-    port in THIS TEST ONLY."""
-    from diffuvolume_b200 import functional as Fn
-    from diffuvolume_b200 import ops
-    monkeypatch.setattr(ops, "gwc_volume", lambda r, t_, D, G, out=None: P.gwc_volume(r, t_, D, G))
-    monkeypatch.setattr(ops, "concat_volume", lambda r, t_, D, mask_left, **k: P.concat_volume(r, t_, D, mask_left))
-    monkeypatch.setattr(ops, "disparity_regression",
-                        lambda x, D, keepdim=False: torch.sum(x * torch.arange(D, dtype=x.dtype).view(1, D, 1, 1), 1, keepdim=keepdim))
-    monkeypatch.setattr(ops, "corr_volume_2sided",
-                        lambda r, t_, m, G: torch.from_numpy(O.build_corrleation_volume(r.detach().numpy(), t_.detach().numpy(), m, G)))
-    monkeypatch.setattr(ops, "groupwise_correlation",
-                        lambda a, b, G: (a * b).view(a.shape[0], G, a.shape[1] // G, *a.shape[2:]).mean(2))
-    tt = lambda a: torch.from_numpy(a.astype(np.float64)).requires_grad_(True)
-    ref, tgt = synth.normal((2, 8, 3, 10), 1), synth.normal((2, 8, 3, 10), 2)
-
-    def check(fn_ours, fn_port, *shape_args):
-        a1, b1 = tt(ref), tt(tgt)
-        a2, b2 = tt(ref), tt(tgt)
-        o1, o2 = fn_ours(a1, b1, *shape_args), fn_port(a2, b2, *shape_args)
-        g = torch.from_numpy(synth.normal(tuple(o2.shape), 9).astype(np.float64))
-        o1.backward(g); o2.backward(g)
-        np.testing.assert_allclose(a1.grad.numpy(), a2.grad.numpy(), atol=1e-5)
-        np.testing.assert_allclose(b1.grad.numpy(), b2.grad.numpy(), atol=1e-5)
-
-    check(Fn.build_gwc_volume, lambda r, t_, D, G: P.gwc_volume(r, t_, D, G), 6, 4)
-    check(Fn.build_concat_volume_m, lambda r, t_, D: P.concat_volume(r, t_, D, False), 6)
-    check(Fn.build_concat_volume_t, lambda r, t_, D: P.concat_volume(r, t_, D, True), 6)
-    check(Fn.groupwise_correlation, lambda a, b, G: (a * b).view(2, G, 8 // G, 3, 10).mean(2), 2)
-
-    # two-sided correlation volume: autograd reference written with slices (KITTI12/models/submodule.py:121-135)
-    def corr_port(r, t_, m, G):
-        B, C, H, W = r.shape
-        vol = r.new_zeros([B, G, 2 * m + 1, H, W])
-        gc = lambda a, b: (a * b).view(B, G, C // G, H, -1).mean(2)
-        for i in range(-m, m + 1):
-            if i > 0:
-                vol[:, :, i + m, :, i:] = gc(r[..., i:], t_[..., :-i])
-            elif i < 0:
-                vol[:, :, i + m, :, :-i] = gc(r[..., :-i], t_[..., i:])
-            else:
-                vol[:, :, m] = gc(r, t_)
-        return vol
-    check(Fn.build_corrleation_volume, corr_port, 3, 2)
-    x = torch.from_numpy(synth.normal((2, 6, 3, 5), 3).astype(np.float64)).requires_grad_(True)
-    Fn.disparity_regression(x, 6, True).sum().backward()
-    np.testing.assert_allclose(x.grad.numpy(), np.broadcast_to(np.arange(6.0).reshape(1, 6, 1, 1), (2, 6, 3, 5)))
-
-
 def test_shard_range_covers_everything():
     from diffuvolume_b200.distributed import shard_range
     for n in (0, 1, 7, 8, 4370):
