@@ -225,22 +225,22 @@ softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__r
 // arithmetic of earlier tiles — the register-resident kernel above alternates between "all loads" and "all math"
 // per warp and reached 4.5 TB/s; per-row 1-D bulk copies (UBLKCP, 256-512 B each) were measured at 2.3 TB/s and
 // dropped.  Consumers copy their slice of the tile to registers (conflict-free LDS.128: a warp reads two adjacent
-// rows = 512 contiguous bytes) and release the stage at once.  Thread (quad q of 16, slice ds of 16) owns
-// d = 16 j + ds; the constant 16 j folds into FFMA/FADD immediates, the per-thread ds enters once per tile.
-// Cross-slice reductions: one shuffle + 8-way shared memory combine behind a 256-thread named barrier (the
-// producer warp never joins it).
+// rows = 512 contiguous bytes) and release the stage at once.  Thread (quad q of 16, slice ds of NDS) owns
+// d = NDS j + ds; the constant NDS j folds into FFMA/FADD immediates, the per-thread ds enters once per tile.
+// Cross-slice reductions: one shuffle + (NDS/2)-way shared memory combine behind a named barrier of the consumer
+// warps (the producer warp never joins it).
 constexpr int kSrSlots = 256;
 static __device__ int g_sr_next[kSrSlots];
 static __device__ int g_sr_done[kSrSlots];
 static std::atomic<unsigned> g_sr_slot{0};
 
-template <int NJ, int STAGES, int SPAN, bool DYN>
-__global__ void __launch_bounds__(288, SPAN == 64 ? 2 : 1)
+template <int NJ, int NDS, int STAGES, int SPAN, int MINB, bool DYN, bool FULLD>
+__global__ void __launch_bounds__(SPAN / 4 * NDS + 32, MINB)
 softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int HW, int spans_per_b, int ntiles, int slot,
                            float *__restrict__ disp_out, float *__restrict__ prob_out, const float *__restrict__ used,
                            float *__restrict__ unc_out, float *__restrict__ vote_out, float thr_dif, float thr_unc,
                            float *__restrict__ ens_acc, float ens_coef, int ens_init) {
-    constexpr int SQ = SPAN / 4, NW = 8, NDS = 256 / SQ;   // quads per span, consumer warps, disparity slices
+    constexpr int SQ = SPAN / 4, NCONS = SQ * NDS, NW = NCONS / 32;   // quads per span, consumer threads / warps
     extern __shared__ __align__(128) float smem[];              // [STAGES][D][SPAN]
     __shared__ float4 red[4][NW][SQ];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
@@ -312,7 +312,7 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
             const float *st = smem + s * stage_floats + ds * SPAN + 4 * q;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                if (NDS * j + ds < D)
+                if (FULLD || NDS * j + ds < D)
                     x[j] = *reinterpret_cast<const float4 *>(st + NDS * j * SPAN);
                 else
                     x[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -334,7 +334,7 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
         m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, 16));
         }
         if (SQ == 32 || lane < SQ) red[0][warp][q] = m;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             const float4 v = red[0][w][q];
@@ -362,7 +362,7 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
             red[1][warp][q] = S;
             red[2][warp][q] = Wd;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
         S = make_float4(0.f, 0.f, 0.f, 0.f);
         Wd = S;
 #pragma unroll
@@ -377,7 +377,7 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
             float *pp = prob_out + static_cast<int64_t>(b) * D * HW + p + static_cast<int64_t>(ds) * HW;
 #pragma unroll
             for (int j = 0; j < NJ; ++j)
-                if (NDS * j + ds < D)
+                if (FULLD || NDS * j + ds < D)
                     *reinterpret_cast<float4 *>(pp + static_cast<int64_t>(NDS * j) * HW) =
                         make_float4(x[j].x * rS.x, x[j].y * rS.y, x[j].z * rS.z, x[j].w * rS.w);
         }
@@ -397,7 +397,7 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
             U.z += __shfl_xor_sync(0xffffffffu, U.z, 16); U.w += __shfl_xor_sync(0xffffffffu, U.w, 16);
             }
             if (SQ == 32 || lane < SQ) red[3][warp][q] = U;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
             if (fin) {
                 U = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -428,30 +428,30 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
     }
 }
 
-template <int NJ, int STAGES, int SPAN>
+template <int NJ, int NDS, int STAGES, int SPAN, int MINB>
 static int launch_sr_tma(const float *cost, int B, int D, int HW, float *disp_out, float *prob_out, const float *used,
                          float *unc_out, float *vote_out, float thr_dif, float thr_unc, float *ens_acc,
                          float ens_coef, int ens_init, cudaStream_t st) {
     const size_t smem = sizeof(float) * STAGES * static_cast<size_t>(D) * SPAN;
     const int spans = (HW + SPAN - 1) / SPAN;
-    constexpr int kCtasPerSm = SPAN == 64 ? 2 : 1;
     const int64_t ntiles = static_cast<int64_t>(spans) * B;
-    const int grid = static_cast<int>(ntiles < 1LL * kCtasPerSm * kNumSMs ? ntiles : 1LL * kCtasPerSm * kNumSMs);
+    const int grid = static_cast<int>(ntiles < 1LL * MINB * kNumSMs ? ntiles : 1LL * MINB * kNumSMs);
     CUtensorMap tmap;
     const uint64_t dims[3] = {static_cast<uint64_t>(HW), static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
     const uint32_t box[3] = {static_cast<uint32_t>(SPAN), static_cast<uint32_t>(D), 1u};
     if (!make_tensor_map_f32(&tmap, cost, 3, dims, box)) return DV_ERR_UNSUPPORTED;
     const int slot = static_cast<int>(g_sr_slot.fetch_add(1, std::memory_order_relaxed) % kSrSlots);
-#define DV_LAUNCH(DYN)                                                                                                 \
+#define DV_LAUNCH(FULLD)                                                                                               \
     {                                                                                                                  \
-        auto kern = softmax_regress_tma_kernel<NJ, STAGES, SPAN, DYN>;                                                 \
+        auto kern = softmax_regress_tma_kernel<NJ, NDS, STAGES, SPAN, MINB, true, FULLD>;                              \
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=         \
             cudaSuccess)                                                                                               \
             return DV_ERR_LAUNCH;                                                                                      \
-        kern<<<grid, 288, smem, st>>>(tmap, D, HW, spans, static_cast<int>(ntiles), slot, disp_out, prob_out, used,    \
-                                      unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init);               \
+        kern<<<grid, SPAN / 4 * NDS + 32, smem, st>>>(tmap, D, HW, spans, static_cast<int>(ntiles), slot, disp_out,    \
+                                                      prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc,    \
+                                                      ens_coef, ens_init);                                             \
     }
-    if (tune_variant("DV_SR_DYN", 1)) DV_LAUNCH(true) else DV_LAUNCH(false)
+    if (D == NJ * NDS) DV_LAUNCH(true) else DV_LAUNCH(false)
 #undef DV_LAUNCH
     return DV_OK;
 }
@@ -587,11 +587,14 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
     if (vec4 && D <= 192 && tune_variant("DV_SR_TMA", 1) && static_cast<int64_t>((HW + 63) / 64) * B <= INT32_MAX) {
         int rc;
 #define DV_SR_TMA_ARGS cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, st
-        const int span = tune_variant("DV_SR_SPAN", 64);
-        if (D <= 48) rc = launch_sr_tma<3, 4, 64>(DV_SR_TMA_ARGS);
-        else if (D <= 96) rc = launch_sr_tma<6, 4, 64>(DV_SR_TMA_ARGS);
-        else if (span == 128) rc = launch_sr_tma<24, 2, 128>(DV_SR_TMA_ARGS);
-        else rc = launch_sr_tma<12, 2, 64>(DV_SR_TMA_ARGS);
+        // thread = (quad of 16, slice of 8): 4 consumer warps per CTA, 2 CTAs per SM.  Measured at D = 192, B = 8
+        // (gpurun_out/bench_sr3.log): 8 slices x 24 d per thread 0.496 ms (6.59 TB/s) vs 16 slices x 12 d 0.586 ms — half as
+        // many partials to merge per pixel and half the per-tile overhead per element; 3 CTAs x 1 stage spills.
+        const int shape = tune_variant("DV_SR_SHAPE", 2);
+        if (D <= 48) rc = launch_sr_tma<6, 8, 4, 64, 2>(DV_SR_TMA_ARGS);
+        else if (D <= 96) rc = launch_sr_tma<12, 8, 4, 64, 2>(DV_SR_TMA_ARGS);
+        else if (shape == 0) rc = launch_sr_tma<12, 16, 2, 64, 2>(DV_SR_TMA_ARGS);
+        else rc = launch_sr_tma<24, 8, 2, 64, 2>(DV_SR_TMA_ARGS);
 #undef DV_SR_TMA_ARGS
         if (rc == DV_OK) return finish_launch();
         if (rc != DV_ERR_UNSUPPORTED) return rc;   // no tensor-map encoder: fall through to the register kernel

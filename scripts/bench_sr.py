@@ -23,7 +23,7 @@ def run(full=True, **env):
 gb = B * (192 * H * W * 4 + 5 * H * W * 4) / 1e9
 ms0, r0 = run(DV_SR_TMA=0)
 print(json.dumps({"variant": "regs", "ms": round(ms0, 4), "GBs": round(gb / ms0 * 1e3, 1)}))
-for name, env in [("tmap64_static", dict(DV_SR_TMA=1, DV_SR_DYN=0, DV_SR_SPAN=64)), ("tmap64_dyn", dict(DV_SR_TMA=1, DV_SR_DYN=1, DV_SR_SPAN=64)), ("tmap128_static", dict(DV_SR_TMA=1, DV_SR_DYN=0, DV_SR_SPAN=128)), ("tmap128_dyn", dict(DV_SR_TMA=1, DV_SR_DYN=1, DV_SR_SPAN=128))]:
+for name, env in [("shape0_16sl_2st_2cta", dict(DV_SR_TMA=1, DV_SR_SHAPE=0)), ("shape1_8sl_1st_3cta", dict(DV_SR_TMA=1, DV_SR_SHAPE=1)), ("shape2_8sl_2st_2cta", dict(DV_SR_TMA=1, DV_SR_SHAPE=2)), ("shape3_16sl_1st_3cta", dict(DV_SR_TMA=1, DV_SR_SHAPE=3))]:
     ms, r = run(**env)
     err = {k: float((r[k] - r0[k]).abs().max()) for k in ("disp", "unc", "vote")}
     print(json.dumps({"variant": name, "ms": round(ms, 4), "GBs": round(gb / ms * 1e3, 1), "maxdiff_vs_regs": err}))
