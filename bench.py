@@ -244,7 +244,10 @@ def run_ours(args):
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text()).get(dom, {}).get("dram_bytes_per_launch")
+                kname = {"filter": "concat_stream_kernel", "concat_acv": "concat_stream_kernel",
+                         "softmax_regress": "softmax_regress_tma_kernel", "gwc_volume": "gwc_volume_kernel",
+                         "ddim_step": "ddim_step_kernel", "filter_factor": "filter_factor_kernel"}.get(dom, dom)
+                traffic = json.loads(tp.read_text()).get(kname, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         result = {

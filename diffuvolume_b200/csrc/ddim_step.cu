@@ -70,10 +70,9 @@ __device__ __forceinline__ float x0_from_tap(const TwoTap &t, int d, int D, floa
     return clampf(x0, -s, s);
 }
 
-constexpr int kDdimPx = 32;   // pixels per CTA (x)
-constexpr int kDdimDg = 8;    // hypothesis groups per CTA (y): thread (px, dg) owns d = dg, dg+8, ...
+// CTA = kDdimPx pixels (x) x kDdimDg hypothesis groups (y): thread (px, dg) owns d = dg, dg + kDdimDg, ...
 
-template <typename XT>
+template <typename XT, int kDdimPx, int kDdimDg>
 __global__ void __launch_bounds__(kDdimPx * kDdimDg)
 ddim_step_kernel(const dv_ddim_step_args a) {
     const int hw = static_cast<int>(a.h * a.w);
@@ -89,6 +88,31 @@ ddim_step_kernel(const dv_ddim_step_args a) {
     const int64_t fb = static_cast<int64_t>(b) * H * W;
     const int64_t o00 = fb + static_cast<int64_t>(ty.i0) * W + tx.i0, o01 = fb + static_cast<int64_t>(ty.i0) * W + tx.i1;
     const int64_t o10 = fb + static_cast<int64_t>(ty.i1) * W + tx.i0, o11 = fb + static_cast<int64_t>(ty.i1) * W + tx.i1;
+
+    // The state loads of the first pass do not depend on the taps / mask below: issue them first so that their
+    // latency overlaps the dependent tap -> mask -> barrier chain.
+    constexpr int UN = 3;
+    const XT *xt = static_cast<const XT *>(a.xt);
+    const XT *sn = static_cast<const XT *>(a.step_noise);
+    XT xv[UN], snv[UN];
+    float shv[UN], shn[UN];
+    auto load_state = [&](int d0) {
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int d = d0 + u * kDdimDg;
+            xv[u] = static_cast<XT>(0); snv[u] = static_cast<XT>(0); shv[u] = 0.0f; shn[u] = 0.0f;
+            if (d < D) {
+                const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
+                xv[u] = xt[e];
+                if (a.shift) shv[u] = a.shift[b * D + d];
+                if (!a.last_step) {
+                    snv[u] = sn[e];
+                    if (a.n_next_out && a.shift_next) shn[u] = a.shift_next[b * D + d];
+                }
+            }
+        }
+    };
+    load_state(dg);
 
     // ---- a10: down-sampled disparity -> 2-tap x_start
     const float d00 = a.disp[o00], d01 = a.disp[o01], d10 = a.disp[o10], d11 = a.disp[o11];
@@ -123,37 +147,27 @@ ddim_step_kernel(const dv_ddim_step_args a) {
     const XT sX = static_cast<XT>(a.scale);
     const float san32 = static_cast<float>(a.sqrt_alpha_next);   // 0-dim fp64 tensor times fp32 tensor: fp32 math
     const float sig32 = static_cast<float>(a.sigma);
-    const XT *xt = static_cast<const XT *>(a.xt);
-    const XT *sn = static_cast<const XT *>(a.step_noise);
 
     // UN hypotheses per pass: every global load of the pass is issued before its first store (the output pointers
     // are not provably distinct from the inputs, so without the explicit batching each iteration would serialise
     // load -> math -> store and the kernel is latency-bound: ncu r01, long-scoreboard 20 cycles per issue)
-    constexpr int UN = 3;
+    const double inv_recipm1 = 1.0 / a.sqrt_recipm1;
     for (int d0 = dg; d0 < D; d0 += UN * kDdimDg) {
-        XT xv[UN], snv[UN];
+        if (d0 != dg) load_state(d0);
         double rzv[UN], asv[UN], qnv[UN];
-        float shv[UN], shn[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             const int d = d0 + u * kDdimDg;
-            xv[u] = static_cast<XT>(0); snv[u] = static_cast<XT>(0); rzv[u] = 0.0; asv[u] = 0.0; qnv[u] = 0.0;
-            shv[u] = 0.0f; shn[u] = 0.0f;
-            if (d < D) {
+            rzv[u] = 0.0; asv[u] = 0.0; qnv[u] = 0.0;
+            if (d < D && !a.last_step) {
                 const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
-                xv[u] = xt[e];
-                if (a.shift) shv[u] = a.shift[b * D + d];
-                if (!a.last_step) {
-                    snv[u] = sn[e];
-                    if (a.n_next_out && a.shift_next) shn[u] = a.shift_next[b * D + d];
-                    if (a.renoise_mode == 1) {
-                        if (renoise_px) rzv[u] = static_cast<const double *>(a.renoise)[e];
-                    } else if (a.renoise_mode == 2) {
-                        asv[u] = a.asd_is_f64 ? static_cast<const double *>(a.asd)[e]
-                                              : static_cast<double>(static_cast<const float *>(a.asd)[e]);
-                        qnv[u] = a.q_noise_is_f64 ? static_cast<const double *>(a.q_noise)[e]
-                                                  : static_cast<double>(static_cast<const float *>(a.q_noise)[e]);
-                    }
+                if (a.renoise_mode == 1) {
+                    if (renoise_px) rzv[u] = static_cast<const double *>(a.renoise)[e];
+                } else if (a.renoise_mode == 2) {
+                    asv[u] = a.asd_is_f64 ? static_cast<const double *>(a.asd)[e]
+                                          : static_cast<double>(static_cast<const float *>(a.asd)[e]);
+                    qnv[u] = a.q_noise_is_f64 ? static_cast<const double *>(a.q_noise)[e]
+                                              : static_cast<double>(static_cast<const float *>(a.q_noise)[e]);
                 }
             }
         }
@@ -166,7 +180,7 @@ ddim_step_kernel(const dv_ddim_step_args a) {
             a.x0_out[e] = x0;
             // a8: pred_noise from the time-embedded, clamped, renormalised state (fp64)
             const XT n = filter_n<XT>(xv[u], shv[u], sX);
-            const double eps = (a.sqrt_recip * static_cast<double>(n) - static_cast<double>(x0)) / a.sqrt_recipm1;
+            const double eps = div_by_const(a.sqrt_recip * static_cast<double>(n) - static_cast<double>(x0), a.sqrt_recipm1, inv_recipm1);
             if (a.eps_out) a.eps_out[e] = eps;
             if (a.last_step) {
                 static_cast<float *>(a.x_next)[e] = x0;  // img = x_start (fp32)
@@ -272,15 +286,21 @@ extern "C" int dv_ddim_step(const dv_ddim_step_args *args, void *stream) {
         if (a.renoise_mode < 0 || a.renoise_mode > 2) return DV_ERR_BAD_DTYPE;
         if (a.renoise_mode != 0 && !a.mask) return DV_ERR_NULL;
     }
+    if (a.xt_is_f64 != 0 && a.xt_is_f64 != 1) return DV_ERR_BAD_DTYPE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dim3 grid(static_cast<unsigned>((a.h * a.w + kDdimPx - 1) / kDdimPx), static_cast<unsigned>(a.B));
-    dim3 block(kDdimPx, kDdimDg);
-    if (a.xt_is_f64 == 1)
-        ddim_step_kernel<double><<<grid, block, 0, st>>>(a);
-    else if (a.xt_is_f64 == 0)
-        ddim_step_kernel<float><<<grid, block, 0, st>>>(a);
-    else
-        return DV_ERR_BAD_DTYPE;
+    // block shape: measured best of {32x8, 64x4, 128x2, 256x1} (scripts/bench_ddim.py)
+    const int shape = tune_variant("DV_DDIM_SHAPE", 2);
+#define DV_DDIM(PX, DG)                                                                                              \
+    {                                                                                                                \
+        dim3 grid(static_cast<unsigned>((a.h * a.w + PX - 1) / PX), static_cast<unsigned>(a.B));                     \
+        dim3 block(PX, DG);                                                                                          \
+        if (a.xt_is_f64)                                                                                             \
+            ddim_step_kernel<double, PX, DG><<<grid, block, 0, st>>>(a);                                             \
+        else                                                                                                         \
+            ddim_step_kernel<float, PX, DG><<<grid, block, 0, st>>>(a);                                              \
+    }
+    if (shape == 0) DV_DDIM(32, 8) else if (shape == 1) DV_DDIM(64, 4) else if (shape == 3) DV_DDIM(256, 1) else DV_DDIM(128, 2)
+#undef DV_DDIM
     return finish_launch();
 }
 
