@@ -1,0 +1,69 @@
+// warp.cu — disparity-driven horizontal warp of the right features to the left view.
+//
+// Replaces warp(x, disp) of KITTI12/models/submodule.py:137-176 (= SceneFlow/submodule.py:188-227), the step right
+// before build_corrleation_volume in PCWNet's refinement (pwcnet_ddim.py:493-494).  The reference builds two [B,1,H,W]
+// mesh grids, normalises them, runs F.grid_sample twice (features, and a ones tensor for the validity mask) and
+// thresholds / multiplies the mask: ~15 launches and four full-resolution temporaries.  Here: one pass, thread =
+// (b, y, x) computes the sampling position and the four tap weights once and streams the C channels.
+//
+// Quirk reproduced: the grid is normalised as 2 v / (size - 1) - 1 (align_corners=True convention) but F.grid_sample
+// runs with its default align_corners=False, so ix = (x - disp) * W / (W - 1) - 0.5 and iy = y * H / (H - 1) - 0.5
+// (the warp is NOT purely horizontal: rows are resampled too).  Zero padding; mask = [sum of in-bounds weights >= 0.999].
+#include "common.cuh"
+
+namespace dv {
+
+__global__ void __launch_bounds__(256)
+warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *__restrict__ out, int C, int H, int W) {
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (px >= W) return;
+    const int64_t HW = static_cast<int64_t>(H) * W;
+    const float d = disp[static_cast<int64_t>(b) * HW + static_cast<int64_t>(y) * W + px];
+    // the reference's op sequence in fp32 (no contraction across its separate tensor ops)
+    const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(static_cast<float>(px), d)), static_cast<float>(max(W - 1, 1))), 1.0f);
+    const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, static_cast<float>(y)), static_cast<float>(max(H - 1, 1))), 1.0f);
+    const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), static_cast<float>(W)), 1.0f), 2.0f);
+    const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), static_cast<float>(H)), 1.0f), 2.0f);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f), x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = ix - x0f, wx0 = (x0f + 1.0f) - ix, wy1 = iy - y0f, wy0 = (y0f + 1.0f) - iy;
+    const bool okx0 = x0 >= 0 && x0 < W, okx1 = x1 >= 0 && x1 < W, oky0 = y0 >= 0 && y0 < H, oky1 = y1 >= 0 && y1 < H;
+    const float w00 = (okx0 && oky0) ? wx0 * wy0 : 0.0f, w01 = (okx1 && oky0) ? wx1 * wy0 : 0.0f;
+    const float w10 = (okx0 && oky1) ? wx0 * wy1 : 0.0f, w11 = (okx1 && oky1) ? wx1 * wy1 : 0.0f;
+    const float msum = ((w00 + w01) + w10) + w11;
+    const float m = msum < 0.999f ? 0.0f : 1.0f;
+    const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
+    const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+    const int64_t o00 = static_cast<int64_t>(cy0) * W + cx0, o01 = static_cast<int64_t>(cy0) * W + cx1;
+    const int64_t o10 = static_cast<int64_t>(cy1) * W + cx0, o11 = static_cast<int64_t>(cy1) * W + cx1;
+    const float *xp = x + static_cast<int64_t>(b) * C * HW;
+    float *op = out + static_cast<int64_t>(b) * C * HW + static_cast<int64_t>(y) * W + px;
+    if (m == 0.0f) {
+        for (int c = 0; c < C; ++c) op[static_cast<int64_t>(c) * HW] = 0.0f;
+        return;
+    }
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+        const float *pc = xp + static_cast<int64_t>(c) * HW;
+        float v = __fmul_rn(__ldg(pc + o00), w00);
+        v = __fadd_rn(v, __fmul_rn(__ldg(pc + o01), w01));
+        v = __fadd_rn(v, __fmul_rn(__ldg(pc + o10), w10));
+        v = __fadd_rn(v, __fmul_rn(__ldg(pc + o11), w11));
+        op[static_cast<int64_t>(c) * HW] = v;
+    }
+}
+
+}  // namespace dv
+
+extern "C" int dv_warp_f32(const float *x, const float *disp, float *out, int64_t B, int64_t C, int64_t H, int64_t W,
+                           void *stream) {
+    using namespace dv;
+    if (!x || !disp || !out) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
+    if (H * W > INT32_MAX || B > 65535 || H > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    dim3 grid(static_cast<unsigned>((W + 255) / 256), static_cast<unsigned>(H), static_cast<unsigned>(B));
+    warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, disp, out, static_cast<int>(C), static_cast<int>(H),
+                                                                   static_cast<int>(W));
+    return finish_launch();
+}

@@ -6,9 +6,10 @@ SceneFlow/submodule.py).
     build_concat_volume       KITTI12/models/submodule.py:86-97     (variant T: BOTH halves zero for x < d)
     build_corrleation_volume  KITTI12/models/submodule.py:121-135   (sic; two-sided, with the negative-shift quirk)
     disparity_regression      KITTI12/models/submodule.py:33-37
+    warp                      KITTI12/models/submodule.py:137-176   (grid_sample + validity mask, align_corners quirk)
 """
 from .functional import build_concat_volume_t as build_concat_volume
-from .functional import build_corrleation_volume, build_gwc_volume, groupwise_correlation
+from .functional import build_corrleation_volume, build_gwc_volume, groupwise_correlation, warp
 
 
 def disparity_regression(x, maxdisp):
@@ -17,4 +18,4 @@ def disparity_regression(x, maxdisp):
 
 
 __all__ = ["build_gwc_volume", "groupwise_correlation", "build_concat_volume", "build_corrleation_volume",
-           "disparity_regression"]
+           "disparity_regression", "warp"]

@@ -526,6 +526,20 @@ def ddim_step(*, disp: torch.Tensor, xt: torch.Tensor, shift: Optional[torch.Ten
     return {"x0": x0, "x_next": x_next, "eps": eps, "asd_out": asd_out, "n_next": n_next}
 
 
+def warp(x: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
+    """f3 — warp(x, disp) of KITTI12/models/submodule.py:137-176: x [B,C,H,W] (right features), disp [B,1,H,W]."""
+    B, C, H, W = x.shape
+    _need_cuda(x, disp)
+    x, disp = _f32c(x, "x"), _f32c(disp, "disp")
+    if disp.numel() != B * H * W:
+        raise RuntimeError(f"disp has shape {tuple(disp.shape)}, expected [B,1,{H},{W}]")
+    out = torch.empty_like(x)
+    if out.numel():
+        with torch.cuda.device(x.device):
+            check(_lib.lib().dv_warp_f32(_ptr(x), _ptr(disp), _ptr(out), B, C, H, W, _stream(x)), "dv_warp_f32")
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # backward passes (SURVEY.md §8f row f1)
 # --------------------------------------------------------------------------------------------

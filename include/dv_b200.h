@@ -276,6 +276,12 @@ int dv_concat_volume_bwd_f32(const float *grad_out, float *grad_ref, float *grad
 int dv_disparity_regression_bwd_f32(const float *grad_out, float *grad_x, int64_t B, int64_t D, int64_t H, int64_t W,
                                     void *stream);
 
+/* ---- f3: warp  (KITTI12/models/submodule.py:137-176; SceneFlow/submodule.py:188-227)
+ * out[b,c,y,x] = mask * bilinear(x_in[b,c], ix, iy), zero padding, ix = (x - disp[b,0,y,x]) * W/(W-1) - 0.5,
+ * iy = y * H/(H-1) - 0.5 (the reference's grid normalisation + grid_sample's default align_corners=False);
+ * mask = 0 where the in-bounds tap weights sum to < 0.999, else 1.                                              */
+int dv_warp_f32(const float *x, const float *disp, float *out, int64_t B, int64_t C, int64_t H, int64_t W, void *stream);
+
 /* ---- a13: ensemble (acv_ddim.py:365-369): out[p] = sum_i cof[i] * maps[i][p], i < n_maps <= 8
  * `maps` is a HOST array of n_maps device pointers, `cof` a HOST array of n_maps floats.          */
 int dv_ensemble_f32(const float *const *maps, const float *cof, int n_maps, float *out,

@@ -133,6 +133,37 @@ def renewal_vote(disp: np.ndarray, used: np.ndarray, unc: Optional[np.ndarray], 
     return m.astype(f32)
 
 
+def warp(x: np.ndarray, disp: np.ndarray) -> np.ndarray:
+    """KITTI12/models/submodule.py:137-176 (= SceneFlow/submodule.py:188-227): warp the right features to the left view.
+    x [B,C,H,W], disp [B,1,H,W].  The reference normalises the sampling grid as 2*v/(size-1)-1 (align_corners=True
+    convention) but calls F.grid_sample with its default align_corners=False, so the sampled coordinate is
+    ix = (x - disp) * W/(W-1) - 0.5, iy = y * H/(H-1) - 0.5 — reproduced here, zero padding, bilinear; the validity mask is
+    the same sampling of a ones tensor, thresholded (< 0.999 -> 0, else 1)."""
+    B, C, H, W = x.shape
+    xx = np.broadcast_to(np.arange(W, dtype=f32).reshape(1, 1, W), (B, H, W))
+    yy = np.broadcast_to(np.arange(H, dtype=f32).reshape(1, H, 1), (B, H, W))
+    gx = (f32(2.0) * (xx - disp[:, 0]).astype(f32) / f32(max(W - 1, 1)) - f32(1.0)).astype(f32)
+    gy = (f32(2.0) * yy / f32(max(H - 1, 1)) - f32(1.0)).astype(f32)
+    ix = (((gx + f32(1)) * f32(W) - f32(1)) / f32(2)).astype(f32)
+    iy = (((gy + f32(1)) * f32(H) - f32(1)) / f32(2)).astype(f32)
+    x0, y0 = np.floor(ix), np.floor(iy)
+    x1, y1 = x0 + 1, y0 + 1
+    wts = [((x1 - ix) * (y1 - iy), x0, y0), ((ix - x0) * (y1 - iy), x1, y0),
+           ((x1 - ix) * (iy - y0), x0, y1), ((ix - x0) * (iy - y0), x1, y1)]
+    out = np.zeros_like(x, dtype=f32)
+    mask = np.zeros((B, H, W), dtype=f32)
+    bi = np.arange(B).reshape(B, 1, 1)
+    for wgt, xi, yi in wts:
+        ok = (xi >= 0) & (xi <= W - 1) & (yi >= 0) & (yi <= H - 1)
+        xc, yc = np.clip(xi, 0, W - 1).astype(np.int64), np.clip(yi, 0, H - 1).astype(np.int64)
+        wv = np.where(ok, wgt, f32(0)).astype(f32)
+        vals = x[bi, :, yc, xc]                      # [B,H,W,C]
+        out += (np.moveaxis(vals, -1, 1) * wv[:, None]).astype(f32)
+        mask += wv
+    mask = np.where(mask < f32(0.999), f32(0), f32(1)).astype(f32)
+    return (out * mask[:, None]).astype(f32)
+
+
 # =============================================================================================
 # diffusion schedule (fp64) — a7, a8, a12 coefficients
 # =============================================================================================

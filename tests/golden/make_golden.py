@@ -52,6 +52,9 @@ def _sample(a: np.ndarray, n: int = 4096) -> np.ndarray:
     return flat[idx]
 
 
+# warp cases: name -> (shape [B,C,H,W], seed, disparity amplitude)
+WARP_CASES = {"small": ((2, 6, 9, 40), 61, 30.0), "odd": ((1, 3, 7, 13), 63, 8.0), "wide": ((1, 4, 5, 156), 65, 60.0)}
+
 # volume cases shared by the sub-projects: name -> (B, C, G, D, H, W, seed)
 GWC_CASES = {
     "w39": (2, 32, 4, 6, 12, 39, 11),        # PCWNet 1/32 scale width (W % 4 != 0, HW % 4 == 0)
@@ -266,6 +269,12 @@ def gen_kitti12():
     out["k12.corr2.m24"] = sub.build_corrleation_volume(_t(ref), _t(tgt), 24, 1).numpy()
     ref, tgt = synth.normal((1, 32, 6, 80), 43), synth.normal((1, 32, 6, 80), 1043)
     out["k12.corr2.w80_m24"] = sub.build_corrleation_volume(_t(ref), _t(tgt), 24, 1).numpy()
+    # warp (KITTI12/models/submodule.py:137-176): x.get_device() is -1 on the CPU, which torch.arange rejects
+    torch.Tensor.get_device = lambda self: self.device
+    for key, (shape, seed, amp) in WARP_CASES.items():
+        x = synth.normal(shape, seed)
+        disp = synth.uniform((shape[0], 1, shape[2], shape[3]), seed + 1, dtype=np.float32) * np.float32(amp) - np.float32(3)
+        out["k12.warp." + key] = sub.warp(_t(x), _t(disp)).detach().numpy()
     np.savez_compressed(HERE / "kitti12.npz", **out)
     print("kitti12:", len(out), "arrays")
 

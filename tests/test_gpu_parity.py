@@ -10,7 +10,7 @@ import torch
 
 import synth
 from conftest import rel_max_err
-from golden.make_golden import CONCAT_CASES, GWC_CASES, trace_inputs
+from golden.make_golden import CONCAT_CASES, GWC_CASES, WARP_CASES, trace_inputs
 from oracle import dv_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -422,6 +422,41 @@ def test_geo_lookup_igev_shape_vs_oracle(ops):
 # ------------------------------------------------------------------------------------------------
 # loud failure on CPU tensors (no fallback)
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# f3: warp
+# ------------------------------------------------------------------------------------------------
+def _warp_inputs(shape, seed, amp):
+    x = synth.normal(shape, seed)
+    disp = synth.uniform((shape[0], 1, shape[2], shape[3]), seed + 1, dtype=np.float32) * np.float32(amp) - np.float32(3)
+    return x, disp
+
+
+@pytest.mark.parametrize("case", list(WARP_CASES))
+def test_warp_golden(ops, golden, case):
+    shape, seed, amp = WARP_CASES[case]
+    x, disp = _warp_inputs(shape, seed, amp)
+    got = host(ops.warp(cu(x), cu(disp)))
+    want = golden["k12.warp." + case]
+    assert np.array_equal(got == 0, want == 0)          # the validity mask agrees everywhere
+    assert np.abs(got - want).max() < 5e-5
+
+
+def test_warp_fullres_vs_oracle_and_autograd(ops):
+    x, disp = _warp_inputs((1, 32, 24, 1248), 67, 150.0)
+    got = host(ops.warp(cu(x), cu(disp)))
+    want = O.warp(x, disp)
+    assert np.array_equal(got == 0, want == 0)
+    assert np.abs(got - want).max() < 2e-4               # |x| ~ 4 sigma, ix up to 1248: fp32 coordinate rounding
+    # the autograd Function differentiates through the reference's own grid_sample sequence
+    from diffuvolume_b200 import functional as Fn
+    xs, ds = _warp_inputs((1, 4, 6, 20), 69, 10.0)
+    xt, dt = cu(xs).requires_grad_(True), cu(ds).requires_grad_(True)
+    out = Fn.warp(xt, dt)
+    out.sum().backward()
+    assert xt.grad is not None and dt.grad is not None and torch.isfinite(xt.grad).all() and torch.isfinite(dt.grad).all()
+    assert np.abs(host(out) - O.warp(xs, ds)).max() < 1e-5
+
+
 def test_cpu_tensor_raises(ops):
     from diffuvolume_b200._lib import DvLibraryError
     x = torch.zeros(1, 8, 4, 8)

@@ -8,7 +8,7 @@ import pytest
 
 import synth
 from conftest import rel_max_err
-from golden.make_golden import CONCAT_CASES, GWC_CASES, trace_inputs
+from golden.make_golden import CONCAT_CASES, GWC_CASES, WARP_CASES, trace_inputs
 from oracle import dv_oracle as O
 
 TOL = 1e-6  # fp32 restatement vs fp32 reference (different summation order only)
@@ -224,3 +224,14 @@ def test_oracle_trilinear_matches_torch(shape, size, align_corners):
     want = F.interpolate(torch.from_numpy(x), size=size, mode="trilinear", align_corners=align_corners).numpy()
     got = O.interpolate_trilinear(x, size, align_corners=align_corners)
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", list(WARP_CASES))
+def test_oracle_warp_golden(golden, case):
+    """O.warp against the reference's own warp() (KITTI12/models/submodule.py:137-176) run on the CPU."""
+    shape, seed, amp = WARP_CASES[case]
+    x = synth.normal(shape, seed)
+    disp = synth.uniform((shape[0], 1, shape[2], shape[3]), seed + 1, dtype=np.float32) * np.float32(amp) - np.float32(3)
+    got, want = O.warp(x, disp), golden["k12.warp." + case]
+    assert np.array_equal(got == 0, want == 0)
+    assert np.abs(got - want).max() < 5e-5
