@@ -351,11 +351,13 @@ __global__ void att_softmax_generic_kernel(const float *__restrict__ att, float 
 // n[b,d,p] = float(((clamp(xt + shift[b,d], -s, s) / s) + 1) / 2)   (acv_ddim.py:256-258)
 template <typename XT>
 __global__ void filter_factor_kernel(const XT *__restrict__ xt, const float *__restrict__ shift, XT scale,
-                                     float *__restrict__ nf, int HW, int64_t total) {
+                                     float *__restrict__ nf, XT *__restrict__ n_native, int HW, int64_t total) {
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t bd = idx / HW;
-        nf[idx] = static_cast<float>(filter_n<XT>(xt[idx], shift ? shift[bd] : 0.0f, scale));
+        const XT n = filter_n<XT>(xt[idx], shift ? shift[bd] : 0.0f, scale);
+        if (nf) nf[idx] = static_cast<float>(n);
+        if (n_native) n_native[idx] = n;
     }
 }
 
@@ -497,11 +499,11 @@ extern "C" int dv_att_softmax_f32(const float *att_logits, float *weights, int64
     return finish_launch();
 }
 
-extern "C" int dv_filter_factor_f32(const void *xt, int xt_is_f64, const float *shift, double scale, float *n_out,
-                                    int64_t B, int64_t D, int64_t H, int64_t W, void *stream) {
+extern "C" int dv_filter_factor(const void *xt, int xt_is_f64, const float *shift, double scale, float *n_out_f32,
+                                void *n_out_native, int64_t B, int64_t D, int64_t H, int64_t W, void *stream) {
     using namespace dv;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!xt || !n_out) return DV_ERR_NULL;
+    if (!xt || (!n_out_f32 && !n_out_native)) return DV_ERR_NULL;
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || !(scale > 0.0)) return DV_ERR_BAD_SHAPE;
     if (xt_is_f64 != 0 && xt_is_f64 != 1) return DV_ERR_BAD_DTYPE;
     const int64_t HW = H * W;
@@ -510,12 +512,17 @@ extern "C" int dv_filter_factor_f32(const void *xt, int xt_is_f64, const float *
     const int64_t blocks = (total + 255) / 256;
     const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 16 ? blocks : static_cast<int64_t>(kNumSMs) * 16);
     if (xt_is_f64)
-        filter_factor_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double *>(xt), shift, scale, n_out,
-                                                           static_cast<int>(HW), total);
+        filter_factor_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double *>(xt), shift, scale, n_out_f32,
+                                                           static_cast<double *>(n_out_native), static_cast<int>(HW), total);
     else
         filter_factor_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(xt), shift, static_cast<float>(scale),
-                                                          n_out, static_cast<int>(HW), total);
+                                                          n_out_f32, static_cast<float *>(n_out_native), static_cast<int>(HW), total);
     return finish_launch();
+}
+
+extern "C" int dv_filter_factor_f32(const void *xt, int xt_is_f64, const float *shift, double scale, float *n_out,
+                                    int64_t B, int64_t D, int64_t H, int64_t W, void *stream) {
+    return dv_filter_factor(xt, xt_is_f64, shift, scale, n_out, nullptr, B, D, H, W, stream);
 }
 
 extern "C" int dv_concat_volume_weighted_f32(const float *ref, const float *tgt, float *out, int64_t B, int64_t C,

@@ -46,6 +46,8 @@ _TIER2 = {
     "kitti15": [("core.igev_stereo_ddim", "IGEVStereo_ddim", {
         "q_sample": sampler.q_sample,
         "predict_noise_from_start": sampler.predict_noise_from_start,
+        "model_predictions": sampler.igev_model_predictions,
+        "ddim_sample": sampler.igev_ddim_sample,
     })],
 }
 

@@ -176,6 +176,24 @@ def filter_factor(xt: torch.Tensor, shift: Optional[torch.Tensor] = None, scale:
     return out
 
 
+def filter_factor_pair(xt: torch.Tensor, shift: Optional[torch.Tensor] = None, scale: float = 1.0):
+    """a9 factor in both precisions: (n in the dtype of xt — the tensor predict_noise_from_start consumes —, n as fp32 —
+    the tensor that multiplies the volume / the IGEV geometry lookup)."""
+    _need_cuda(xt, shift)
+    B, D, H, W = xt.shape
+    f64 = _is_f64(xt, "xt")
+    xt = xt.contiguous()
+    if shift is not None:
+        shift = _f32c(shift.reshape(B, D), "shift")
+    n_native = torch.empty_like(xt)
+    n32 = torch.empty((B, D, H, W), dtype=torch.float32, device=xt.device) if f64 else None
+    if xt.numel():
+        with torch.cuda.device(xt.device):
+            check(_lib.lib().dv_filter_factor(_ptr(xt), f64, _ptr(shift), float(scale), _ptr(n32), _ptr(n_native), B, D, H, W,
+                                              _stream(xt)), "dv_filter_factor")
+    return n_native, (n32 if f64 else n_native)
+
+
 def concat_volume_weighted(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, *, mask_left: bool,
                            att_weights: Optional[torch.Tensor] = None, n: Optional[torch.Tensor] = None,
                            out: Optional[torch.Tensor] = None) -> torch.Tensor:

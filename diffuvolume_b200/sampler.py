@@ -5,6 +5,9 @@ dtypes), so the conv stacks, parameters and checkpoints stay the reference's.
 
 ACVNet_DDIM   (SceneFlow/models/acv_ddim.py):  q_sample :241-246, predict_noise_from_start :248-252,
                                                model_predictions :254-296, ddim_sample :298-370
+IGEVStereo_ddim (KITTI15/core/igev_stereo_ddim.py): q_sample :213-218, predict_noise_from_start :220-224,
+                                               model_predictions :226-292, ddim_sample :294-359 (the GRU iteration
+                                               loop keeps the reference's update block / upsampler modules)
 PWCNet_ddim   (KITTI12/models/pwcnet_ddim.py): q_sample :453-458, predict_noise_from_start :460-464,
                                                ddim_sample :530-602 (model_predictions keeps the reference's
                                                conv / warp / refinement code, with the fused filter,
@@ -229,3 +232,109 @@ def pcw_ddim_sample(self, volume, used, asd, features_left, features_right):
         final = ops.ensemble(disps, cof[: len(disps)])
         return final, pred3_volume
     return disp, pred3_volume
+
+
+# ------------------------------------------------------------------------------------------------
+# IGEVStereo_ddim
+# ------------------------------------------------------------------------------------------------
+def _igev_autocast(self):
+    """`autocast(enabled=self.args.mixed_precision)` as the reference module defines it (igev_stereo_ddim.py:13-22)."""
+    import sys
+    mod = sys.modules.get(type(self).__module__)
+    ac = getattr(mod, "autocast", None)
+    if ac is not None:
+        return ac(enabled=self.args.mixed_precision)
+    return torch.autocast("cuda", enabled=bool(self.args.mixed_precision))
+
+
+def _igev_gru_loop(self, coords0, coords1, flow_init, iters, net_list, inp_list, corr_fn, n32, stem_2x):
+    """The GRU iteration loop of IGEVStereo_ddim.model_predictions (igev_stereo_ddim.py:233-264): the update block and the
+    convex upsampler are the reference's own modules; every `corr_fn` call is the fused geometry lookup kernel."""
+    if flow_init is not None:
+        coords1 = coords1 + flow_init
+    flow_up = None
+    for itr in range(iters):
+        coords1 = coords1.detach()
+        flow = coords1 - coords0
+        corr = corr_fn(flow, coords1, n32)
+        with _igev_autocast(self):
+            if self.args.n_gru_layers == 3 and self.args.slow_fast_gru:
+                net_list = self.update_block(net_list, inp_list, iter32=True, iter16=False, iter08=False, update=False)
+            if self.args.n_gru_layers >= 2 and self.args.slow_fast_gru:
+                net_list = self.update_block(net_list, inp_list, iter32=self.args.n_gru_layers == 3, iter16=True, iter08=False,
+                                             update=False)
+            net_list, up_mask, delta_flow = self.update_block(net_list, inp_list, corr, flow,
+                                                              iter16=self.args.n_gru_layers == 3,
+                                                              iter08=self.args.n_gru_layers >= 2)
+        coords1 = coords1 + delta_flow
+        if itr < iters - 1:
+            continue
+        if up_mask is None:
+            import sys
+            upflow8 = getattr(sys.modules.get(type(self).__module__), "upflow8")
+            flow_up = upflow8(coords1 - coords0)
+        else:
+            flow_up = self.upsample_disp(coords1 - coords0, up_mask, stem_2x)
+        flow_up = flow_up[:, :1]
+    return flow_up, coords1
+
+
+def igev_model_predictions(self, coords0, coords1, flow_init, iters, net_list, inp_list, corr_fn, noise, t, stem_2x):
+    """IGEVStereo_ddim.model_predictions (igev_stereo_ddim.py:226-292): returns (pred_noise, x_start, pred, coords1)."""
+    b, D = noise.shape[0], noise.shape[1]
+    ti = _time_index(t)
+    hb = _host_buffers(self)
+    shift = _time_shift(self, t, b, D, noise.device)
+    n, n32 = ops.filter_factor_pair(noise, shift, self.scale)
+    pred, coords1 = _igev_gru_loop(self, coords0, coords1, flow_init, iters, net_list, inp_list, corr_fn, n32, stem_2x)
+    H, W = pred.shape[-2:]
+    disp_q = ops.downsample_bilinear(pred.float().reshape(b, H, W), (H // 4, W // 4), clamp=(0, D - 1), post_scale=0.25)
+    true_coords1 = torch.clamp(coords0.reshape(b, H // 4, W // 4).float() + disp_q, 0, D - 1)
+    x_start = ops.xstart_from_disp(true_coords1, D, self.scale)
+    pred_noise = ops.predict_noise_from_start(n, x_start, hb["sqrt_recip"][ti], hb["sqrt_recipm1"][ti])
+    return pred_noise, x_start, pred, coords1
+
+
+@torch.no_grad()
+def igev_ddim_sample(self, coords0, coords1, flow_init, iters, net_list, inp_list, corr_fn, used, asd, stem_2x):
+    """IGEVStereo_ddim.ddim_sample (igev_stereo_ddim.py:294-359): T = 2 DDIM steps around the GRU loop; renewal vote
+    |disp - used| < 5, fallback to `used` where |disp - used| >= 3, non-cumulative re-noising q_sample(asd, t), ensemble
+    [0.6, 0.1, 0.3].  RNG draws in the reference's order: randn_like(asd) (start state), then per non-final step
+    randn_like(img), randint, randn_like(asd) (inside q_sample).  The reference is only shape-consistent for batch 1
+    (its `where(mask.unsqueeze(1) == 0, used, disp)` broadcasts across the batch); this follows it exactly at B = 1
+    and treats every sample independently otherwise."""
+    batch, d, h, w = asd.shape
+    dev = asd.device
+    hb = _host_buffers(self)
+    pairs = _time_pairs(self)
+    img = torch.randn_like(asd, device=dev)
+    used_map = used.float().reshape(batch, used.shape[-2], used.shape[-1]).contiguous()
+    H, W = used_map.shape[-2:]
+    c0 = coords0.float().reshape(batch, h, w).contiguous()
+    disps = [used_map]
+    mask = torch.zeros((batch, h, w), dtype=torch.float32, device=dev)
+    for time, time_next in pairs:
+        time_cond = torch.full((batch,), time, device=dev, dtype=torch.long)
+        shift = _time_shift(self, time_cond, batch, d, dev)
+        n32 = ops.filter_factor(img, shift, self.scale)
+        pred, coords1 = _igev_gru_loop(self, coords0, coords1, flow_init, iters, net_list, inp_list, corr_fn, n32, stem_2x)
+        disp = pred.float().reshape(batch, H, W).contiguous()
+        # fallback to the initial disparity where the sampled one strays (igev_stereo_ddim.py:323-325)
+        disps.append(torch.where(torch.abs(disp - used_map) < 3, disp, used_map))
+        last = time_next < 0
+        kw = {}
+        if not last:
+            san, c, sigma = _update_coefficients(self, time, time_next)
+            noise = torch.randn_like(img)
+            torch.randint(time, time + 1, (1,), device=dev)
+            qn = torch.randn_like(asd)
+            kw = dict(sqrt_alpha_next=san, c=c, sigma=sigma, step_noise=noise, asd=asd, q_noise=qn,
+                      sqrt_ac=hb["sqrt_ac"][time], sqrt_1m_ac=hb["sqrt_1m_ac"][time])
+        st = ops.ddim_step(disp=disp, xt=img, shift=shift, scale=self.scale, sqrt_recip=hb["sqrt_recip"][time],
+                           sqrt_recipm1=hb["sqrt_recipm1"][time], last_step=last, disp_clamp_hi=float(d - 1), coords0=c0,
+                           used=used_map if self.renewal else None, vote_thr_dif=5.0, mask=mask, **kw)
+        img = st["x_next"]
+    if self.use_ensemble:
+        cof = [0.6, 0.1, 0.3]
+        return ops.ensemble(disps, cof[: len(disps)])
+    return disps[-1]

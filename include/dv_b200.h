@@ -88,6 +88,10 @@ int dv_att_softmax_f32(const float *att_logits, float *weights, int64_t B, int64
                        void *stream);
 int dv_filter_factor_f32(const void *xt, int xt_is_f64, const float *shift, double scale, float *n_out,
                          int64_t B, int64_t D, int64_t H, int64_t W, void *stream);
+/* the same factor in the dtype of xt (n_out_native, what predict_noise_from_start consumes: acv_ddim.py:294,
+ * igev_stereo_ddim.py:290) and / or as fp32 (n_out_f32, what multiplies the volume); either may be NULL            */
+int dv_filter_factor(const void *xt, int xt_is_f64, const float *shift, double scale, float *n_out_f32,
+                     void *n_out_native, int64_t B, int64_t D, int64_t H, int64_t W, void *stream);
 int dv_concat_volume_weighted_f32(const float *ref, const float *tgt, float *out,
                                   int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int mask_left,
                                   const float *att_weights, const float *n, void *stream);

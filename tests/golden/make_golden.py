@@ -279,6 +279,72 @@ def gen_kitti12():
     print("kitti12:", len(out), "arrays")
 
 
+def _igev_sampler_trace(out, GeoDdim):
+    """Trace of the REFERENCE's IGEVStereo_ddim.ddim_sample / model_predictions (KITTI15/core/igev_stereo_ddim.py:226-359).
+    The class itself cannot be constructed (timm / opt_einsum / pretrained download), so its unmodified sampler methods
+    are bound onto tests/igev_mock.py:MockIGEV; `timm` and `opt_einsum` are stubbed only to make the module importable."""
+    import types
+    import torch
+    for name in ("timm", "opt_einsum"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    if not hasattr(sys.modules["opt_einsum"], "contract"):
+        sys.modules["opt_einsum"].contract = lambda *a, **k: None
+    import core.igev_stereo_ddim as M
+    from igev_mock import IGEV_TRACE, MockIGEV, igev_trace_inputs
+    sys.path.insert(0, str(HERE.parent.parent))
+    from oracle import dv_oracle as O
+
+    inp = igev_trace_inputs("cpu")
+    net = MockIGEV(O.Schedule(), inp["shifts"])
+    for name in ("q_sample", "predict_noise_from_start", "model_predictions", "ddim_sample"):
+        setattr(MockIGEV, name, getattr(M.IGEVStereo_ddim, name))
+    geo_fn = GeoDdim(inp["f1"], inp["f2"], inp["geo"], radius=4, num_levels=2)
+    # asd = x_start of the (quarter-res) ground-truth / origin disparity: the reference's inline code (:403-420)
+    b, _, h, w = inp["gt_q"].shape
+    tc = torch.clamp(inp["gt_q"], 0, 48 - 1)
+    dv = torch.zeros([b, 48, h, w], dtype=torch.float32)
+    real = torch.floor(tc).long()
+    mask = real == 47
+    coff = real - tc + 1
+    dv = dv.view(b, 48, -1).scatter_(1, real.view(b, 1, -1), coff.view(b, 1, -1)).reshape(b, 48, h, w)
+    dv = dv.view(b, 48, -1).scatter_(1, torch.clamp(real + 1, 0, 47).view(b, 1, -1), (1 - coff).view(b, 1, -1)).reshape(b, 48, h, w)
+    fuzhi = torch.zeros([b, 48, h, w], dtype=torch.float32)
+    fuzhi[:, -1] = 1
+    asd = (torch.where(mask == True, fuzhi, dv) * 2 - 1) * net.scale  # noqa: E712
+    out["igev.asd"] = asd.numpy()
+
+    rec = {"img": [], "eps": [], "x0": [], "disp": [], "coords1": []}
+    orig_mp = net.model_predictions
+
+    def mp(*a):
+        rec["img"].append(a[7].detach().clone())
+        r = orig_mp(*a)
+        for key, v in zip(("eps", "x0", "disp", "coords1"), r):
+            rec[key].append(v.detach().clone())
+        return r
+    net.model_predictions = mp
+    k = {"n": 0}
+    seeds = []
+    o_randn_like = torch.randn_like
+
+    def randn_like(x, **kw):
+        seed = 3000 + k["n"]; k["n"] += 1
+        seeds.append((seed, 1 if x.dtype == torch.float64 else 0))
+        return _t(synth.normal(tuple(x.shape), seed, dtype=np.float64)).to(x.dtype)
+    torch.randn_like = randn_like
+    try:
+        with torch.no_grad():
+            pred = net.ddim_sample(inp["init_disp"], inp["init_disp"], None, IGEV_TRACE["iters"], [], [], geo_fn, inp["used"],
+                                   asd, None)
+    finally:
+        torch.randn_like = o_randn_like
+    out["igev.pred"] = pred.numpy()
+    for key, lst in rec.items():
+        for i, v in enumerate(lst):
+            out[f"igev.{key}.{i}"] = v.numpy()
+    out["igev.randn_like_seeds"] = np.array(seeds, dtype=np.int64)
+
+
 def gen_kitti15():
     import torch
     sys.path.insert(0, str(REF / "KITTI15"))
@@ -314,6 +380,7 @@ def gen_kitti15():
         z = torch.zeros(B, D, 1, 1)
         out["k15.head.shift48"] = dh(z, tc).reshape(B, D).numpy()
         out["k15.head.raw180"] = dh.block_time_mlp(dh.time_mlp(tc)).numpy()
+    _igev_sampler_trace(out, GeoDdim)
     np.savez_compressed(HERE / "kitti15.npz", **out)
     print("kitti15:", len(out), "arrays")
 

@@ -45,7 +45,7 @@ class MockIGEV(nn.Module):
 
     def update_block(self, net_list, inp_list, corr=None, flow=None, iter08=True, iter16=True, iter32=True, update=True):
         c = corr.float()
-        delta = 0.6 * torch.tanh(0.2 * c[:, :72].mean(1, keepdim=True) + 0.1 * c[:, 81:].mean(1, keepdim=True)) - 0.02 * flow
+        delta = 0.6 * torch.tanh(4.0 * c[:, :72].mean(1, keepdim=True) + 2.0 * c[:, 81:].mean(1, keepdim=True)) - 0.02 * flow
         return net_list, torch.ones(1, device=corr.device), delta
 
     def upsample_disp(self, disp, mask_feat_4, stem_2x):
@@ -61,9 +61,10 @@ def igev_trace_inputs(device="cpu"):
     f1, f2 = synth.normal((B, c["Cf"], h, w), 401), synth.normal((B, c["Cf"], h, w), 402)
     geo = synth.normal((B, c["Cg"], D, h, w), 403)
     init_disp = synth.uniform((B, 1, h, w), 404, dtype=np.float32) * np.float32(40.0)
-    # the origin model's full-resolution disparity (`flow_full`): x4 upsampled init disparity plus a perturbation
-    up = np.repeat(np.repeat(init_disp, 4, axis=2), 4, axis=3) * np.float32(4.0)
-    used = (up + synth.normal((B, 1, H, W), 405) * np.float32(3.0)).astype(np.float32)
+    # `used` (flow_full in the reference's forward) is compared with the up-sampled flow coords1 - coords0, which starts
+    # at zero in this variant (ddim_sample(disp, disp, ...), igev_stereo_ddim.py:424): keep it of the same magnitude so
+    # that the renewal mask (< 5) and the fallback (< 3) both fire on part of the image
+    used = (synth.normal((B, 1, H, W), 405) * np.float32(3.0)).astype(np.float32)
     gt_q = np.clip(init_disp + synth.normal((B, 1, h, w), 406) * np.float32(1.5), 0, 47).astype(np.float32)
     shifts = {tt: t(synth.normal((B, D), 410 + i) * np.float32(0.1)) for i, tt in enumerate(c["times"])}
     return dict(f1=t(f1), f2=t(f2), geo=t(geo), init_disp=t(init_disp), used=t(used), gt_q=t(gt_q), shifts=shifts)
