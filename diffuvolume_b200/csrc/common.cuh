@@ -157,13 +157,21 @@ __device__ __forceinline__ float ldg_stream_f32(const float *p) {
 // n = ((clamp(xt + shift, -s, s) / s) + 1) / 2 in the dtype of xt, then float()
 // (SceneFlow/models/acv_ddim.py:256-260)
 template <typename T>
+__device__ __noinline__ T divide_noinline(T a, T b) {
+    return a / b;
+}
+
+template <typename T>
 __device__ __forceinline__ T filter_n(T xt, float shift, T s) {
     T v = xt + static_cast<T>(shift);
     v = v < -s ? -s : (v > s ? s : v);
     // v / s is the identity for the reference's scale (self.scale = 1.0, acv_ddim.py:131) and (r + 1) / 2 == (r + 1) * 0.5
     // exactly: no division is issued on the hot path (an fp64 division is ~30 instructions; ncu r01b showed the fused DDIM
     // step executing 237 instructions per element because of five of them).
-    const T r = (s == static_cast<T>(1)) ? v : v / s;
+    // (ptxas if-converts `s == 1 ? v : v / s` and runs the inlined division sequence regardless — 19 DFMA + 2 MUFU per
+    // element in ncu r01c — so the general case lives behind a call that cannot be speculated)
+    T r = v;
+    if (s != static_cast<T>(1)) r = divide_noinline(v, s);
     return (r + static_cast<T>(1)) * static_cast<T>(0.5);
 }
 

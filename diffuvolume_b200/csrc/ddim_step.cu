@@ -72,7 +72,8 @@ __device__ __forceinline__ float x0_from_tap(const TwoTap &t, int d, int D, floa
 
 // CTA = kDdimPx pixels (x) x kDdimDg hypothesis groups (y): thread (px, dg) owns d = dg, dg + kDdimDg, ...
 
-template <typename XT, int kDdimPx, int kDdimDg>
+// MODE = renoise_mode (0 none, 1 given tensor, 2 q_sample(asd)); LAST = the final DDIM step (x_next = x0, fp32).
+template <typename XT, int kDdimPx, int kDdimDg, int MODE, bool LAST>
 __global__ void __launch_bounds__(kDdimPx * kDdimDg)
 ddim_step_kernel(const dv_ddim_step_args a) {
     const int hw = static_cast<int>(a.h * a.w);
@@ -89,30 +90,36 @@ ddim_step_kernel(const dv_ddim_step_args a) {
     const int64_t o00 = fb + static_cast<int64_t>(ty.i0) * W + tx.i0, o01 = fb + static_cast<int64_t>(ty.i0) * W + tx.i1;
     const int64_t o10 = fb + static_cast<int64_t>(ty.i1) * W + tx.i0, o11 = fb + static_cast<int64_t>(ty.i1) * W + tx.i1;
 
-    // The state loads of the first pass do not depend on the taps / mask below: issue them first so that their
-    // latency overlaps the dependent tap -> mask -> barrier chain.
+    // Running element offset of (b, d = dg + i*kDdimDg, pix): one 64-bit add per hypothesis instead of an IMAD chain per
+    // array (ncu r01c: 31 IMAD + 8 LDC per element in the generic loop); every pointer is read from the argument
+    // struct once.
     constexpr int UN = 3;
-    const XT *xt = static_cast<const XT *>(a.xt);
-    const XT *sn = static_cast<const XT *>(a.step_noise);
+    const int64_t e0 = (static_cast<int64_t>(b) * D + dg) * hw + pix;
+    const int64_t es = static_cast<int64_t>(kDdimDg) * hw;
+    const int nsteps = dg < D ? (D - dg + kDdimDg - 1) / kDdimDg : 0;
+    const XT *__restrict__ xt = static_cast<const XT *>(a.xt) + e0;
+    const XT *__restrict__ sn = LAST ? nullptr : static_cast<const XT *>(a.step_noise) + e0;
+    const float *__restrict__ shp = a.shift ? a.shift + b * D + dg : nullptr;
+    const float *__restrict__ shnp = (!LAST && a.n_next_out && a.shift_next) ? a.shift_next + b * D + dg : nullptr;
     XT xv[UN], snv[UN];
     float shv[UN], shn[UN];
-    auto load_state = [&](int d0) {
+    // The state loads do not depend on the taps / mask below: the first pass is issued before that dependent chain.
+    auto load_state = [&](int i0) {
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-            const int d = d0 + u * kDdimDg;
             xv[u] = static_cast<XT>(0); snv[u] = static_cast<XT>(0); shv[u] = 0.0f; shn[u] = 0.0f;
-            if (d < D) {
-                const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
-                xv[u] = xt[e];
-                if (a.shift) shv[u] = a.shift[b * D + d];
-                if (!a.last_step) {
-                    snv[u] = sn[e];
-                    if (a.n_next_out && a.shift_next) shn[u] = a.shift_next[b * D + d];
+            if (i0 + u < nsteps) {
+                const int64_t o = (i0 + u) * es;
+                xv[u] = xt[o];
+                if (shp) shv[u] = shp[(i0 + u) * kDdimDg];
+                if (!LAST) {
+                    snv[u] = sn[o];
+                    if (shnp) shn[u] = shnp[(i0 + u) * kDdimDg];
                 }
             }
         }
     };
-    load_state(dg);
+    load_state(0);
 
     // ---- a10: down-sampled disparity -> 2-tap x_start
     const float d00 = a.disp[o00], d01 = a.disp[o01], d10 = a.disp[o10], d11 = a.disp[o11];
@@ -141,70 +148,78 @@ ddim_step_kernel(const dv_ddim_step_args a) {
     __syncthreads();
     if (a.mask && (a.vote || a.used) && dg == 0 && live) a.mask[static_cast<int64_t>(b) * hw + pix] = m;
     if (!live) return;
-    const bool renoise_px = (a.renoise_mode != 0) && (m == 0.0f);
+    const bool renoise_px = (MODE != 0) && (m == 0.0f);
 
     const float s32 = static_cast<float>(a.scale);
     const XT sX = static_cast<XT>(a.scale);
+    const double sD = a.scale;
     const float san32 = static_cast<float>(a.sqrt_alpha_next);   // 0-dim fp64 tensor times fp32 tensor: fp32 math
     const float sig32 = static_cast<float>(a.sigma);
+    const double sqrt_recip = a.sqrt_recip, sqrt_recipm1 = a.sqrt_recipm1, cc = a.c, sigma = a.sigma;
+    const double sqrt_ac = a.sqrt_ac, sqrt_1m_ac = a.sqrt_1m_ac;
+    const double inv_recipm1 = 1.0 / sqrt_recipm1;
+    float *__restrict__ x0p = a.x0_out + e0;
+    double *__restrict__ epsp = a.eps_out ? a.eps_out + e0 : nullptr;
+    float *__restrict__ nnp = (!LAST && a.n_next_out) ? a.n_next_out + e0 : nullptr;
+    double *__restrict__ asdo = (MODE == 2 && a.asd_out) ? a.asd_out + e0 : nullptr;
+    const double *__restrict__ rzp = MODE == 1 ? static_cast<const double *>(a.renoise) + e0 : nullptr;
 
-    // UN hypotheses per pass: every global load of the pass is issued before its first store (the output pointers
-    // are not provably distinct from the inputs, so without the explicit batching each iteration would serialise
-    // load -> math -> store and the kernel is latency-bound: ncu r01, long-scoreboard 20 cycles per issue)
-    const double inv_recipm1 = 1.0 / a.sqrt_recipm1;
-    for (int d0 = dg; d0 < D; d0 += UN * kDdimDg) {
-        if (d0 != dg) load_state(d0);
+    // UN hypotheses per pass: every global load of the pass is issued before its first store (the outputs are not
+    // provably distinct from the inputs for the compiler, so each iteration would otherwise serialise load -> math -> store)
+    for (int i0 = 0; i0 < nsteps; i0 += UN) {
+        if (i0 != 0) load_state(i0);
         double rzv[UN], asv[UN], qnv[UN];
+        if (!LAST && MODE != 0) {
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const int d = d0 + u * kDdimDg;
-            rzv[u] = 0.0; asv[u] = 0.0; qnv[u] = 0.0;
-            if (d < D && !a.last_step) {
-                const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
-                if (a.renoise_mode == 1) {
-                    if (renoise_px) rzv[u] = static_cast<const double *>(a.renoise)[e];
-                } else if (a.renoise_mode == 2) {
-                    asv[u] = a.asd_is_f64 ? static_cast<const double *>(a.asd)[e]
-                                          : static_cast<double>(static_cast<const float *>(a.asd)[e]);
-                    qnv[u] = a.q_noise_is_f64 ? static_cast<const double *>(a.q_noise)[e]
-                                              : static_cast<double>(static_cast<const float *>(a.q_noise)[e]);
+            for (int u = 0; u < UN; ++u) {
+                rzv[u] = 0.0; asv[u] = 0.0; qnv[u] = 0.0;
+                if (i0 + u < nsteps) {
+                    const int64_t o = (i0 + u) * es;
+                    if (MODE == 1) {
+                        if (renoise_px) rzv[u] = rzp[o];
+                    } else {
+                        asv[u] = a.asd_is_f64 ? static_cast<const double *>(a.asd)[e0 + o]
+                                              : static_cast<double>(static_cast<const float *>(a.asd)[e0 + o]);
+                        qnv[u] = a.q_noise_is_f64 ? static_cast<const double *>(a.q_noise)[e0 + o]
+                                                  : static_cast<double>(static_cast<const float *>(a.q_noise)[e0 + o]);
+                    }
                 }
             }
         }
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-            const int d = d0 + u * kDdimDg;
-            if (d >= D) break;
-            const int64_t e = (static_cast<int64_t>(b) * D + d) * hw + pix;
+            if (i0 + u >= nsteps) break;
+            const int64_t o = (i0 + u) * es;
+            const int d = dg + (i0 + u) * kDdimDg;
             const float x0 = x0_from_tap(tap, d, D, s32);
-            a.x0_out[e] = x0;
+            x0p[o] = x0;
             // a8: pred_noise from the time-embedded, clamped, renormalised state (fp64)
             const XT n = filter_n<XT>(xv[u], shv[u], sX);
-            const double eps = div_by_const(a.sqrt_recip * static_cast<double>(n) - static_cast<double>(x0), a.sqrt_recipm1, inv_recipm1);
-            if (a.eps_out) a.eps_out[e] = eps;
-            if (a.last_step) {
-                static_cast<float *>(a.x_next)[e] = x0;  // img = x_start (fp32)
+            const double eps = div_by_const(sqrt_recip * static_cast<double>(n) - static_cast<double>(x0), sqrt_recipm1, inv_recipm1);
+            if (epsp) epsp[o] = eps;
+            if (LAST) {
+                static_cast<float *>(a.x_next)[e0 + o] = x0;  // img = x_start (fp32)
                 continue;
             }
             // a12: img = x0 * sqrt(alpha_next) + c * eps + sigma * noise
             const float t1 = __fmul_rn(x0, san32);
-            const double t2 = a.c * eps;
+            const double t2 = cc * eps;
             double t3;
             if constexpr (sizeof(XT) == 4)
                 t3 = static_cast<double>(__fmul_rn(sig32, static_cast<float>(snv[u])));
             else
-                t3 = a.sigma * static_cast<double>(snv[u]);
+                t3 = sigma * static_cast<double>(snv[u]);
             double img = (static_cast<double>(t1) + t2) + t3;
-            if (a.renoise_mode == 1) {
+            if (MODE == 1) {
                 if (renoise_px) img = rzv[u];
-            } else if (a.renoise_mode == 2) {
-                const double rn = a.sqrt_ac * asv[u] + a.sqrt_1m_ac * qnv[u];   // q_sample(asd, t)
-                if (a.asd_out) a.asd_out[e] = rn;
+            } else if (MODE == 2) {
+                const double rn = sqrt_ac * asv[u] + sqrt_1m_ac * qnv[u];   // q_sample(asd, t)
+                if (asdo) asdo[o] = rn;
                 if (renoise_px) img = rn;
             }
-            static_cast<double *>(a.x_next)[e] = img;
+            static_cast<double *>(a.x_next)[e0 + o] = img;
             // the next step's filter factor from the fp64 state just produced (acv_ddim.py:256-258 of the next iteration)
-            if (a.n_next_out) a.n_next_out[e] = static_cast<float>(filter_n<double>(img, shn[u], a.scale));
+            if (nnp) nnp[o] = static_cast<float>(filter_n<double>(img, shn[u], sD));
         }
     }
 }
@@ -288,18 +303,26 @@ extern "C" int dv_ddim_step(const dv_ddim_step_args *args, void *stream) {
     }
     if (a.xt_is_f64 != 0 && a.xt_is_f64 != 1) return DV_ERR_BAD_DTYPE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // block shape: measured best of {32x8, 64x4, 128x2, 256x1} (scripts/bench_ddim.py)
+    // block shape: 128x2 measured best of {32x8, 64x4, 128x2, 256x1} (scripts/bench_ddim.py); 32x8 kept as a switch
     const int shape = tune_variant("DV_DDIM_SHAPE", 2);
-#define DV_DDIM(PX, DG)                                                                                              \
+#define DV_DDIM3(PX, DG, MODE, LAST)                                                                                   \
     {                                                                                                                \
         dim3 grid(static_cast<unsigned>((a.h * a.w + PX - 1) / PX), static_cast<unsigned>(a.B));                     \
         dim3 block(PX, DG);                                                                                          \
         if (a.xt_is_f64)                                                                                             \
-            ddim_step_kernel<double, PX, DG><<<grid, block, 0, st>>>(a);                                             \
+            ddim_step_kernel<double, PX, DG, MODE, LAST><<<grid, block, 0, st>>>(a);                                 \
         else                                                                                                         \
-            ddim_step_kernel<float, PX, DG><<<grid, block, 0, st>>>(a);                                              \
+            ddim_step_kernel<float, PX, DG, MODE, LAST><<<grid, block, 0, st>>>(a);                                  \
     }
-    if (shape == 0) DV_DDIM(32, 8) else if (shape == 1) DV_DDIM(64, 4) else if (shape == 3) DV_DDIM(256, 1) else DV_DDIM(128, 2)
+#define DV_DDIM(PX, DG)                                                                                              \
+    {                                                                                                                \
+        if (a.last_step) DV_DDIM3(PX, DG, 0, true)                                                                   \
+        else if (a.renoise_mode == 1) DV_DDIM3(PX, DG, 1, false)                                                     \
+        else if (a.renoise_mode == 2) DV_DDIM3(PX, DG, 2, false)                                                     \
+        else DV_DDIM3(PX, DG, 0, false)                                                                              \
+    }
+    if (shape == 0) DV_DDIM(32, 8) else DV_DDIM(128, 2)
+#undef DV_DDIM3
 #undef DV_DDIM
     return finish_launch();
 }
