@@ -95,6 +95,9 @@ SIGNATURES = {
     "dv_geo_permute_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_avgpool_w2_f32": (_I, [_P, _P, _I64, _I64, _P]),
     "dv_geo_lookup_f32": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),
+    "dv_geo_pack_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P]),
+    "dv_geo_filter_packed_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I, _P]),
+    "dv_geo_lookup_packed_f32": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),
     "dv_gwc_volume_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_corr_volume_2sided_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_groupwise_correlation_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P]),

@@ -189,6 +189,351 @@ geo_lookup_kernel(const GeoLookupArgs a) {
     }
 }
 
+
+// ---- packed pyramid: hypothesis-major rows ------------------------------------------------------
+// The reference keeps geo as [N, C, D] (geometry_ddim.py:19), so the 2r+2 hypotheses one lookup needs are C
+// separate 40-byte windows 4*D bytes apart: ~2 sectors per channel, half of every sector unused, and a warp of
+// 32 pixels touches 32 different 128-byte lines per load.  The packed layout is [N, D_l, C]: the window of one
+// pixel and level is ONE contiguous run of (2r+2)*C floats, and for C = 8 every hypothesis is exactly one 32-byte
+// sector.  geo_pack_kernel builds every level in one pass over the [B,C,D,h,w] volume (permute + avg-pool fused:
+// the volume is read once; the reference layout is never materialised).
+__device__ __forceinline__ const float *pick4(const float *const (&arr)[4], int i) {
+    return i == 0 ? arr[0] : i == 1 ? arr[1] : i == 2 ? arr[2] : arr[3];  // no dynamically indexed kernel-parameter copy
+}
+__device__ __forceinline__ float *pick4w(float *const (&arr)[4], int i) {
+    return i == 0 ? arr[0] : i == 1 ? arr[1] : i == 2 ? arr[2] : arr[3];
+}
+struct GeoPackArgs {
+    float *rows[4];  // level l: [N, D >> l, C]
+    int C, D, hw, levels;
+};
+
+constexpr int kPackDch = 16;  // hypotheses per CTA (multiple of 2^(levels-1) for levels <= 4 ... 8 | 16)
+
+__device__ __forceinline__ float pooled_at(const float *__restrict__ tile, int C, int c, int pl, int level, int j) {
+    // tile[(d_local * C + c) * 33 + pl]; level-l value j = avg_pool2d applied l times (pairwise (a + b) / 2, floor)
+    if (level == 0) return tile[(j * C + c) * 33 + pl];
+    const float a = pooled_at(tile, C, c, pl, level - 1, 2 * j), b = pooled_at(tile, C, c, pl, level - 1, 2 * j + 1);
+    return __fadd_rn(a, b) / 2.0f;
+}
+
+// CTA = (32 pixels, kPackDch hypotheses, batch b): a warp reads 32 consecutive pixels of one (c, d) plane (128 bytes),
+// the tile is transposed through shared memory, and every pixel's (d-chunk x C) block leaves as one contiguous run
+// (512 bytes at level 0 for C = 8, 256 at level 1): one warp per pixel, lanes along the run.
+// CT > 0: C == CT at compile time and only full kPackDch chunks take this instantiation (every index split is a shift).
+template <int CT>
+__global__ void __launch_bounds__(256)
+geo_pack_kernel(const float *__restrict__ geo, const GeoPackArgs a) {
+    extern __shared__ float tile[];  // [kPackDch * C][33], slot (d_local * C + c)
+    const int C = CT > 0 ? CT : a.C;
+    const int b = blockIdx.z, d0 = blockIdx.y * kPackDch, p0 = blockIdx.x * 32;
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const int nd = CT > 0 ? kPackDch : min(kPackDch, a.D - d0);
+    const int p = p0 + lane;
+    // 8 independent 128-byte row reads in flight per warp (a single outstanding load per warp caps the kernel at
+    // ~1.3 TB/s by Little's law)
+    const float *gb = geo + (static_cast<int64_t>(b) * C * a.D + d0) * a.hw + p;
+    const int nrows = C * nd;
+    for (int r0 = warp; r0 < nrows; r0 += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = r0 + 8 * u;
+            const int c = r / nd, dd = r % nd;
+            v[u] = (r < nrows && p < a.hw) ? __ldg(gb + (static_cast<int64_t>(c) * a.D + dd) * a.hw) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = r0 + 8 * u;
+            if (r < nrows) tile[((r % nd) * C + r / nd) * 33 + lane] = v[u];
+        }
+    }
+    __syncthreads();
+    const int npx = min(32, a.hw - p0);
+    for (int lvl = 0; lvl < a.levels; ++lvl) {
+        const int Dl = a.D >> lvl;
+        const int j0 = d0 >> lvl;
+        const int nj = min((d0 + kPackDch) >> lvl, Dl) - j0;  // pooled entries whose sources all lie in this chunk
+        if (nj <= 0) break;
+        const int run = nj * C;
+        float *base = pick4w(a.rows, lvl) + ((static_cast<int64_t>(b) * a.hw + p0) * Dl + j0) * C;
+        for (int px = warp; px < npx; px += 8) {
+            float *dst = base + static_cast<int64_t>(px) * Dl * C;
+            if (lvl == 0) {
+                for (int j = lane; j < run; j += 32) dst[j] = tile[j * 33 + px];
+            } else if (lvl == 1) {
+                for (int j = lane; j < run; j += 32) {
+                    const int c = j % C, jj = j / C;
+                    dst[j] = __fadd_rn(tile[((2 * jj) * C + c) * 33 + px], tile[((2 * jj + 1) * C + c) * 33 + px]) / 2.0f;
+                }
+            } else {
+                for (int j = lane; j < run; j += 32) dst[j] = pooled_at(tile, C, j % C, px, lvl, j / C);
+            }
+        }
+    }
+}
+
+// a9 for IGEV (geometry_ddim.py:37-43,56): geo_l * noise_l on the packed pyramid, every level in one launch.
+// out_l[n, j, c] = in_l[n, j, c] * noise_l[n, j], noise_l = the raw [N, D] rows avg-pooled l times.
+struct GeoFilterArgs {
+    const float *in[4];
+    float *out[4];
+    const float *noisy;
+    int C, D, levels;
+    int64_t N;
+};
+__global__ void __launch_bounds__(256)
+geo_filter_packed_kernel(const GeoFilterArgs a) {
+    const int lvl = blockIdx.y;
+    const int Dl = a.D >> lvl;
+    const float *in = pick4(a.in, lvl);
+    float *out = pick4w(a.out, lvl);
+    const int64_t per_row = static_cast<int64_t>(Dl) * a.C;
+    const int64_t total = a.N * per_row;
+    if (a.C % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+        const int c4 = a.C / 4;
+        const int64_t total4 = total / 4;
+        for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < total4;
+             q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+            const int64_t nj = q / c4;  // n * Dl + j
+            const int64_t n = nj / Dl;
+            const int j = static_cast<int>(nj % Dl);
+            const float nz = noise_at(a.noisy + n * a.D, lvl, j);
+            float4 v = __ldg(reinterpret_cast<const float4 *>(in) + q);
+            v.x = __fmul_rn(v.x, nz); v.y = __fmul_rn(v.y, nz); v.z = __fmul_rn(v.z, nz); v.w = __fmul_rn(v.w, nz);
+            reinterpret_cast<float4 *>(out)[q] = v;
+        }
+    } else {
+        for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+             e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+            const int64_t nj = e / a.C;
+            const int64_t n = nj / Dl;
+            const int j = static_cast<int>(nj % Dl);
+            out[e] = __fmul_rn(in[e], noise_at(a.noisy + n * a.D, lvl, j));
+        }
+    }
+}
+
+struct GeoLookupPackedArgs {
+    const float *geo[4];   // level l: [N, D >> l, C]
+    const float *corr[4];  // level l: [N, W2 >> l]
+    const float *noisy, *disp, *coords;
+    float *out;
+    int C, D, hw, W2, levels, radius;
+    int64_t N;
+    float rcpD[4], rcpW[4];  // RN(1 / (D_l - 1)), RN(1 / (W2_l - 1)), computed on the host
+};
+
+// a / b correctly rounded from y = RN(1/b): q = RN(a*y), r = a - q*b (exact, FMA), RN(q + r*y).  Equal to __fdiv_rn for
+// every integer-valued b <= 4096 and every normal a (checked exhaustively over the 2^23 significands per divisor; scaling
+// by powers of two is exact), without the slow-path branches of the IEEE division sequence.
+__device__ __forceinline__ float div_by_rcp(float a, float b, float y) {
+    const float q = __fmul_rn(a, y);
+    const float r = __fmaf_rn(-q, b, a);
+    return __fmaf_rn(r, y, q);
+}
+__device__ __forceinline__ float grid_coord_rcp(float x, float wm1, float rcp) {
+    const float g = __fsub_rn(div_by_rcp(__fmul_rn(2.0f, x), wm1, rcp), 1.0f);
+    return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), wm1);
+}
+
+// Window kernel (compile-time radius R, C == 4*C4): C4 adjacent lanes share a pixel, each owns 4 channels.  All 2R+2
+// hypothesis vectors of the window [i0(tap 0), i0(tap 0) + 2R + 1] are fetched up front with clamped, unconditional
+// loads (every gather of a pixel is in flight at once; one LDG.128 per hypothesis and lane, the C4 lanes of a pixel
+// read one contiguous run) and each tap then blends registers.  No noise operand: the DDIM filter is applied to the
+// packed pyramid once per timestep (geo_filter_packed_kernel) — the 32 GRU iterations of a step share one noise.  A tap whose
+// own floor() disagrees with the window position (possible only through rounding at exact integers) takes a
+// direct-load slow path with the same arithmetic.
+template <int C4, int R, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+geo_lookup_window_kernel(const GeoLookupPackedArgs a) {
+    constexpr int TAPS = 2 * R + 1, K = TAPS + 1, CC = 4 * C4, PIX = 128 / C4;
+    const int lvl = blockIdx.y;
+    const int Dl = a.D >> lvl, Wl = a.W2 >> lvl;
+    const int64_t n0 = blockIdx.x * static_cast<int64_t>(PIX);
+    const bool valid = n0 + threadIdx.x / C4 < a.N;
+    const int64_t n = valid ? n0 + threadIdx.x / C4 : a.N - 1;  // tail lanes shadow the last pixel, they never store
+    const int sub = threadIdx.x % C4;
+    const int64_t b = n / a.hw;
+    const int p = static_cast<int>(n % a.hw);
+    constexpr int chan_per_level = (CC + 1) * TAPS;
+    const float scale = static_cast<float>(1 << lvl);
+    const float dm1 = static_cast<float>(Dl - 1), wm1 = static_cast<float>(Wl - 1);
+    const float rD = lvl == 0 ? a.rcpD[0] : lvl == 1 ? a.rcpD[1] : lvl == 2 ? a.rcpD[2] : a.rcpD[3];
+    const float rW = lvl == 0 ? a.rcpW[0] : lvl == 1 ? a.rcpW[1] : lvl == 2 ? a.rcpW[2] : a.rcpW[3];
+    const float dl = __ldg(a.disp + n) / scale;                    // power of two: exact
+    const float cl = __fsub_rn(__ldg(a.coords + n) / scale, dl);
+    const float4 *grow = reinterpret_cast<const float4 *>(pick4(a.geo, lvl) + n * static_cast<int64_t>(CC) * Dl) + sub;
+    const float *crow = pick4(a.corr, lvl) + n * static_cast<int64_t>(Wl);
+    float *ol = a.out + (b * a.levels + lvl) * static_cast<int64_t>(chan_per_level) * a.hw + p;
+
+    // Tap t samples at grid_coord(dx_t + dl); only the window origin and the corr tap indices are needed before the
+    // loads are issued — the weights are recomputed at blend time (a dozen ALU ops per tap) instead of living in ~50
+    // registers across the memory latency.
+    auto geo_tap = [&](int t, int &i0, float &w0, float &w1) {
+        const float ix = grid_coord_rcp(__fadd_rn(static_cast<float>(t - R), dl), dm1, rD);
+        const float fl = floorf(ix);
+        i0 = static_cast<int>(fl);
+        w0 = __fsub_rn(static_cast<float>(i0 + 1), ix);
+        w1 = __fsub_rn(ix, fl);
+    };
+    auto corr_tap = [&](int t, int &j0, float &w0, float &w1) {
+        const float jx = grid_coord_rcp(__fadd_rn(cl, static_cast<float>(t - R)), wm1, rW);
+        const float fj = floorf(jx);
+        j0 = static_cast<int>(fj);
+        w0 = __fsub_rn(static_cast<float>(j0 + 1), jx);
+        w1 = __fsub_rn(jx, fj);
+    };
+    // window fetch: hypothesis i00 + k, clamped (out-of-range ones are never blended)
+    float4 hyp[K];
+    int i00;
+    {
+        float w0, w1;
+        geo_tap(0, i00, w0, w1);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int i = min(max(i00 + k, 0), Dl - 1);
+        hyp[k] = __ldg(grow + static_cast<int64_t>(i) * C4);
+    }
+    // corr taps owned by this lane: t % C4 == sub
+    float cv0[TAPS], cv1[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+        if (t % C4 == sub) {
+            int j0;
+            float w0, w1;
+            corr_tap(t, j0, w0, w1);
+            cv0[t] = __ldg(crow + min(max(j0, 0), Wl - 1));
+            cv1[t] = __ldg(crow + min(max(j0 + 1, 0), Wl - 1));
+        }
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+        int i0;
+        float gw0, gw1;
+        geo_tap(t, i0, gw0, gw1);
+        const int i1 = i0 + 1;
+        const bool in0 = i0 >= 0 && i0 < Dl, in1 = i1 >= 0 && i1 < Dl;
+        float4 v0 = hyp[t], v1 = hyp[t + 1];
+        if (i0 != i00 + t) {  // rounding at an exact integer moved this tap off the window grid
+            v0 = __ldg(grow + static_cast<int64_t>(min(max(i0, 0), Dl - 1)) * C4);
+            v1 = __ldg(grow + static_cast<int64_t>(min(max(i1, 0), Dl - 1)) * C4);
+        }
+        const float a0[4] = {v0.x, v0.y, v0.z, v0.w}, a1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float acc = in0 ? __fmul_rn(a0[c], gw0) : 0.0f;
+            if (in1) acc = __fadd_rn(acc, __fmul_rn(a1[c], gw1));
+            ol[static_cast<int64_t>((4 * sub + c) * TAPS + t) * a.hw] = acc;
+        }
+        if (t % C4 == sub) {
+            int j0;
+            float cw0, cw1;
+            corr_tap(t, j0, cw0, cw1);
+            const int j1 = j0 + 1;
+            float acc = (j0 >= 0 && j0 < Wl) ? __fmul_rn(cv0[t], cw0) : 0.0f;
+            if (j1 >= 0 && j1 < Wl) acc = __fadd_rn(acc, __fmul_rn(cv1[t], cw1));
+            ol[static_cast<int64_t>(CC * TAPS + t) * a.hw] = acc;
+        }
+    }
+}
+
+// thread = (pixel n, level blockIdx.y).  C4 > 0: C == 4*C4 at compile time (hypothesis vectors in registers, the upper
+// hypothesis of tap t is reused as the lower one of tap t+1 when the indices agree); C4 == 0: any C, scalar loads.
+template <int C4, int R>
+__global__ void __launch_bounds__(128)
+geo_lookup_packed_kernel(const GeoLookupPackedArgs a) {
+    const int64_t n = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (n >= a.N) return;
+    const int lvl = blockIdx.y;
+    const int64_t b = n / a.hw;
+    const int p = static_cast<int>(n % a.hw);
+    // R >= 0: radius known at compile time -> the tap loop is fully unrolled and every gather of a pixel is in flight
+    // at once (the loads depend only on disp/coords); R < 0: run-time radius
+    const int radius = R >= 0 ? R : a.radius;
+    const int taps = 2 * radius + 1;
+    const int chan_per_level = (a.C + 1) * taps;
+    const float scale = static_cast<float>(1 << lvl);
+    const int Dl = a.D >> lvl, Wl = a.W2 >> lvl;
+    const float dl = a.disp[n] / scale;
+    const float cl = __fsub_rn(a.coords[n] / scale, dl);
+    const float *nrow = a.noisy ? a.noisy + n * a.D : nullptr;
+    const float *grow = pick4(a.geo, lvl) + n * static_cast<int64_t>(a.C) * Dl;
+    const float *crow = pick4(a.corr, lvl) + n * static_cast<int64_t>(Wl);
+    float *ol = a.out + (b * a.levels + lvl) * static_cast<int64_t>(chan_per_level) * a.hw + p;
+
+    constexpr int CR = C4 > 0 ? 4 * C4 : 1;
+    float carry[CR];  // hypothesis `carry_i`, already multiplied by its noise
+    int carry_i = INT32_MIN;
+#pragma unroll
+    for (int t = 0; t < taps; ++t) {
+        const float dx = static_cast<float>(t - radius);
+        {
+            const float ix = grid_coord(__fadd_rn(dx, dl), Dl);
+            const float fl = floorf(ix);
+            const int i0 = static_cast<int>(fl), i1 = i0 + 1;
+            const float w0 = __fsub_rn(static_cast<float>(i1), ix), w1 = __fsub_rn(ix, fl);
+            const bool in0 = i0 >= 0 && i0 < Dl, in1 = i1 >= 0 && i1 < Dl;
+            const float n0 = (nrow && in0) ? noise_at(nrow, lvl, i0) : 1.0f;
+            const float n1 = (nrow && in1) ? noise_at(nrow, lvl, i1) : 1.0f;
+            if constexpr (C4 > 0) {
+                float v0[CR], v1[CR];
+                if (in0) {
+                    if (i0 == carry_i) {
+#pragma unroll
+                        for (int c = 0; c < CR; ++c) v0[c] = carry[c];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < C4; ++q) {
+                            const float4 g = __ldg(reinterpret_cast<const float4 *>(grow + static_cast<int64_t>(i0) * CR) + q);
+                            v0[4 * q + 0] = __fmul_rn(g.x, n0); v0[4 * q + 1] = __fmul_rn(g.y, n0);
+                            v0[4 * q + 2] = __fmul_rn(g.z, n0); v0[4 * q + 3] = __fmul_rn(g.w, n0);
+                        }
+                    }
+                }
+                if (in1) {
+#pragma unroll
+                    for (int q = 0; q < C4; ++q) {
+                        const float4 g = __ldg(reinterpret_cast<const float4 *>(grow + static_cast<int64_t>(i1) * CR) + q);
+                        v1[4 * q + 0] = __fmul_rn(g.x, n1); v1[4 * q + 1] = __fmul_rn(g.y, n1);
+                        v1[4 * q + 2] = __fmul_rn(g.z, n1); v1[4 * q + 3] = __fmul_rn(g.w, n1);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CR; ++c) {
+                    float acc = in0 ? __fmul_rn(v0[c], w0) : 0.0f;
+                    if (in1) acc = __fadd_rn(acc, __fmul_rn(v1[c], w1));
+                    ol[static_cast<int64_t>(c * taps + t) * a.hw] = acc;
+                }
+                if (in1) {
+#pragma unroll
+                    for (int c = 0; c < CR; ++c) carry[c] = v1[c];
+                    carry_i = i1;
+                }
+            } else {
+                for (int c = 0; c < a.C; ++c) {
+                    float acc = 0.0f;
+                    if (in0) acc = __fmul_rn(__fmul_rn(grow[static_cast<int64_t>(i0) * a.C + c], n0), w0);
+                    if (in1) acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(grow[static_cast<int64_t>(i1) * a.C + c], n1), w1));
+                    ol[static_cast<int64_t>(c * taps + t) * a.hw] = acc;
+                }
+            }
+        }
+        {
+            const float ix = grid_coord(__fadd_rn(cl, dx), Wl);
+            const float fl = floorf(ix);
+            const int i0 = static_cast<int>(fl), i1 = i0 + 1;
+            const float w0 = __fsub_rn(static_cast<float>(i1), ix), w1 = __fsub_rn(ix, fl);
+            float acc = 0.0f;
+            if (i0 >= 0 && i0 < Wl) acc = __fmul_rn(__ldg(crow + i0), w0);
+            if (i1 >= 0 && i1 < Wl) acc = __fadd_rn(acc, __fmul_rn(__ldg(crow + i1), w1));
+            ol[static_cast<int64_t>(a.C * taps + t) * a.hw] = acc;
+        }
+    }
+}
+
 }  // namespace dv
 
 extern "C" int dv_corr1d_allpairs_f32(const float *fmap1, const float *fmap2, float *out, int64_t B, int64_t C,
@@ -258,5 +603,101 @@ extern "C" int dv_geo_lookup_f32(const float *const *geo_pyr, const float *const
     const int64_t blocks = (a.N + 127) / 128;
     if (blocks > INT32_MAX) return DV_ERR_BAD_SHAPE;
     geo_lookup_kernel<<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return finish_launch();
+}
+
+extern "C" int dv_geo_pack_f32(const float *geo, float *const *rows_pyr, int64_t B, int64_t C, int64_t D, int64_t h,
+                               int64_t w, int num_levels, void *stream) {
+    using namespace dv;
+    if (!geo || !rows_pyr) return DV_ERR_NULL;
+    if (num_levels < 1 || num_levels > 4) return DV_ERR_UNSUPPORTED;
+    if (B <= 0 || C <= 0 || D <= 0 || h <= 0 || w <= 0 || B > 65535 || h * w > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    if ((D >> (num_levels - 1)) < 1) return DV_ERR_BAD_SHAPE;
+    const size_t smem = sizeof(float) * static_cast<size_t>(C) * kPackDch * 33;
+    if (smem > 200 * 1024 || (D + kPackDch - 1) / kPackDch > 65535) return DV_ERR_UNSUPPORTED;
+    GeoPackArgs a;
+    for (int i = 0; i < 4; ++i) {
+        a.rows[i] = i < num_levels ? rows_pyr[i] : nullptr;
+        if (i < num_levels && !a.rows[i]) return DV_ERR_NULL;
+    }
+    a.C = static_cast<int>(C); a.D = static_cast<int>(D); a.hw = static_cast<int>(h * w); a.levels = num_levels;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(geo_pack_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return DV_ERR_LAUNCH;
+    dim3 grid(static_cast<unsigned>((a.hw + 31) / 32), static_cast<unsigned>((D + kPackDch - 1) / kPackDch),
+              static_cast<unsigned>(B));
+    if (C == 8 && D % kPackDch == 0) {
+        geo_pack_kernel<8><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(geo, a);
+        return finish_launch();
+    }
+    geo_pack_kernel<0><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(geo, a);
+    return finish_launch();
+}
+
+extern "C" int dv_geo_lookup_packed_f32(const float *const *geo_pyr, const float *const *corr_pyr, const float *noisy,
+                                        const float *disp, const float *coords, float *out, int64_t B, int64_t C,
+                                        int64_t D, int64_t h, int64_t w, int64_t W2, int num_levels, int radius,
+                                        void *stream) {
+    using namespace dv;
+    if (!geo_pyr || !corr_pyr || !disp || !coords || !out) return DV_ERR_NULL;
+    if (num_levels < 1 || num_levels > 4 || radius < 0 || radius > 16) return DV_ERR_UNSUPPORTED;
+    if (B <= 0 || C <= 0 || D <= 0 || h <= 0 || w <= 0 || W2 <= 0 || h * w > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    if ((D >> (num_levels - 1)) < 2 || (W2 >> (num_levels - 1)) < 2) return DV_ERR_BAD_SHAPE;
+    GeoLookupPackedArgs a;
+    bool al16 = true;
+    for (int i = 0; i < 4; ++i) {
+        a.geo[i] = i < num_levels ? geo_pyr[i] : nullptr;
+        a.corr[i] = i < num_levels ? corr_pyr[i] : nullptr;
+        if (i < num_levels && (!a.geo[i] || !a.corr[i])) return DV_ERR_NULL;
+        if (i < num_levels) al16 = al16 && aligned16(a.geo[i]);
+    }
+    a.noisy = noisy; a.disp = disp; a.coords = coords; a.out = out;
+    a.C = static_cast<int>(C); a.D = static_cast<int>(D); a.hw = static_cast<int>(h * w); a.W2 = static_cast<int>(W2);
+    a.levels = num_levels; a.radius = radius; a.N = B * h * w;
+    const int64_t blocks = (a.N + 127) / 128;
+    if (blocks > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(num_levels));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bool small_divisors = true;
+    for (int i = 0; i < 4; ++i) {
+        const int64_t dm1 = (D >> i) - 1, wm1 = (W2 >> i) - 1;
+        a.rcpD[i] = dm1 > 0 ? 1.0f / static_cast<float>(dm1) : 0.0f;
+        a.rcpW[i] = wm1 > 0 ? 1.0f / static_cast<float>(wm1) : 0.0f;
+        if (i < num_levels && (dm1 > 4096 || wm1 > 4096)) small_divisors = false;  // range div_by_rcp was verified on
+    }
+    if (al16 && C == 8 && radius == 4 && small_divisors && !noisy && tune_variant("DV_GEO_WINDOW", 1)) {  // IGEV
+        const int64_t wblocks = (a.N + 63) / 64;  // 64 pixels x 2 lanes per block
+        if (wblocks > INT32_MAX) return DV_ERR_BAD_SHAPE;
+        const size_t smem = 0;
+        const dim3 wgrid(static_cast<unsigned>(wblocks), static_cast<unsigned>(num_levels));
+        const int minb = tune_variant("DV_GEO_MINB", 6);
+        if (minb == 4) geo_lookup_window_kernel<2, 4, 4><<<wgrid, 128, smem, st>>>(a);
+        else if (minb == 8) geo_lookup_window_kernel<2, 4, 8><<<wgrid, 128, smem, st>>>(a);
+        else geo_lookup_window_kernel<2, 4, 6><<<wgrid, 128, smem, st>>>(a);
+    } else if (al16 && C == 8 && radius == 4) geo_lookup_packed_kernel<2, 4><<<grid, 128, 0, st>>>(a);
+    else if (al16 && C == 8) geo_lookup_packed_kernel<2, -1><<<grid, 128, 0, st>>>(a);
+    else if (al16 && C == 4) geo_lookup_packed_kernel<1, -1><<<grid, 128, 0, st>>>(a);
+    else if (al16 && C == 16) geo_lookup_packed_kernel<4, -1><<<grid, 128, 0, st>>>(a);
+    else geo_lookup_packed_kernel<0, -1><<<grid, 128, 0, st>>>(a);
+    return finish_launch();
+}
+
+extern "C" int dv_geo_filter_packed_f32(const float *const *rows_in, const float *noisy, float *const *rows_out, int64_t N,
+                                        int64_t C, int64_t D, int num_levels, void *stream) {
+    using namespace dv;
+    if (!rows_in || !rows_out || !noisy) return DV_ERR_NULL;
+    if (num_levels < 1 || num_levels > 4) return DV_ERR_UNSUPPORTED;
+    if (N <= 0 || C <= 0 || D <= 0 || C > INT32_MAX || D > INT32_MAX || (D >> (num_levels - 1)) < 1) return DV_ERR_BAD_SHAPE;
+    GeoFilterArgs a;
+    for (int i = 0; i < 4; ++i) {
+        a.in[i] = i < num_levels ? rows_in[i] : nullptr;
+        a.out[i] = i < num_levels ? rows_out[i] : nullptr;
+        if (i < num_levels && (!a.in[i] || !a.out[i])) return DV_ERR_NULL;
+    }
+    a.noisy = noisy; a.C = static_cast<int>(C); a.D = static_cast<int>(D); a.levels = num_levels; a.N = N;
+    const int64_t work = (N * D * C + 3) / 4;
+    const int64_t blocks = (work + 255) / 256;
+    const unsigned gx = static_cast<unsigned>(blocks < static_cast<int64_t>(kNumSMs) * 16 ? blocks : static_cast<int64_t>(kNumSMs) * 16);
+    geo_filter_packed_kernel<<<dim3(gx, static_cast<unsigned>(num_levels)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return finish_launch();
 }

@@ -146,6 +146,117 @@ gwc_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, 
     }
 }
 
+// Wide groups (channels per group a multiple of 8, > 8): the same span / sliding-window scheme, but the K dimension
+// is streamed through shared memory in chunks of KC channels while the DC x 4 accumulator tile stays in registers, so the
+// staging buffer is 17 KB per stage whatever cpg is (the one-shot kernel above needs cpg x 2.2 KB: 140 KB at cpg = 32,
+// one 128-thread CTA per SM).  Used by PCWNet's refinement correlation (C = 32, G = 1, KITTI12/models/pwcnet_ddim.py:494).
+// Every thread owns ONE disparity chunk (NCH = number of chunks), pipeline stage = (span, k-chunk).
+template <int KC, int DC, int SQ, int NCH, int MINB>
+__global__ void __launch_bounds__(SQ * NCH, MINB)
+gwc_volume_kchunk_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out,
+                         int C, int HW, int W, int D, int G, int cpg, int Dpad, int Dtot, int dofs, int tiles_per_cta) {
+    constexpr int SPAN = SQ * 4;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int rpitch = SPAN + Dpad;
+    const int stage_floats = KC * SPAN + KC * rpitch;
+    const int b = blockIdx.z, g = blockIdx.y;
+    const int nspans = (HW + SPAN - 1) / SPAN;
+    const int t0 = blockIdx.x * tiles_per_cta;
+    const int nt = min(tiles_per_cta, nspans - t0);
+    const int nkc = cpg / KC;
+    const int nstages = nt * nkc;
+    const int64_t plane0 = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * cpg) * HW;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int st) {  // warp 0 only
+        float *sL = smem + (st & 1) * stage_floats;
+        float *sR = sL + KC * SPAN;
+        const int p0 = (t0 + st / nkc) * SPAN;
+        const int k0 = (st % nkc) * KC;
+        const int len = min(SPAN, HW - p0);
+        const int64_t roff0 = plane0 + static_cast<int64_t>(k0) * HW + p0 - Dpad;
+        const int skip0 = roff0 < 0 ? static_cast<int>(-roff0) : 0;  // only the very first plane of the tensor
+        if (threadIdx.x == 0)
+            mbar_expect_tx(&bar[st & 1], static_cast<uint32_t>(KC) * (2u * len + Dpad) * 4u - 4u * skip0);
+        __syncwarp();
+        for (int k = threadIdx.x; k < KC; k += 32) {
+            bulk_g2s(sL + k * SPAN, ref + plane0 + static_cast<int64_t>(k0 + k) * HW + p0, 4u * len, &bar[st & 1]);
+            const int skip = k == 0 ? skip0 : 0;
+            bulk_g2s(sR + k * rpitch + skip, tgt + roff0 + static_cast<int64_t>(k) * HW + skip, 4u * (len + Dpad - skip),
+                     &bar[st & 1]);
+        }
+    };
+    if (threadIdx.x < 32) issue(0);
+
+    const int q = threadIdx.x % SQ;
+    const int d0 = (threadIdx.x / SQ) * DC;
+    const float inv = 1.0f / static_cast<float>(cpg);
+    float acc[DC][4];
+    for (int st = 0; st < nstages; ++st) {
+        if (threadIdx.x < 32 && st + 1 < nstages) issue(st + 1);
+        mbar_wait(&bar[st & 1], (st >> 1) & 1);
+        const int kc = st % nkc;
+        const float *sL = smem + (st & 1) * stage_floats;
+        const float *sR = sL + KC * SPAN;
+        const int p = (t0 + st / nkc) * SPAN + 4 * q;
+        if (p < HW && d0 < D) {
+            if (kc == 0) {
+#pragma unroll
+                for (int j = 0; j < DC; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
+            }
+            const float *lp = sL + 4 * q;
+            const float *rp = sR + Dpad + 4 * q - d0 - DC;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const float4 l4 = *reinterpret_cast<const float4 *>(lp + k * SPAN);
+                const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+                float rw[DC + 4];
+#pragma unroll
+                for (int m = 0; m < DC / 4 + 1; ++m) {
+                    const float4 r4 = *reinterpret_cast<const float4 *>(rp + k * rpitch + 4 * m);
+                    rw[4 * m + 0] = r4.x; rw[4 * m + 1] = r4.y; rw[4 * m + 2] = r4.z; rw[4 * m + 3] = r4.w;
+                }
+#pragma unroll
+                for (int j = 0; j < DC; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(l[i], rw[DC + i - j], acc[j][i]);
+            }
+            if (kc == nkc - 1) {
+                int xs[4];
+                xs[0] = p % W;
+#pragma unroll
+                for (int i = 1; i < 4; ++i) {
+                    xs[i] = xs[i - 1] + 1;
+                    if (xs[i] >= W) xs[i] -= W;
+                }
+                float *op = out + ((static_cast<int64_t>(b) * G + g) * Dtot + dofs + d0) * HW + p;
+#pragma unroll
+                for (int j = 0; j < DC; ++j) {
+                    const int d = d0 + j;
+                    if (d < D) {
+                        float4 v;
+                        v.x = xs[0] >= d ? acc[j][0] * inv : 0.0f;
+                        v.y = xs[1] >= d ? acc[j][1] * inv : 0.0f;
+                        v.z = xs[2] >= d ? acc[j][2] * inv : 0.0f;
+                        v.w = xs[3] >= d ? acc[j][3] * inv : 0.0f;
+                        stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(j) * HW), v);
+                    }
+                }
+            }
+        }
+        if (st + 1 < nstages) __syncthreads();
+    }
+}
+
 // Shape-agnostic kernel for planes with (H*W) % 4 != 0, unaligned pointers or an unusual
 // channels-per-group: one thread per output element, coalesced along x.  <1 % of the bytes
 // of any reference configuration ever take this path.
@@ -204,6 +315,75 @@ __global__ void corr_negative_kernel(const float *__restrict__ ref, const float 
     }
 }
 
+// The same for 16-byte aligned planes with HW % 4 == 0: one 128-bit streaming store per 4 pixels; >95 % of the quads lie
+// entirely in the zero region (x >= k) and are pure stores.
+__global__ void __launch_bounds__(256)
+corr_negative_quad_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out, int C,
+                          int HW, int W, int m, int G, int cpg, int64_t total_quads) {
+    const float inv = 1.0f / static_cast<float>(cpg);
+    const int Dtot = 2 * m + 1;
+    const int HQ = HW / 4;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total_quads;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(idx % HQ) * 4;
+        int64_t t = idx / HQ;
+        const int slot = static_cast<int>(t % m);
+        t /= m;
+        const int g = static_cast<int>(t % G);
+        const int64_t b = t / G;
+        const int k = m - slot;
+        const int x0 = p % W;
+        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (x0 < k || x0 + 3 >= W) {  // the quad touches the first k columns of this row or wraps into the next row
+            const float *l = ref + (b * C + static_cast<int64_t>(g) * cpg) * HW + p;
+            const float *r = tgt + (b * C + static_cast<int64_t>(g) * cpg) * HW + p + max(W - k, 0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int x = x0 + i;
+                if (x >= W) x -= W;
+                if (x < k) {
+                    float acc = 0.0f;
+                    for (int c = 0; c < cpg; ++c)
+                        acc = fmaf(l[static_cast<int64_t>(c) * HW + i], r[static_cast<int64_t>(c) * HW + i], acc);
+                    v[i] = acc * inv;
+                }
+            }
+        }
+        stg_cs(reinterpret_cast<float4 *>(out + ((b * G + g) * Dtot + slot) * HW + p), make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
+template <int KC, int DC, int SQ, int NCH, int MINB>
+static int launch_gwc_kchunk(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int G,
+                             int cpg, int Dtot, int dofs, cudaStream_t st) {
+    constexpr int SPAN = SQ * 4;
+    const int Dpad = ((D + DC - 1) / DC) * DC;
+    const int nspans = (HW + SPAN - 1) / SPAN;
+    int tpc = tune_variant("DV_GWC_TPC", 8);
+    while (tpc > 1 && static_cast<int64_t>((nspans + tpc - 1) / tpc) * G * B < 4LL * kNumSMs * MINB) tpc /= 2;
+    const size_t smem = sizeof(float) * 2 * (static_cast<size_t>(KC) * SPAN + static_cast<size_t>(KC) * (SPAN + Dpad));
+    auto kern = gwc_volume_kchunk_kernel<KC, DC, SQ, NCH, MINB>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return DV_ERR_LAUNCH;
+    dim3 grid((nspans + tpc - 1) / tpc, G, B);
+    kern<<<grid, SQ * NCH, smem, st>>>(ref, tgt, out, C, HW, W, D, G, cpg, Dpad, Dtot, dofs, tpc);
+    return finish_launch();
+}
+
+static int dispatch_gwc_kchunk(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int G,
+                               int cpg, int Dtot, int dofs, cudaStream_t st) {
+    constexpr int KC = 8, DC = 12, SQ = 64;
+    const int nch = (D + DC - 1) / DC;
+    switch (nch) {
+        case 1: return launch_gwc_kchunk<KC, DC, SQ, 1, 8>(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+        case 2: return launch_gwc_kchunk<KC, DC, SQ, 2, 4>(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+        case 3: return launch_gwc_kchunk<KC, DC, SQ, 3, 3>(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+        case 4: return launch_gwc_kchunk<KC, DC, SQ, 4, 2>(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+        default: return DV_ERR_UNSUPPORTED;
+    }
+}
+
 template <int CPG, int DC, int SQ, int NCH, int MINB>
 static int launch_gwc(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int G,
                       int Dtot, int dofs, cudaStream_t st) {
@@ -251,6 +431,9 @@ static int gwc_volume_impl(const float *ref, const float *tgt, float *out, int64
                       W >= 4;
     if (fast) {
         int rc = DV_ERR_UNSUPPORTED;
+        if (cpg > 8 && cpg % 8 == 0 && D <= 48 && tune_variant("DV_GWC_KCHUNK", 1))
+            rc = dispatch_gwc_kchunk(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+        if (rc != DV_ERR_UNSUPPORTED) return rc;
         switch (cpg) {
             case 4: rc = dispatch_gwc<4>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
             case 8: rc = dispatch_gwc<8>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
@@ -295,6 +478,15 @@ extern "C" int dv_corr_volume_2sided_f32(const float *ref, const float *tgt, flo
     if (rc != DV_OK || maxdisp == 0) return rc;
     const int64_t HW = H * W;
     const int64_t total = B * G * maxdisp * HW;
+    if (HW % 4 == 0 && aligned16(out)) {
+        const int64_t quads = total / 4;
+        const int64_t qblocks = (quads + 255) / 256;
+        const int qgrid = static_cast<int>(qblocks < static_cast<int64_t>(kNumSMs) * 16 ? qblocks : static_cast<int64_t>(kNumSMs) * 16);
+        corr_negative_quad_kernel<<<qgrid, 256, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(HW),
+                                                         static_cast<int>(W), static_cast<int>(maxdisp), static_cast<int>(G),
+                                                         static_cast<int>(C / G), quads);
+        return finish_launch();
+    }
     const int64_t blocks = (total + 255) / 256;
     const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
     corr_negative_kernel<<<grid, 256, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(HW),

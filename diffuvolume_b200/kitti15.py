@@ -29,31 +29,51 @@ class Combined_Geo_Encoding_Volume:
     def __init__(self, init_fmap1, init_fmap2, geo_volume, num_levels=2, radius=4):
         self.num_levels = num_levels
         self.radius = radius
-        self.geo_volume_pyramid = []
         self.init_corr_pyramid = []
         init_corr = Combined_Geo_Encoding_Volume.corr(init_fmap1, init_fmap2)
         b, h, w, _, w2 = init_corr.shape
         b, c, d, h, w = geo_volume.shape
         self.channel = c
-        geo = ops.geo_permute(geo_volume.float())                 # [b*h*w, c, 1, d]
+        self._geo_volume = geo_volume.float()
+        self._geo_reference_layout = None
+        self._geo_filtered, self._noise_ref, self._noise_version = None, None, -1
+        # hypothesis-major pyramid [b*h*w, d >> l, c], all levels in one pass (permute + avg-pool chain fused)
+        self._geo_packed = ops.geo_pack(self._geo_volume, num_levels)
         init_corr = init_corr.reshape(b * h * w, 1, 1, w2)
-        self.geo_volume_pyramid.append(geo)
         self.init_corr_pyramid.append(init_corr)
-        for _ in range(self.num_levels - 1):
-            geo = ops.avgpool_w2(geo)
-            self.geo_volume_pyramid.append(geo)
         for _ in range(self.num_levels - 1):
             init_corr = ops.avgpool_w2(init_corr)
             self.init_corr_pyramid.append(init_corr)
 
+    @property
+    def geo_volume_pyramid(self):
+        """The reference's attribute (geometry_ddim.py:18-26): [b*h*w, c, 1, d >> l] per level.  The lookup does not
+        use this layout; it is materialised on first access only."""
+        if self._geo_reference_layout is None:
+            geo = ops.geo_permute(self._geo_volume)
+            pyr = [geo]
+            for _ in range(self.num_levels - 1):
+                geo = ops.avgpool_w2(geo)
+                pyr.append(geo)
+            self._geo_reference_layout = pyr
+        return self._geo_reference_layout
+
+    def _filtered_pyramid(self, noisy):
+        """geo_l * noise_l (geometry_ddim.py:37-43,56).  The reference redoes this full-volume product inside every
+        call; the 32 GRU iterations of a DDIM step pass the SAME tensor (igev_stereo_ddim.py:226-240), so the product is
+        cached per (tensor object, version counter).  The cache holds a reference to `noisy`, so its storage cannot be
+        recycled for different data while the entry is live; an in-place update bumps `_version` and invalidates it."""
+        hit = self._noise_ref is noisy and self._noise_version == noisy._version
+        if not hit:
+            # the reference reshapes the [B,D,h,w] buffer to [b*h*w, 1, 1, D] WITHOUT a permute (geometry_ddim.py:37);
+            # the kernel reads the same raw layout
+            self._geo_filtered = ops.geo_filter_packed(self._geo_packed, noisy.float().contiguous(), out=self._geo_filtered)
+            self._noise_ref, self._noise_version = noisy, noisy._version
+        return self._geo_filtered
+
     def __call__(self, disp, coords, noisy=None):
-        b, _, h, w = disp.shape
-        if noisy is not None:
-            # the reference reshapes the [B,D,h,w] buffer to [b*h*w, 1, 1, D] WITHOUT a permute
-            # (geometry_ddim.py:37); the kernel reads the same raw layout
-            noisy = noisy.float().contiguous()
-        return ops.geo_lookup(self.geo_volume_pyramid, self.init_corr_pyramid, disp.float(), coords.float(), noisy,
-                              self.radius)
+        pyr = self._geo_packed if noisy is None else self._filtered_pyramid(noisy)
+        return ops.geo_lookup_packed(pyr, self.init_corr_pyramid, disp.float(), coords.float(), None, self.radius)
 
     @staticmethod
     def corr(fmap1, fmap2):

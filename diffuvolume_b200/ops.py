@@ -688,3 +688,59 @@ def geo_lookup(geo_pyr: Sequence[torch.Tensor], corr_pyr: Sequence[torch.Tensor]
         check(_lib.lib().dv_geo_lookup_f32(gp, cp, _ptr(noisy), _ptr(disp), _ptr(coords), _ptr(out), b, Cc, D, h, w,
                                            W2, levels, radius, _stream(out)), "dv_geo_lookup_f32")
     return out
+
+
+def geo_pack(geo: torch.Tensor, num_levels: int = 2):
+    """a14 — geo [B,C,D,h,w] -> hypothesis-major pyramid [[B*h*w, D>>l, C] for l < num_levels]: the reference's
+    permute(0,3,4,1,2) (geometry_ddim.py:19) and its avg_pool2d chain (:24-26) in one pass over the volume."""
+    B, Cc, D, h, w = geo.shape
+    _need_cuda(geo)
+    geo = _f32c(geo, "geo_volume")
+    rows = [torch.empty((B * h * w, D >> l, Cc), dtype=torch.float32, device=geo.device) for l in range(num_levels)]
+    rp = (C.c_void_p * num_levels)(*[r.data_ptr() for r in rows])
+    with torch.cuda.device(geo.device):
+        check(_lib.lib().dv_geo_pack_f32(_ptr(geo), rp, B, Cc, D, h, w, num_levels, _stream(geo)), "dv_geo_pack_f32")
+    return rows
+
+
+def geo_lookup_packed(geo_pyr: Sequence[torch.Tensor], corr_pyr: Sequence[torch.Tensor], disp: torch.Tensor,
+                      coords: torch.Tensor, noisy: Optional[torch.Tensor], radius: int) -> torch.Tensor:
+    """a15 on the packed pyramid of `geo_pack` (geo_pyr[l] is [N, D>>l, C]); same result as `geo_lookup`."""
+    b, _, h, w = disp.shape
+    _need_cuda(disp, coords, noisy, *geo_pyr, *corr_pyr)
+    levels = len(geo_pyr)
+    D, Cc = geo_pyr[0].shape[1], geo_pyr[0].shape[2]
+    W2 = corr_pyr[0].shape[-1]
+    disp, coords = _f32c(disp, "disp"), _f32c(coords, "coords")
+    assert coords.numel() == b * h * w
+    if noisy is not None:
+        noisy = _f32c(noisy, "noisy")
+        assert noisy.numel() == b * h * w * D
+    geo_pyr = [_f32c(g, "geo_pyramid") for g in geo_pyr]
+    corr_pyr = [_f32c(c_, "corr_pyramid") for c_ in corr_pyr]
+    out = torch.empty((b, levels * (Cc + 1) * (2 * radius + 1), h, w), dtype=torch.float32, device=disp.device)
+    gp = (C.c_void_p * levels)(*[g.data_ptr() for g in geo_pyr])
+    cp = (C.c_void_p * levels)(*[c_.data_ptr() for c_ in corr_pyr])
+    with torch.cuda.device(disp.device):
+        check(_lib.lib().dv_geo_lookup_packed_f32(gp, cp, _ptr(noisy), _ptr(disp), _ptr(coords), _ptr(out), b, Cc, D, h,
+                                                  w, W2, levels, radius, _stream(out)), "dv_geo_lookup_packed_f32")
+    return out
+
+
+def geo_filter_packed(geo_pyr: Sequence[torch.Tensor], noisy: torch.Tensor, out: Optional[Sequence[torch.Tensor]] = None):
+    """a9 (IGEV) — geo_l * noise_l on the packed pyramid (geometry_ddim.py:37-43,56), every level in one launch.
+    `noisy` is the caller's [B,D,h,w] tensor read as raw [N, D] rows (the reference's reshape without a permute)."""
+    levels = len(geo_pyr)
+    N, D, Cc = geo_pyr[0].shape
+    _need_cuda(noisy, *geo_pyr)
+    noisy = _f32c(noisy, "noisy")
+    assert noisy.numel() == N * D
+    geo_pyr = [_f32c(g, "geo_pyramid") for g in geo_pyr]
+    if out is None:
+        out = [torch.empty_like(g) for g in geo_pyr]
+    ip = (C.c_void_p * levels)(*[g.data_ptr() for g in geo_pyr])
+    op = (C.c_void_p * levels)(*[g.data_ptr() for g in out])
+    with torch.cuda.device(noisy.device):
+        check(_lib.lib().dv_geo_filter_packed_f32(ip, _ptr(noisy), op, N, Cc, D, levels, _stream(noisy)),
+              "dv_geo_filter_packed_f32")
+    return list(out)

@@ -259,6 +259,27 @@ int dv_geo_lookup_f32(const float *const *geo_pyr, const float *const *corr_pyr,
                       int64_t B, int64_t C, int64_t D, int64_t h, int64_t w, int64_t W2,
                       int num_levels, int radius, void *stream);
 
+/* ---- a14 + a15, packed pyramid (same reference lines as above).
+ * The reference keeps geo as [N, C, D_l] rows (geometry_ddim.py:19); a lookup then touches C separate 40-byte windows
+ * per pixel and level.  dv_geo_pack_f32 builds a hypothesis-major pyramid rows_pyr[l] = [N, D >> l, C] for every level
+ * l < num_levels in ONE pass over geo [B,C,D,h,w] (permute(0,3,4,1,2) and the avg_pool2d([1,2]) chain fused, same
+ * pairwise (a+b)/2 rounding), so the (2r+2)*C floats one lookup needs are one contiguous run.
+ * dv_geo_lookup_packed_f32 is dv_geo_lookup_f32 on that layout: identical arithmetic, identical output.             */
+int dv_geo_pack_f32(const float *geo, float *const *rows_pyr, int64_t B, int64_t C, int64_t D,
+                    int64_t h, int64_t w, int num_levels, void *stream);
+int dv_geo_lookup_packed_f32(const float *const *geo_pyr, const float *const *corr_pyr,
+                             const float *noisy, const float *disp, const float *coords, float *out,
+                             int64_t B, int64_t C, int64_t D, int64_t h, int64_t w, int64_t W2,
+                             int num_levels, int radius, void *stream);
+
+/* ---- a9 for IGEV: the DDIM filter on the packed pyramid (KITTI15/core/geometry_ddim.py:37-43,56).
+ * rows_out[l][n, j, c] = rows_in[l][n, j, c] * noise_l[n, j]; noise_l = `noisy` (raw [N, D] rows, as in
+ * dv_geo_lookup_f32) avg-pooled l times.  The reference redoes this product inside every lookup (64 per pair); the 32
+ * GRU iterations of one DDIM step share one noise tensor (igev_stereo_ddim.py:226-240), so the product is taken once per
+ * step and the lookups then run on rows_out with noisy = NULL — bit-identical (same single fp32 product per element). */
+int dv_geo_filter_packed_f32(const float *const *rows_in, const float *noisy, float *const *rows_out,
+                             int64_t N, int64_t C, int64_t D, int num_levels, void *stream);
+
 /* ---- f1: backward passes of the volume ops — the reference's training scripts differentiate through them
  *          (SceneFlow/main.py:154 -> models/acv_ddim.py:424-482; KITTI12/main.py; KITTI15/train_stereo.py).
  * Gradients of the functions above with respect to their feature inputs; grad_out has the forward output's shape.

@@ -189,6 +189,18 @@ def main():
         smooth = (torch.linspace(2, 40, w, device=dev).view(1, 1, 1, w).expand(B, 1, h, w)).contiguous()
         R.time("a15 geo_lookup (+noise, smooth disp)", f"igev B={B}", lambda: ops.geo_lookup(gp, cp, smooth, coords, noisy, 4),
                lookup_bytes + B * hw * 30 * F4)
+        R.time("a14 geo_pack (permute+pool fused, 2 levels)", f"igev B={B} [B,8,48,96,312]", lambda: ops.geo_pack(geo, 2),
+               int(2.5 * B * Cg * D * hw * F4))
+        pk = ops.geo_pack(geo, 2)
+        R.time("a15 geo_lookup_packed (+noise)", f"igev B={B} r=4 L=2 -> [B,162,96,312]",
+               lambda: ops.geo_lookup_packed(pk, cp, disp, coords, noisy, 4), lookup_bytes + B * hw * 30 * F4,
+               note="random disparities: worst-case gather")
+        R.time("a9 geo_filter_packed (once per DDIM step)", f"igev B={B}", lambda: ops.geo_filter_packed(pk, noisy),
+               int(B * hw * (2 * 1.5 * Cg * D + D) * F4))
+        R.time("a15 geo_lookup_packed (origin)", f"igev B={B} r=4 L=2", lambda: ops.geo_lookup_packed(pk, cp, disp, coords, None, 4),
+               lookup_bytes)
+        R.time("a15 geo_lookup_packed (+noise, smooth disp)", f"igev B={B}",
+               lambda: ops.geo_lookup_packed(pk, cp, smooth, coords, noisy, 4), lookup_bytes + B * hw * 30 * F4)
         cost = rn(B, 48, h, w)
         R.time("a6 softmax_regress D=48", f"igev B={B} [B,48,96,312]", lambda: ops.softmax_regress(cost),
                B * 49 * hw * F4)

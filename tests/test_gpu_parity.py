@@ -419,6 +419,74 @@ def test_geo_lookup_igev_shape_vs_oracle(ops):
     assert rel_max_err(host(got), vol(disp, coords, noisy)) < VOL_TOL
 
 
+@pytest.mark.parametrize("shape", [(1, 8, 48, 12, 312), (2, 8, 48, 5, 13), (1, 4, 24, 6, 40), (1, 5, 17, 3, 11), (1, 16, 48, 4, 37)])
+@pytest.mark.parametrize("levels", [1, 2, 3])
+def test_geo_pack_and_packed_lookup_match_reference_layout(ops, shape, levels):
+    """The hypothesis-major pyramid is the reference pyramid transposed (bit-exact), and the packed lookup gives the
+    bit-identical result of the reference-layout lookup and the oracle's, with and without the noise multiply."""
+    B, Cg, D, h, w = shape
+    if (D >> (levels - 1)) < 2:
+        pytest.skip("pyramid too deep for D")
+    W2 = w + 3
+    geo = synth.normal((B, Cg, D, h, w), 201)
+    corr0 = synth.normal((B * h * w, 1, 1, W2), 202)
+    disp = synth.uniform((B, 1, h, w), 203, dtype=np.float32) * np.float32(D + 6) - np.float32(3)
+    coords = np.broadcast_to(np.arange(w, dtype=np.float32).reshape(1, 1, 1, w), (B, 1, h, w)).copy()
+    noisy = synth.uniform((B, D, h, w), 204, dtype=np.float32)
+    if (W2 >> (levels - 1)) < 2:
+        pytest.skip("pyramid too deep for W2")
+    ref_pyr = [ops.geo_permute(cu(geo))]
+    corr_pyr = [cu(corr0)]
+    for _ in range(levels - 1):
+        ref_pyr.append(ops.avgpool_w2(ref_pyr[-1]))
+        corr_pyr.append(ops.avgpool_w2(corr_pyr[-1]))
+    packed = ops.geo_pack(cu(geo), levels)
+    for l in range(levels):
+        assert packed[l].shape == (B * h * w, D >> l, Cg)
+        assert torch.equal(packed[l], ref_pyr[l][:, :, 0, :].transpose(1, 2).contiguous())
+    for nz in (None, cu(noisy)):
+        want = ops.geo_lookup(ref_pyr, corr_pyr, cu(disp), cu(coords), nz, 4)
+        got = ops.geo_lookup_packed(packed, corr_pyr, cu(disp), cu(coords), nz, 4)
+        assert torch.equal(got, want)
+    # the DDIM filter taken once on the packed pyramid, then a noise-free lookup: the same bits
+    filtered = ops.geo_filter_packed(packed, cu(noisy))
+    assert torch.equal(ops.geo_lookup_packed(filtered, corr_pyr, cu(disp), cu(coords), None, 4), want)
+    for r in (1, 3):   # run-time radius path
+        assert torch.equal(ops.geo_lookup_packed(filtered, corr_pyr, cu(disp), cu(coords), None, r),
+                           ops.geo_lookup(ref_pyr, corr_pyr, cu(disp), cu(coords), cu(noisy), r))
+    if levels == 2:
+        vol = O.CombinedGeoEncodingVolume.__new__(O.CombinedGeoEncodingVolume)
+        vol.num_levels, vol.radius = 2, 4
+        vol.geo_volume_pyramid = [host(g) for g in ref_pyr]
+        vol.init_corr_pyramid = [host(c) for c in corr_pyr]
+        assert rel_max_err(host(got), vol(disp, coords, noisy)) < VOL_TOL
+
+
+def test_kitti15_geo_class_matches_oracle(ops):
+    """The drop-in class (packed pyramid inside) against the oracle class, both call conventions; the reference-layout
+    attribute is still available."""
+    from diffuvolume_b200 import kitti15
+    B, Cf, h, w, Cg, D = 1, 32, 6, 44, 8, 48
+    f1, f2 = synth.normal((B, Cf, h, w), 211), synth.normal((B, Cf, h, w), 212)
+    geo = synth.normal((B, Cg, D, h, w), 213)
+    disp = synth.uniform((B, 1, h, w), 214, dtype=np.float32) * np.float32(47)
+    coords = np.broadcast_to(np.arange(w, dtype=np.float32).reshape(1, 1, 1, w), (B, 1, h, w)).copy()
+    noisy = synth.uniform((B, D, h, w), 215, dtype=np.float32)
+    vol = O.CombinedGeoEncodingVolume(f1, f2, geo, 2, 4)
+    fn = kitti15.Combined_Geo_Encoding_Volume(cu(f1), cu(f2), cu(geo), num_levels=2, radius=4)
+    assert rel_max_err(host(fn(cu(disp), cu(coords))), vol(disp, coords)) < VOL_TOL
+    assert rel_max_err(host(fn(cu(disp), cu(coords), cu(noisy))), vol(disp, coords, noisy)) < VOL_TOL
+    # the per-step filter cache: same tensor object -> cached product; in-place update or a new tensor -> recomputed
+    nz = cu(noisy)
+    first = fn(cu(disp), cu(coords), nz)
+    assert torch.equal(fn(cu(disp), cu(coords), nz), first)
+    nz.mul_(0.5)
+    assert rel_max_err(host(fn(cu(disp), cu(coords), nz)), vol(disp, coords, noisy * np.float32(0.5))) < VOL_TOL
+    assert rel_max_err(host(fn(cu(disp), cu(coords), cu(noisy))), vol(disp, coords, noisy)) < VOL_TOL
+    assert [tuple(g.shape) for g in fn.geo_volume_pyramid] == [(B * h * w, Cg, 1, D), (B * h * w, Cg, 1, D // 2)]
+    assert rel_max_err(host(fn.geo_volume_pyramid[1]), vol.geo_volume_pyramid[1].reshape(B * h * w, Cg, 1, D // 2)) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------------
 # loud failure on CPU tensors (no fallback)
 # ------------------------------------------------------------------------------------------------
