@@ -315,42 +315,37 @@ __global__ void corr_negative_kernel(const float *__restrict__ ref, const float 
     }
 }
 
-// The same for 16-byte aligned planes with HW % 4 == 0: one 128-bit streaming store per 4 pixels; >95 % of the quads lie
-// entirely in the zero region (x >= k) and are pure stores.
+// The same for 16-byte aligned planes with HW % 4 == 0, split in two: >98 % of the negative-shift planes is zeros, so
+// (1) a pure 128-bit store stream clears planes [0, m) of every (b, g), then (2) one thread per LIVE element (x < k)
+// computes its dot product — every thread of that launch has work, instead of one slow lane per warp of a store loop.
 __global__ void __launch_bounds__(256)
-corr_negative_quad_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out, int C,
-                          int HW, int W, int m, int G, int cpg, int64_t total_quads) {
-    const float inv = 1.0f / static_cast<float>(cpg);
-    const int Dtot = 2 * m + 1;
-    const int HQ = HW / 4;
-    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total_quads;
-         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int p = static_cast<int>(idx % HQ) * 4;
-        int64_t t = idx / HQ;
-        const int slot = static_cast<int>(t % m);
-        t /= m;
-        const int g = static_cast<int>(t % G);
-        const int64_t b = t / G;
-        const int k = m - slot;
-        const int x0 = p % W;
-        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (x0 < k || x0 + 3 >= W) {  // the quad touches the first k columns of this row or wraps into the next row
-            const float *l = ref + (b * C + static_cast<int64_t>(g) * cpg) * HW + p;
-            const float *r = tgt + (b * C + static_cast<int64_t>(g) * cpg) * HW + p + max(W - k, 0);
+zero_planes_kernel(float *__restrict__ out, int64_t plane_stride, int64_t quads_per_bg) {
+    float *o = out + static_cast<int64_t>(blockIdx.y) * plane_stride;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int x = x0 + i;
-                if (x >= W) x -= W;
-                if (x < k) {
-                    float acc = 0.0f;
-                    for (int c = 0; c < cpg; ++c)
-                        acc = fmaf(l[static_cast<int64_t>(c) * HW + i], r[static_cast<int64_t>(c) * HW + i], acc);
-                    v[i] = acc * inv;
-                }
-            }
-        }
-        stg_cs(reinterpret_cast<float4 *>(out + ((b * G + g) * Dtot + slot) * HW + p), make_float4(v[0], v[1], v[2], v[3]));
+    for (int u = 0; u < 4; ++u) {
+        const int64_t qd = static_cast<int64_t>(blockIdx.x) * 1024 + u * 256 + threadIdx.x;
+        if (qd < quads_per_bg) stg_cs(reinterpret_cast<float4 *>(o) + qd, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     }
+}
+__global__ void __launch_bounds__(128)
+corr_negative_live_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out, int C,
+                          int H, int W, int m, int G, int cpg) {
+    // grid: x = row chunks, y = slot, z = b*G + g; thread = (row, column x < min(k, W))
+    const int slot = blockIdx.y, k = m - slot;
+    const int kw = min(k, W);
+    const int rows_per_cta = max(128 / kw, 1);
+    const int y = blockIdx.x * rows_per_cta + threadIdx.x / kw;
+    const int x = threadIdx.x % kw;
+    if (threadIdx.x >= rows_per_cta * kw || y >= H) return;
+    const int g = blockIdx.z % G, b = blockIdx.z / G;
+    const int64_t HW = static_cast<int64_t>(H) * W;
+    const int64_t p = static_cast<int64_t>(y) * W + x;
+    const float *l = ref + (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * cpg) * HW + p;
+    const float *r = tgt + (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * cpg) * HW + p + max(W - k, 0);
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int c = 0; c < cpg; ++c) acc = fmaf(__ldg(l + c * HW), __ldg(r + c * HW), acc);
+    out[(static_cast<int64_t>(blockIdx.z) * (2 * m + 1) + slot) * HW + p] = acc * (1.0f / static_cast<float>(cpg));
 }
 
 template <int KC, int DC, int SQ, int NCH, int MINB>
@@ -478,14 +473,16 @@ extern "C" int dv_corr_volume_2sided_f32(const float *ref, const float *tgt, flo
     if (rc != DV_OK || maxdisp == 0) return rc;
     const int64_t HW = H * W;
     const int64_t total = B * G * maxdisp * HW;
-    if (HW % 4 == 0 && aligned16(out)) {
-        const int64_t quads = total / 4;
-        const int64_t qblocks = (quads + 255) / 256;
-        const int qgrid = static_cast<int>(qblocks < static_cast<int64_t>(kNumSMs) * 16 ? qblocks : static_cast<int64_t>(kNumSMs) * 16);
-        corr_negative_quad_kernel<<<qgrid, 256, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(HW),
+    if (HW % 4 == 0 && aligned16(out) && maxdisp <= 128 && B * G <= 65535 && HW <= INT32_MAX) {
+        const int64_t quads_per_bg = maxdisp * HW / 4;
+        dim3 zgrid(static_cast<unsigned>((quads_per_bg + 1023) / 1024), static_cast<unsigned>(B * G));
+        zero_planes_kernel<<<zgrid, 256, 0, st>>>(out, (2 * maxdisp + 1) * HW, quads_per_bg);
+        // rows per CTA for the widest slot (k = m) bound the grid; narrower slots use fewer of their CTAs' threads
+        dim3 lgrid(static_cast<unsigned>(H), static_cast<unsigned>(maxdisp), static_cast<unsigned>(B * G));
+        corr_negative_live_kernel<<<lgrid, 128, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(H),
                                                          static_cast<int>(W), static_cast<int>(maxdisp), static_cast<int>(G),
-                                                         static_cast<int>(C / G), quads);
-        return finish_launch();
+                                                         static_cast<int>(C / G));
+        return finish_launch(2);
     }
     const int64_t blocks = (total + 255) / 256;
     const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);

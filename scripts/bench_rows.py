@@ -150,6 +150,8 @@ def main():
         R.time("f3 warp", f"pcw B={Bc} C=32 384x1248", lambda: ops.warp(fr, dsp), Bc * (2 * 32 + 1) * 384 * 1248 * F4)
         R.time("a5 corr_volume_2sided", f"pcw B={Bc} C=32 m=24 384x1248", lambda: ops.corr_volume_2sided(fl, fr, 24, 1),
                Bc * (2 * 32 + 49) * 384 * 1248 * F4, flops=2.0 * Bc * 32 * 49 * 384 * 1248)
+        R.time("a2 gwc_volume C=32 G=1 D=25 (positive half of a5)", f"pcw B={Bc} 384x1248", lambda: ops.gwc_volume(fl, fr, 25, 1),
+               Bc * (2 * 32 + 25) * 384 * 1248 * F4)
         gv = rn(Bc, 1, 49, 384, 1248)
         R.time("f1 corr_volume_2sided_bwd", f"pcw B={Bc}", lambda: ops.gwc_volume_bwd(gv, fl, fr, 1, two_sided_maxdisp=24),
                Bc * (49 + 4 * 32) * 384 * 1248 * F4)
