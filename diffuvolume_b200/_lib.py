@@ -96,6 +96,9 @@ SIGNATURES = {
     "dv_avgpool_w2_f32": (_I, [_P, _P, _I64, _I64, _P]),
     "dv_geo_lookup_f32": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),
     "dv_geo_pack_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P]),
+    "dv_depthwise3x3_chain_f32": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),
+    "dv_context_upsample_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _P]),
+    "dv_context_upsample_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "dv_geo_filter_packed_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I, _P]),
     "dv_geo_lookup_packed_f32": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),
     "dv_gwc_volume_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),

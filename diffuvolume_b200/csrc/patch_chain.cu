@@ -1,0 +1,240 @@
+// patch_chain.cu — ACVNet's "patch" depth-wise (1,3,3) convolutions on the gwc volume.
+//
+// Replaces the module chain of SceneFlow/models/acv_ddim.py:181-188,377-381 (same in acv.py):
+//     g  = patch(gwc)                      nn.Conv3d(40,40,(1,3,3), groups=40, dilation 1, padding (0,1,1), no bias)
+//     l1 = patch_l1(g[:, :8])   dil 1      l2 = patch_l2(g[:, 8:24])   dil 2      l3 = patch_l3(g[:, 24:40])   dil 3
+//     patch_volume = cat(l1, l2, l3)
+// i.e. per (b, c, d) plane two chained 3x3 stencils, each with ZERO PADDING OF ITS OWN INPUT (the intermediate is zero
+// outside the image, it is not the first stencil evaluated out there).  cuDNN runs them as five volume-sized passes
+// (conv, 3 grouped convs on strided slices, cat: ~6 x 249 MB per pair).  Here one kernel per dilation class reads an
+// input tile with a (dil1 + dil2)-pixel halo into shared memory, builds the intermediate tile in shared memory and
+// writes the final channels in place of the cat: the volume is read once and written once.
+//   CTA = (tile of one [H,W] plane, plane (c,d), b); thread = strips of 4 horizontal pixels.
+#include "common.cuh"
+
+namespace dv {
+
+constexpr int kPcTH = 32, kPcTW = 64;  // maximum output tile; the launch balances the actual tile to the plane
+
+__global__ void __launch_bounds__(256)
+depthwise_chain_kernel(const float *__restrict__ in, const float *__restrict__ w1, const float *__restrict__ w2,
+                       float *__restrict__ out, int C, int D, int H, int W, int c0, int nc, int dil1, int dil2, int th,
+                       int tw, int tiles_x) {
+    extern __shared__ float sm[];
+    const int r2 = w2 ? dil2 : 0, halo = dil1 + r2;
+    const int iw = tw + 2 * halo, ih = th + 2 * halo;  // staged input tile
+    const int mw = tw + 2 * r2, mh = th + 2 * r2;      // intermediate tile
+    float *s_in = sm, *s_mid = sm + ih * iw;
+    const int tile = blockIdx.x, ty0 = (tile / tiles_x) * th, tx0 = (tile % tiles_x) * tw;
+    const int cd = blockIdx.y;                         // (c - c0) * D + d
+    const int c = c0 + cd / D, d = cd % D, b = blockIdx.z;
+    const int64_t plane = ((static_cast<int64_t>(b) * C + c) * D + d) * H * W;
+    const float *ip = in + plane;
+    float k1[9], k2[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        k1[i] = __ldg(w1 + c * 9 + i);
+        k2[i] = w2 ? __ldg(w2 + c * 9 + i) : 0.0f;
+    }
+    // stage the input tile (zero outside the image)
+    for (int e = threadIdx.x; e < ih * iw; e += 256) {
+        const int yy = e / iw, xx = e % iw;
+        const int y = ty0 - halo + yy, x = tx0 - halo + xx;
+        s_in[e] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(ip + static_cast<int64_t>(y) * W + x) : 0.0f;
+    }
+    __syncthreads();
+    if (w2) {
+        // first stencil on the (th + 2 dil2) x (tw + 2 dil2) region; zero where the intermediate lies outside the image
+        for (int e = threadIdx.x; e < mh * mw; e += 256) {
+            const int yy = e / mw, xx = e % mw;
+            const int y = ty0 - r2 + yy, x = tx0 - r2 + xx;
+            float acc = 0.0f;
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                const float *sp = s_in + (yy + dil1) * iw + xx + dil1;  // centre in the staged tile
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) acc = fmaf(k1[ky * 3 + kx], sp[(ky - 1) * dil1 * iw + (kx - 1) * dil1], acc);
+            }
+            s_mid[e] = acc;
+        }
+        __syncthreads();
+    }
+    const float *src = w2 ? s_mid : s_in;
+    const int sw = w2 ? mw : iw, dl = w2 ? dil2 : dil1;
+    float kk[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) kk[i] = w2 ? k2[i] : k1[i];
+    float *op = out + plane;
+    const int strips = (tw + 3) / 4;
+    for (int e = threadIdx.x; e < th * strips; e += 256) {
+        const int yy = e / strips, xs = (e % strips) * 4;
+        const int y = ty0 + yy;
+        if (y >= H) continue;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const float *sp = src + (yy + dl) * sw + xs + dl;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const float *row = sp + (ky - 1) * dl * sw;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float wv = kk[ky * 3 + kx];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wv, row[(kx - 1) * dl + i], acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = tx0 + xs + i;
+            if (xs + i < tw && x < W) op[static_cast<int64_t>(y) * W + x] = acc[i];
+        }
+    }
+}
+
+
+// ---- 128-bit path: W % 4 == 0, 16-byte aligned planes, dilations <= 4 ---------------------------------------------------
+// Everything is laid out in quads (4 horizontal pixels): the staged input tile starts 8 columns left of the output tile,
+// the intermediate tile 4 columns left, so the 3 taps x 4 outputs of one row always lie in three aligned float4 of the
+// source tile (columns [m, m+12) around the quad at m+4) whatever the dilation: 9 LDS.128 + 36 FMA per output quad and
+// stencil.  Because W % 4 == 0 a quad is either entirely inside the image or entirely outside (zero padding per quad).
+__device__ __forceinline__ void stencil_quad(const float *__restrict__ row0, int pitch, int dil, const float (&k)[9],
+                                             float (&acc)[4]) {
+    // row0 points at column m of the tap row ky = 0; outputs sit at columns m+4 .. m+7
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const float *r = row0 + ky * dil * pitch;
+        const float4 a = *reinterpret_cast<const float4 *>(r), b = *reinterpret_cast<const float4 *>(r + 4),
+                     c = *reinterpret_cast<const float4 *>(r + 8);
+        const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float wv = k[ky * 3 + kx];
+            // tap column for output i: 4 + i + (kx-1)*dil  (dil <= 4 keeps it inside [0, 12))
+            if (dil == 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wv, v[4 + i + (kx - 1) * 1], acc[i]);
+            } else if (dil == 2) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wv, v[4 + i + (kx - 1) * 2], acc[i]);
+            } else if (dil == 3) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wv, v[4 + i + (kx - 1) * 3], acc[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wv, v[4 + i + (kx - 1) * 4], acc[i]);
+            }
+        }
+    }
+}
+
+template <bool CHAIN>
+__global__ void __launch_bounds__(256)
+depthwise_chain_quad_kernel(const float *__restrict__ in, const float *__restrict__ w1, const float *__restrict__ w2,
+                            float *__restrict__ out, int C, int D, int H, int W, int c0, int dil1, int dil2, int th, int tw,
+                            int tiles_x) {
+    extern __shared__ __align__(16) float sm[];
+    const int r2 = CHAIN ? dil2 : 0;
+    const int ih = th + 2 * (dil1 + r2), ipitch = tw + (CHAIN ? 16 : 8);   // input tile starts (CHAIN ? 8 : 4) columns left
+    const int mh = th + 2 * r2, mpitch = tw + 8;                          // intermediate tile starts 4 columns left
+    float *s_in = sm, *s_mid = sm + ih * ipitch;
+    const int tile = blockIdx.x, ty0 = (tile / tiles_x) * th, tx0 = (tile % tiles_x) * tw;
+    const int cd = blockIdx.y;
+    const int c = c0 + cd / D, d = cd % D, b = blockIdx.z;
+    const int64_t plane = ((static_cast<int64_t>(b) * C + c) * D + d) * H * W;
+    const float *ip = in + plane;
+    float k1[9], k2[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        k1[i] = __ldg(w1 + c * 9 + i);
+        k2[i] = CHAIN ? __ldg(w2 + c * 9 + i) : 0.0f;
+    }
+    {   // stage: quads of the input tile
+        const int qpr = ipitch / 4, xl = tx0 - (CHAIN ? 8 : 4), yt = ty0 - dil1 - r2;
+        for (int e = threadIdx.x; e < ih * qpr; e += 256) {
+            const int yy = e / qpr, qx = e - yy * qpr;
+            const int y = yt + yy, x = xl + 4 * qx;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const float4 *>(ip + static_cast<int64_t>(y) * W + x));
+            *reinterpret_cast<float4 *>(s_in + e * 4) = v;
+        }
+    }
+    __syncthreads();
+    if (CHAIN) {
+        const int qpr = mpitch / 4;
+        for (int e = threadIdx.x; e < mh * qpr; e += 256) {
+            const int yy = e / qpr, qx = e - yy * qpr;
+            const int y = ty0 - r2 + yy, x = tx0 - 4 + 4 * qx;
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            // intermediate quad at mid column 4*qx == input column 4*qx + 4; centre row yy + dil1 of the input tile
+            if (y >= 0 && y < H && x >= 0 && x < W) stencil_quad(s_in + yy * ipitch + 4 * qx, ipitch, dil1, k1, acc);
+            *reinterpret_cast<float4 *>(s_mid + e * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+        __syncthreads();
+    }
+    float *op = out + plane;
+    const int qpr = tw / 4;
+    for (int e = threadIdx.x; e < th * qpr; e += 256) {
+        const int yy = e / qpr, qx = e - yy * qpr;
+        const int y = ty0 + yy, x = tx0 + 4 * qx;
+        if (y >= H || x >= W) continue;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (CHAIN) stencil_quad(s_mid + yy * mpitch + 4 * qx, mpitch, dil2, k2, acc);
+        else stencil_quad(s_in + yy * ipitch + 4 * qx, ipitch, dil1, k1, acc);
+        *reinterpret_cast<float4 *>(op + static_cast<int64_t>(y) * W + x) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
+}  // namespace dv
+
+extern "C" int dv_depthwise3x3_chain_f32(const float *in, const float *w1, const float *w2, float *out, int64_t B, int64_t C,
+                                         int64_t D, int64_t H, int64_t W, int64_t c0, int64_t c1, int dil1, int dil2,
+                                         void *stream) {
+    using namespace dv;
+    if (!in || !w1 || !out) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || c0 < 0 || c1 > C || c0 >= c1) return DV_ERR_BAD_SHAPE;
+    if (dil1 < 1 || dil1 > 8 || (w2 && (dil2 < 1 || dil2 > 8))) return DV_ERR_UNSUPPORTED;
+    if (B > 65535 || (c1 - c0) * D > 65535 || H * W > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    if (in == out) return DV_ERR_UNSUPPORTED;  // tiles read their neighbours' inputs
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (W % 4 == 0 && aligned16(in) && aligned16(out) && dil1 <= 4 && (!w2 || dil2 <= 4) && tune_variant("DV_PATCH_QUAD", 1)) {
+        // tiles: up to 32 rows x 128 columns, balanced to the plane, widths in quads
+        const int tiles_y = static_cast<int>((H + 31) / 32), tiles_x = static_cast<int>((W + 127) / 128);
+        const int th = static_cast<int>((H + tiles_y - 1) / tiles_y);
+        const int tw = static_cast<int>((((W + tiles_x - 1) / tiles_x) + 3) / 4 * 4);
+        const int tiles_x2 = static_cast<int>((W + tw - 1) / tw);
+        const int r2 = w2 ? dil2 : 0;
+        const size_t smem = sizeof(float) * (static_cast<size_t>(th + 2 * (dil1 + r2)) * (tw + (w2 ? 16 : 8)) +
+                                             (w2 ? static_cast<size_t>(th + 2 * r2) * (tw + 8) : 0));
+        dim3 grid(static_cast<unsigned>(tiles_y * tiles_x2), static_cast<unsigned>((c1 - c0) * D), static_cast<unsigned>(B));
+        if (w2) {
+            if (smem > 48 * 1024 && cudaFuncSetAttribute(depthwise_chain_quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         static_cast<int>(smem)) != cudaSuccess)
+                return DV_ERR_LAUNCH;
+            depthwise_chain_quad_kernel<true><<<grid, 256, smem, st>>>(in, w1, w2, out, static_cast<int>(C), static_cast<int>(D),
+                                                                      static_cast<int>(H), static_cast<int>(W), static_cast<int>(c0),
+                                                                      dil1, dil2, th, tw, tiles_x2);
+        } else {
+            if (smem > 48 * 1024 && cudaFuncSetAttribute(depthwise_chain_quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         static_cast<int>(smem)) != cudaSuccess)
+                return DV_ERR_LAUNCH;
+            depthwise_chain_quad_kernel<false><<<grid, 256, smem, st>>>(in, w1, w2, out, static_cast<int>(C), static_cast<int>(D),
+                                                                       static_cast<int>(H), static_cast<int>(W), static_cast<int>(c0),
+                                                                       dil1, dil2, th, tw, tiles_x2);
+        }
+        return finish_launch();
+    }
+    const int tiles_y = static_cast<int>((H + kPcTH - 1) / kPcTH), tiles_x = static_cast<int>((W + kPcTW - 1) / kPcTW);
+    const int th = static_cast<int>((H + tiles_y - 1) / tiles_y), tw = static_cast<int>((((W + tiles_x - 1) / tiles_x) + 3) / 4 * 4);
+    const int r2 = w2 ? dil2 : 0, halo = dil1 + r2;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(th + 2 * halo) * (tw + 2 * halo) +
+                                         (w2 ? static_cast<size_t>(th + 2 * r2) * (tw + 2 * r2) : 0));
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(depthwise_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return DV_ERR_LAUNCH;
+    const int tiles_x2 = static_cast<int>((W + tw - 1) / tw);
+    dim3 grid(static_cast<unsigned>(tiles_y * tiles_x2), static_cast<unsigned>((c1 - c0) * D), static_cast<unsigned>(B));
+    depthwise_chain_kernel<<<grid, 256, smem, st>>>(
+        in, w1, w2, out, static_cast<int>(C), static_cast<int>(D), static_cast<int>(H), static_cast<int>(W),
+        static_cast<int>(c0), static_cast<int>(c1 - c0), dil1, dil2, th, tw, tiles_x2);
+    return finish_launch();
+}

@@ -163,3 +163,25 @@ def build_corrleation_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
 def disparity_regression(x, maxdisp, keepdim=False):
     assert len(x.shape) == 4
     return _DisparityRegression.apply(x, maxdisp, keepdim)
+
+
+class _ContextUpsample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp_low, up_weights):
+        ctx.save_for_backward(disp_low, up_weights)
+        return ops.context_upsample(_as_f32(disp_low), _as_f32(up_weights))
+
+    @staticmethod
+    def backward(ctx, g):
+        disp_low, up_weights = ctx.saved_tensors
+        glow, gw = ops.context_upsample_bwd(g.float().contiguous(), disp_low.float(), up_weights.float(),
+                                            need_low=ctx.needs_input_grad[0], need_weights=ctx.needs_input_grad[1])
+        return (None if glow is None else glow.to(disp_low.dtype), None if gw is None else gw.to(up_weights.dtype))
+
+
+def context_upsample(disp_low, up_weights):
+    """KITTI15/core/submodule.py:241-253 — result is fp32 when either input is (the reference multiplies the fp32
+    unfolded disparity by the weights), else the inputs' common dtype."""
+    out = _ContextUpsample.apply(disp_low, up_weights)
+    rt = torch.result_type(disp_low, up_weights)
+    return out if rt == torch.float32 else out.to(rt)

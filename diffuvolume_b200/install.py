@@ -103,3 +103,48 @@ def uninstall() -> int:
                 pass
         n += 1
     return n
+
+
+# ------------------------------------------------------------------------------------------------
+# ACVNet's patch convolutions
+# ------------------------------------------------------------------------------------------------
+def fuse_acv_patch(model) -> bool:
+    """Fuse `patch` -> `patch_l1/l2/l3` -> `torch.cat` of an ACVNet / ACVNet_DDIM instance
+    (SceneFlow/models/acv_ddim.py:181-188,377-381) into the depth-wise chain kernel WITHOUT touching the model's
+    forward or its state_dict: the four Conv3d modules keep their parameters; `patch.forward` returns the finished
+    patch volume and `patch_l*.forward` pass the slices of that tensor through, so the reference's own
+    `torch.cat((patch_l1, patch_l2, patch_l3), dim=1)` reassembles it.  Only taken when autograd is off (inference);
+    with gradients enabled the original cuDNN convolutions run.  Returns False when `model` has no such modules."""
+    import types
+
+    import torch
+    import torch.nn.functional as F
+
+    from . import ops
+
+    model = getattr(model, "module", model)          # nn.DataParallel
+    names = ("patch", "patch_l1", "patch_l2", "patch_l3")
+    if not all(hasattr(model, n) for n in names):
+        return False
+    patch, l1, l2, l3 = (getattr(model, n) for n in names)
+
+    def conv(self, x):
+        return F.conv3d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+    def patch_forward(self, x):
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad) or not x.is_cuda:
+            return conv(self, x)
+        out = ops.acv_patch_volume(x, self.weight, l1.weight, l2.weight, l3.weight).to(x.dtype)
+        out._dv_fused_patch = True
+        return out
+
+    def slice_forward(self, x):
+        base = x._base if x._base is not None else x
+        if getattr(base, "_dv_fused_patch", False):
+            return x                                  # already patch_l*(patch(gwc)[:, slice])
+        return conv(self, x)
+
+    _bind(patch, "forward", types.MethodType(patch_forward, patch))
+    for m in (l1, l2, l3):
+        _bind(m, "forward", types.MethodType(slice_forward, m))
+    return True

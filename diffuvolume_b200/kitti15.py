@@ -4,6 +4,7 @@ core/geometry_ddim.py and core/utils/utils.py:bilinear_sampler.
     build_gwc_volume / groupwise_correlation   KITTI15/core/submodule.py:151-169
     build_concat_volume                        KITTI15/core/submodule.py:206-217   (variant M)
     disparity_regression                       KITTI15/core/submodule.py:219-223   (keepdim=True)
+    context_upsample                           KITTI15/core/submodule.py:241-253
     Combined_Geo_Encoding_Volume               KITTI15/core/geometry.py:6-68  (`__call__(disp, coords)`)
     Combined_Geo_Encoding_Volume_DDIM          KITTI15/core/geometry_ddim.py:6-80 (`__call__(disp, coords, noisy)`)
 """
@@ -13,7 +14,7 @@ import torch
 
 from . import ops
 from .functional import build_concat_volume_m as build_concat_volume
-from .functional import build_gwc_volume, groupwise_correlation
+from .functional import build_gwc_volume, context_upsample, groupwise_correlation
 
 
 def disparity_regression(x, maxdisp):
@@ -84,5 +85,5 @@ class Combined_Geo_Encoding_Volume:
 
 Combined_Geo_Encoding_Volume_DDIM = Combined_Geo_Encoding_Volume
 
-__all__ = ["build_gwc_volume", "groupwise_correlation", "build_concat_volume", "disparity_regression",
+__all__ = ["build_gwc_volume", "groupwise_correlation", "build_concat_volume", "disparity_regression", "context_upsample",
            "Combined_Geo_Encoding_Volume", "Combined_Geo_Encoding_Volume_DDIM"]

@@ -744,3 +744,77 @@ def geo_filter_packed(geo_pyr: Sequence[torch.Tensor], noisy: torch.Tensor, out:
         check(_lib.lib().dv_geo_filter_packed_f32(ip, _ptr(noisy), op, N, Cc, D, levels, _stream(noisy)),
               "dv_geo_filter_packed_f32")
     return list(out)
+
+
+# --------------------------------------------------------------------------------------------
+# f4: context_upsample (KITTI15/core/submodule.py:241-253)
+# --------------------------------------------------------------------------------------------
+def context_upsample(disp_low: torch.Tensor, up_weights: torch.Tensor) -> torch.Tensor:
+    """disp_low [B,1,h,w], up_weights [B,9,4h,4w] -> [B,4h,4w]."""
+    b, c, h, w = disp_low.shape
+    _need_cuda(disp_low, up_weights)
+    if c != 1 or tuple(up_weights.shape) != (b, 9, 4 * h, 4 * w):
+        raise RuntimeError(f"context_upsample: disp_low {tuple(disp_low.shape)} / up_weights {tuple(up_weights.shape)}, "
+                           f"expected [B,1,h,w] / [B,9,4h,4w]")
+    disp_low, up_weights = _f32c(disp_low, "disp_low"), _f32c(up_weights, "up_weights")
+    out = torch.empty((b, 4 * h, 4 * w), dtype=torch.float32, device=disp_low.device)
+    if out.numel():
+        with torch.cuda.device(out.device):
+            check(_lib.lib().dv_context_upsample_f32(_ptr(disp_low), _ptr(up_weights), _ptr(out), b, h, w, _stream(out)),
+                  "dv_context_upsample_f32")
+    return out
+
+
+def context_upsample_bwd(grad_out: torch.Tensor, disp_low: torch.Tensor, up_weights: torch.Tensor, *,
+                         need_low: bool = True, need_weights: bool = True):
+    b, _, h, w = disp_low.shape
+    _need_cuda(grad_out, disp_low, up_weights)
+    grad_out, disp_low, up_weights = _f32c(grad_out, "grad_out"), _f32c(disp_low, "disp_low"), _f32c(up_weights, "up_weights")
+    glow = torch.empty_like(disp_low) if need_low else None
+    gw = torch.empty_like(up_weights) if need_weights else None
+    if grad_out.numel() and (need_low or need_weights):
+        with torch.cuda.device(grad_out.device):
+            check(_lib.lib().dv_context_upsample_bwd_f32(_ptr(grad_out), _ptr(disp_low), _ptr(up_weights), _ptr(glow), _ptr(gw),
+                                                         b, h, w, _stream(grad_out)), "dv_context_upsample_bwd_f32")
+    return glow, gw
+
+
+# --------------------------------------------------------------------------------------------
+# f4: ACVNet patch convolutions (SceneFlow/models/acv_ddim.py:181-188,377-381)
+# --------------------------------------------------------------------------------------------
+def depthwise3x3_chain(vol: torch.Tensor, w1: torch.Tensor, w2: Optional[torch.Tensor], dil1: int, dil2: int = 1, *,
+                       channels: Optional[Sequence[int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Depth-wise (1,3,3) Conv3d (zero padding = dilation, no bias) on vol [B,C,D,H,W], optionally chained with a second
+    one; w1, w2 are the Conv3d weights [C,1,1,3,3] (or [C,9]).  `channels=(c0, c1)` restricts the work to a slice and
+    leaves the other channels of `out` untouched."""
+    B, Cc, D, H, W = vol.shape
+    _need_cuda(vol, w1, w2, out)
+    vol = _f32c(vol, "vol")
+    w1 = _f32c(w1.reshape(-1, 9), "w1")
+    if w2 is not None:
+        w2 = _f32c(w2.reshape(-1, 9), "w2")
+    c0, c1 = (0, Cc) if channels is None else (int(channels[0]), int(channels[1]))
+    if w1.shape[0] != Cc or (w2 is not None and w2.shape[0] != Cc):
+        raise RuntimeError(f"depthwise3x3_chain: weights must be [C={Cc},9]")
+    if out is None:
+        out = torch.empty_like(vol)
+    assert out.shape == vol.shape and out.dtype == torch.float32 and out.is_contiguous()
+    if vol.numel():
+        with torch.cuda.device(vol.device):
+            check(_lib.lib().dv_depthwise3x3_chain_f32(_ptr(vol), _ptr(w1), _ptr(w2), _ptr(out), B, Cc, D, H, W, c0, c1,
+                                                       int(dil1), int(dil2), _stream(vol)), "dv_depthwise3x3_chain_f32")
+    return out
+
+
+def acv_patch_volume(gwc: torch.Tensor, w_patch: torch.Tensor, w_l1: torch.Tensor, w_l2: torch.Tensor,
+                     w_l3: torch.Tensor) -> torch.Tensor:
+    """cat(patch_l1(g[:, :8]), patch_l2(g[:, 8:24]), patch_l3(g[:, 24:40])) with g = patch(gwc)
+    (acv_ddim.py:377-381): three launches (one per dilation class), the volume read once and written once."""
+    n1, n2, n3 = w_l1.shape[0], w_l2.shape[0], w_l3.shape[0]
+    assert gwc.shape[1] == n1 + n2 + n3 == w_patch.shape[0]
+    w2 = torch.cat([w_l1.reshape(n1, 9), w_l2.reshape(n2, 9), w_l3.reshape(n3, 9)], 0)
+    out = torch.empty_like(_f32c(gwc, "gwc"))
+    depthwise3x3_chain(gwc, w_patch, w2, 1, 1, channels=(0, n1), out=out)
+    depthwise3x3_chain(gwc, w_patch, w2, 1, 2, channels=(n1, n1 + n2), out=out)
+    depthwise3x3_chain(gwc, w_patch, w2, 1, 3, channels=(n1 + n2, n1 + n2 + n3), out=out)
+    return out

@@ -280,6 +280,27 @@ int dv_geo_lookup_packed_f32(const float *const *geo_pyr, const float *const *co
 int dv_geo_filter_packed_f32(const float *const *rows_in, const float *noisy, float *const *rows_out,
                              int64_t N, int64_t C, int64_t D, int num_levels, void *stream);
 
+/* ---- f4: context_upsample  (KITTI15/core/submodule.py:241-253; call sites
+ *          igev_stereo_ddim.py:209,462, igev_stereo.py:146,220)
+ * out[b,Y,X] = sum_{k=ky*3+kx} disp_low[b, Y/4+ky-1, X/4+kx-1] * up_weights[b,k,Y,X]   (zero padding, taps in order)
+ * disp_low [B,1,h,w], up_weights [B,9,4h,4w], out [B,4h,4w]; up_weights/out 16-byte aligned.
+ * Backward: grad_low [B,1,h,w] and/or grad_weights [B,9,4h,4w] (either may be NULL).                               */
+int dv_context_upsample_f32(const float *disp_low, const float *up_weights, float *out,
+                            int64_t B, int64_t h, int64_t w, void *stream);
+int dv_context_upsample_bwd_f32(const float *grad_out, const float *disp_low, const float *up_weights,
+                                float *grad_low, float *grad_weights, int64_t B, int64_t h, int64_t w, void *stream);
+
+/* ---- f4: ACVNet's depth-wise "patch" convolutions on the gwc volume
+ *          (SceneFlow/models/acv_ddim.py:181-188 module definitions, :377-381 call chain; same in acv.py)
+ * For channels c in [c0, c1) of in [B,C,D,H,W], per (b,c,d) plane:
+ *   mid = conv3x3(in,  w1[c], dilation dil1, zero padding)        w1, w2: [C,9] (= Conv3d weight [C,1,1,3,3] flattened)
+ *   out = conv3x3(mid, w2[c], dilation dil2, zero padding)        w2 == NULL: out = mid (a single depth-wise conv)
+ * `out` is [B,C,D,H,W] too (the reference's torch.cat of the three dilation classes is written in place); channels
+ * outside [c0, c1) are not touched.  in != out.                                                                     */
+int dv_depthwise3x3_chain_f32(const float *in, const float *w1, const float *w2, float *out,
+                              int64_t B, int64_t C, int64_t D, int64_t H, int64_t W, int64_t c0, int64_t c1,
+                              int dil1, int dil2, void *stream);
+
 /* ---- f1: backward passes of the volume ops — the reference's training scripts differentiate through them
  *          (SceneFlow/main.py:154 -> models/acv_ddim.py:424-482; KITTI12/main.py; KITTI15/train_stereo.py).
  * Gradients of the functions above with respect to their feature inputs; grad_out has the forward output's shape.

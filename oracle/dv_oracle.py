@@ -491,3 +491,50 @@ class CombinedGeoEncodingVolume:
             out.append(bilinear_sampler_1d(self.init_corr_pyramid[i], init_x0).reshape(b, h, w, -1))
         res = np.concatenate(out, axis=-1)
         return np.ascontiguousarray(res.transpose(0, 3, 1, 2)).astype(f32)
+
+
+# ------------------------------------------------------------------------------------------------
+# f4: context_upsample  (KITTI15/core/submodule.py:241-253)
+# ------------------------------------------------------------------------------------------------
+def context_upsample(disp_low: np.ndarray, up_weights: np.ndarray) -> np.ndarray:
+    """F.unfold(disp_low, 3, 1, 1) -> nearest x4 -> (* up_weights).sum(1).  disp_low [B,1,h,w], up_weights [B,9,4h,4w]
+    -> [B,4h,4w].  Tap k = ky*3 + kx reads disp_low[y+ky-1, x+kx-1] (zero padding), F.unfold's channel order."""
+    b, c, h, w = disp_low.shape
+    assert c == 1 and up_weights.shape == (b, 9, 4 * h, 4 * w)
+    pad = np.zeros((b, h + 2, w + 2), dtype=f32)
+    pad[:, 1:-1, 1:-1] = disp_low[:, 0]
+    out = np.zeros((b, 4 * h, 4 * w), dtype=f32)
+    for ky in range(3):
+        for kx in range(3):
+            tap = pad[:, ky:ky + h, kx:kx + w]                          # [B,h,w]
+            up = np.repeat(np.repeat(tap, 4, axis=1), 4, axis=2)        # nearest x4
+            out = (out + up * up_weights[:, ky * 3 + kx].astype(f32)).astype(f32)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# f4: ACVNet patch convolutions  (SceneFlow/models/acv_ddim.py:181-188,377-381)
+# ------------------------------------------------------------------------------------------------
+def depthwise_conv3x3(vol: np.ndarray, w: np.ndarray, dilation: int) -> np.ndarray:
+    """nn.Conv3d(C, C, (1,3,3), groups=C, dilation=dilation, padding=(0,dilation,dilation), bias=False) on
+    vol [B,C,D,H,W]; w is [C,9] (= weight[C,1,1,3,3] flattened).  Cross-correlation, zero padding."""
+    B, C, D, H, W = vol.shape
+    p = dilation
+    pad = np.zeros((B, C, D, H + 2 * p, W + 2 * p), dtype=f32)
+    pad[..., p:p + H, p:p + W] = vol
+    out = np.zeros_like(vol, dtype=f32)
+    for ky in range(3):
+        for kx in range(3):
+            tap = pad[..., ky * p:ky * p + H, kx * p:kx * p + W]
+            out = (out + tap * w[:, ky * 3 + kx].reshape(1, C, 1, 1, 1).astype(f32)).astype(f32)
+    return out
+
+
+def acv_patch_volume(gwc: np.ndarray, w_patch: np.ndarray, w_l: np.ndarray, splits=(8, 16, 16), dils=(1, 2, 3)) -> np.ndarray:
+    """g = patch(gwc); cat(patch_l1(g[:, :8]), patch_l2(g[:, 8:24]), patch_l3(g[:, 24:40]))  (acv_ddim.py:377-381)."""
+    g = depthwise_conv3x3(gwc, w_patch, 1)
+    outs, c = [], 0
+    for n, dl in zip(splits, dils):
+        outs.append(depthwise_conv3x3(g[:, c:c + n], w_l[c:c + n], dl))
+        c += n
+    return np.concatenate(outs, axis=1)

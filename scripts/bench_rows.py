@@ -123,6 +123,11 @@ def main():
         R.time("f1 disparity_regression_bwd", f"acv B={B}", lambda: ops.disparity_regression_bwd(gd, 192),
                B * (192 + 1) * 540 * 960 * F4)
         del cost, used, gd
+        gwcv = rn(B, G, D, h, w)
+        wp, wl = rn(40, 9), rn(40, 9)
+        R.time("f4 acv_patch_volume (2 chained depth-wise 3x3 + cat)", f"acv B={B} [B,40,48,135,240]",
+               lambda: ops.acv_patch_volume(gwcv, wp, wl[:8], wl[8:24], wl[24:]), 2 * B * G * D * hw * F4)
+        del gwcv
         cq = rn(B, 1, D, h, w) * 4.0
         R.time("f2 upsample_softmax_regress", f"acv B={B} [B,1,48,135,240]->540x960",
                lambda: ops.upsample_softmax_regress(cq, (192, 540, 960)), B * (D * hw + 540 * 960) * F4,
@@ -203,6 +208,10 @@ def main():
                lookup_bytes)
         R.time("a15 geo_lookup_packed (+noise, smooth disp)", f"igev B={B}",
                lambda: ops.geo_lookup_packed(pk, cp, smooth, coords, noisy, 4), lookup_bytes + B * hw * 30 * F4)
+        low, upw = ru(B, 1, h, w) * 190.0, ru(B, 9, 4 * h, 4 * w)
+        R.time("f4 context_upsample", f"igev B={B} -> [B,384,1248]", lambda: ops.context_upsample(low, upw),
+               B * (hw + 10 * 16 * hw) * F4)
+        del upw
         cost = rn(B, 48, h, w)
         R.time("a6 softmax_regress D=48", f"igev B={B} [B,48,96,312]", lambda: ops.softmax_regress(cost),
                B * 49 * hw * F4)

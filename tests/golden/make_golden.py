@@ -385,10 +385,48 @@ def gen_kitti15():
     print("kitti15:", len(out), "arrays")
 
 
+def gen_f4():
+    """context_upsample (KITTI15/core/submodule.py:241-253) with its autograd gradients, and the
+    ACVNet patch convolutions (SceneFlow/models/acv_ddim.py:181-188,377-381: depth-wise (1,3,3) Conv3d chain, dilations
+    1 then 1/2/3, then the channel concat) run through torch's own nn.Conv3d with seeded weights."""
+    import torch
+    sub = _load(REF / "KITTI15" / "core" / "submodule.py", "k15_submodule_f4")
+    out = {}
+    for name, (B, h, w) in {"a": (2, 6, 10), "b": (1, 24, 78)}.items():
+        low = synth.uniform((B, 1, h, w), 301, dtype=np.float32) * np.float32(190)
+        wts = synth.normal((B, 9, 4 * h, 4 * w), 302)
+        wts = np.exp(wts) / np.exp(wts).sum(1, keepdims=True)            # softmax over the 9 taps, as spx_pred is
+        lt, wt = _t(low).requires_grad_(True), _t(wts.astype(np.float32)).requires_grad_(True)
+        res = sub.context_upsample(lt, wt)
+        out[f"f4.ctxup.{name}"] = res.detach().numpy()
+        gout = synth.normal((B, 4 * h, 4 * w), 303)
+        res.backward(_t(gout))
+        out[f"f4.ctxup.{name}.glow"] = lt.grad.numpy()
+        out[f"f4.ctxup.{name}.gw"] = _sample(wt.grad.numpy()) if name == "b" else wt.grad.numpy()
+    # ACV patch chain: the module definitions of acv_ddim.py:181-188 with seeded weights
+    torch.manual_seed(0)
+    import torch.nn as nn
+    patch = nn.Conv3d(40, 40, kernel_size=(1, 3, 3), stride=1, dilation=1, groups=40, padding=(0, 1, 1), bias=False)
+    l1 = nn.Conv3d(8, 8, kernel_size=(1, 3, 3), stride=1, dilation=1, groups=8, padding=(0, 1, 1), bias=False)
+    l2 = nn.Conv3d(16, 16, kernel_size=(1, 3, 3), stride=1, dilation=2, groups=16, padding=(0, 2, 2), bias=False)
+    l3 = nn.Conv3d(16, 16, kernel_size=(1, 3, 3), stride=1, dilation=3, groups=16, padding=(0, 3, 3), bias=False)
+    for name, (B, D, H, W) in {"a": (1, 3, 9, 14), "b": (1, 4, 27, 60)}.items():
+        vol = synth.normal((B, 40, D, H, W), 311)
+        with torch.no_grad():
+            g = patch(_t(vol))                                           # acv_ddim.py:377
+            res = torch.cat((l1(g[:, :8]), l2(g[:, 8:24]), l3(g[:, 24:40])), dim=1)   # :378-381
+        out[f"f4.patch.{name}.first"] = g.numpy() if name == "a" else _sample(g.numpy())
+        out[f"f4.patch.{name}"] = res.numpy() if name == "a" else _sample(res.numpy())
+    out["f4.patch.w_patch"] = patch.weight.detach().numpy().reshape(40, 9)
+    out["f4.patch.w_l"] = np.concatenate([m.weight.detach().numpy().reshape(-1, 9) for m in (l1, l2, l3)], 0)
+    np.savez_compressed(HERE / "f4.npz", **out)
+    print("f4:", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sceneflow", "kitti12", "kitti15"]
+    which = sys.argv[1:] or ["sceneflow", "kitti12", "kitti15", "f4"]
     if len(which) == 1 and os.environ.get("DV_GOLDEN_CHILD") == "1":
-        {"sceneflow": gen_sceneflow, "kitti12": gen_kitti12, "kitti15": gen_kitti15}[which[0]]()
+        {"sceneflow": gen_sceneflow, "kitti12": gen_kitti12, "kitti15": gen_kitti15, "f4": gen_f4}[which[0]]()
     else:
         for name in which:
             env = dict(os.environ, DV_GOLDEN_CHILD="1")
