@@ -82,6 +82,153 @@ gwc_bwd_kernel(const float *__restrict__ go, const float *__restrict__ ref, cons
     }
 }
 
+// ---- quad kernel (plain gwc volume, HW % 4 == 0, 16-byte aligned) ------------------------------------------------------
+// Same tiling idea as the forward kernel (gwc_volume.cu): CTA = (span of SQ quads, group x channel chunk, batch); the CK
+// channel rows of ref (span + Dpad) and of the tgt window (Dpad + span) are staged once in shared memory by bulk copies;
+// thread = one quad (4 pixels), 2 x CK x 4 accumulators in registers, the D loop runs in blocks of 4 disparities so that
+// every feature operand is a static pick from two aligned float4 of shared memory:
+//     d_ref[k][p+i] += g[d][p+i]   * tgt[k][p+i-d]      window  tgt[p-d0-4 .. p-d0+3], element 4 + i - (d-d0)
+//     d_tgt[k][p+i] += g[d][p+i+d] * ref[k][p+i+d]      window  ref[p+d0 .. p+d0+7],   element i + (d-d0)
+// g is read straight from global (128-bit, L1-cached: the shifted d_tgt reads of a CTA overlap its d_ref reads).  Per 4
+// disparities a thread issues 4*CK LDS.128 + 12 LDG.128 for 32*CK FMA (the thread-per-pixel kernel: 8 LDG per FMA pair).
+template <int CK, int SQ>
+__global__ void __launch_bounds__(2 * SQ)
+gwc_bwd_quad_kernel(const float *__restrict__ go, const float *__restrict__ ref, const float *__restrict__ tgt,
+                    float *__restrict__ gref, float *__restrict__ gtgt, int C, int HW, int W, int D, int G, int cpg, int Dpad,
+                    int64_t go_elems) {
+    constexpr int SPAN = SQ * 4;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int pitch = SPAN + Dpad;
+    float *sR = smem;               // ref rows  [CK][SPAN + Dpad], element 0 = flat index p0
+    float *sT = smem + CK * pitch;  // tgt rows  [CK][Dpad + SPAN], element Dpad = flat index p0
+    const int chunks = cpg / CK;
+    const int g = blockIdx.y / chunks, kc = blockIdx.y % chunks, b = blockIdx.z;
+    const int p0 = blockIdx.x * SPAN;
+    const int len = min(SPAN, HW - p0);
+    const int64_t fb = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * cpg + kc * CK) * HW;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int rlen = min(len + Dpad, HW - p0);        // ref: do not run past the plane (masked terms only)
+        const int64_t toff = fb + p0 - Dpad;              // tgt window start; negative only for the very first plane
+        const int skip0 = toff < 0 ? static_cast<int>(-toff) : 0;
+        if (threadIdx.x == 0) mbar_expect_tx(&bar, 4u * (CK * (rlen + len + Dpad) - skip0));
+        __syncwarp();
+        for (int k = threadIdx.x; k < CK; k += 32) {
+            bulk_g2s(sR + k * pitch, ref + fb + static_cast<int64_t>(k) * HW + p0, 4u * rlen, &bar);
+            const int skip = k == 0 ? skip0 : 0;
+            bulk_g2s(sT + k * pitch + skip, tgt + toff + static_cast<int64_t>(k) * HW + skip, 4u * (len + Dpad - skip), &bar);
+        }
+    }
+    {   // the parts of the windows no copy lands in (plane tail of ref, tensor head of tgt) are only ever multiplied by a
+        // masked (zero) gradient: clear them so that stale shared memory cannot inject NaNs
+        const int rlen = min(len + Dpad, HW - p0);
+        const int64_t toff = fb + p0 - Dpad;
+        const int skip0 = toff < 0 ? static_cast<int>(-toff) : 0;
+        for (int k = 0; k < CK; ++k) {
+            for (int e = rlen + threadIdx.x; e < pitch; e += 2 * SQ) sR[k * pitch + e] = 0.0f;
+            for (int e = len + Dpad + threadIdx.x; e < pitch; e += 2 * SQ) sT[k * pitch + e] = 0.0f;
+        }
+        for (int e = threadIdx.x; e < skip0; e += 2 * SQ) sT[e] = 0.0f;
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    // warps [0, SQ/32) accumulate d_ref, warps [SQ/32, 2 SQ/32) accumulate d_tgt: the two gradients share no operand
+    // besides the staged rows, and splitting them halves the registers and the serial work per thread
+    const int q = threadIdx.x % SQ;
+    const bool tgt_pass = threadIdx.x >= SQ;
+    float *gdst = tgt_pass ? gtgt : gref;
+    const int p = p0 + 4 * q;
+    if (p >= HW || !gdst) return;
+    int xs[4];
+    xs[0] = p % W;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        xs[i] = xs[i - 1] + 1;
+        if (xs[i] >= W) xs[i] -= W;
+    }
+    float acc[CK][4];
+#pragma unroll
+    for (int k = 0; k < CK; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[k][i] = 0.0f;
+    const float *gp = go + (static_cast<int64_t>(b) * G + g) * D * HW + p;
+    const int64_t gbase = (static_cast<int64_t>(b) * G + g) * D * HW + p;   // flat index of gp[0]
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (!tgt_pass) {
+        for (int d0 = 0; d0 < D; d0 += 4) {
+            float m[4][4];  // masked gradient: the d_ref term needs x >= d
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = d0 + j;
+                const float4 gv = d < D ? __ldg(reinterpret_cast<const float4 *>(gp + static_cast<int64_t>(d) * HW)) : zero4;
+                const float v[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m[j][i] = xs[i] >= d ? v[i] : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < CK; ++k) {
+                const float *tp = sT + k * pitch + Dpad + 4 * q - d0 - 4;
+                const float4 t0 = *reinterpret_cast<const float4 *>(tp), t1 = *reinterpret_cast<const float4 *>(tp + 4);
+                const float tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(m[j][i], tw[4 + i - j], acc[k][i]);
+            }
+        }
+    } else {
+        for (int d0 = 0; d0 < D; d0 += 4) {
+            float m[4][4];  // masked shifted gradient g[d][p+i+d]: the d_tgt term needs x + d < W
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = d0 + j;
+                const int64_t o = static_cast<int64_t>(d) * HW + d0;
+                // shifted reads may run past the plane (masked terms) but must not run past the tensor
+                const float4 ga = (d < D && gbase + o + 3 < go_elems) ? __ldg(reinterpret_cast<const float4 *>(gp + o)) : zero4;
+                const float4 gb = (d < D && gbase + o + 7 < go_elems) ? __ldg(reinterpret_cast<const float4 *>(gp + o + 4)) : zero4;
+                const float v[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m[j][i] = (d < D && xs[i] + d < W) ? v[i + j] : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < CK; ++k) {
+                const float *rp = sR + k * pitch + 4 * q + d0;
+                const float4 r0 = *reinterpret_cast<const float4 *>(rp), r1 = *reinterpret_cast<const float4 *>(rp + 4);
+                const float rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(m[j][i], rw[i + j], acc[k][i]);
+            }
+        }
+    }
+    const float inv = 1.0f / static_cast<float>(cpg);
+#pragma unroll
+    for (int k = 0; k < CK; ++k)
+        *reinterpret_cast<float4 *>(gdst + fb + static_cast<int64_t>(k) * HW + p) =
+            make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
+}
+
+template <int CK>
+static int launch_gwc_bwd_quad(const float *go, const float *ref, const float *tgt, float *gref, float *gtgt, int B, int C,
+                               int HW, int W, int D, int G, int cpg, cudaStream_t st) {
+    constexpr int SQ = 64, SPAN = SQ * 4;
+    const int Dpad = (D + 3) / 4 * 4 + 4;  // the last block of 4 disparities reads up to d0 + 7 floats past a quad
+    const size_t smem = sizeof(float) * 2 * CK * (SPAN + Dpad);
+    auto kern = gwc_bwd_quad_kernel<CK, SQ>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return DV_ERR_LAUNCH;
+    dim3 grid((HW + SPAN - 1) / SPAN, G * (cpg / CK), B);
+    kern<<<grid, 2 * SQ, smem, st>>>(go, ref, tgt, gref, gtgt, C, HW, W, D, G, cpg, Dpad, static_cast<int64_t>(B) * G * D * HW);
+    return finish_launch();
+}
+
 // any channels-per-group: thread = (b, channel, pixel)
 __global__ void gwc_bwd_generic_kernel(const float *__restrict__ go, const float *__restrict__ ref,
                                        const float *__restrict__ tgt, float *__restrict__ gref, float *__restrict__ gtgt,
@@ -121,6 +268,15 @@ static int gwc_bwd_impl(const float *go, const float *ref, const float *tgt, flo
     const int64_t HW = H * W;
     if (HW > INT32_MAX || B > 65535 || G > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
     const int cpg = static_cast<int>(C / G);
+    if (mneg == 0 && dofs == 0 && Dtot == D && HW % 4 == 0 && W >= 4 && D <= 256 && aligned16(go) && aligned16(ref) &&
+        aligned16(tgt) && (!gref || aligned16(gref)) && (!gtgt || aligned16(gtgt)) && G * static_cast<int64_t>(cpg) <= 65535 &&
+        tune_variant("DV_GWC_BWD_QUAD", 1)) {
+        const int Bi = static_cast<int>(B), Ci = static_cast<int>(C), HWi = static_cast<int>(HW), Wi = static_cast<int>(W),
+                  Di = static_cast<int>(D), Gi = static_cast<int>(G);
+        if (cpg % 8 == 0) return launch_gwc_bwd_quad<8>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, st);
+        if (cpg % 6 == 0) return launch_gwc_bwd_quad<6>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, st);
+        if (cpg % 4 == 0) return launch_gwc_bwd_quad<4>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, st);
+    }
     dim3 grid(static_cast<unsigned>((HW + 127) / 128), static_cast<unsigned>(G), static_cast<unsigned>(B));
 #define DV_GB(CPGV)                                                                                                   \
     gwc_bwd_kernel<CPGV><<<grid, 128, 0, st>>>(go, ref, tgt, gref, gtgt, static_cast<int>(C), static_cast<int>(HW),   \
