@@ -14,9 +14,13 @@ namespace dv {
 
 // ---- a14: all-pairs correlation, one (b, y) row pair per blockIdx.z --------------------------
 // out[b,y,x1,x2] = sum_c f1[b,c,y,x1] * f2[b,c,y,x2]; fp32 FMA (TF32 would break the 1e-4 bound).
-constexpr int kApTile = 64;  // 64 x 64 output tile, 256 threads, 4 x 4 per thread
+// 64 x 64 output tile per CTA, 64 threads, 8 x 8 register tile per thread: per channel a thread reads 4 LDS.128 (two for
+// its 8 rows, two for its 8 columns) for 64 FMA — the 4 x 4 tile of the first version (2 LDS.128 per 16 FMA) left the
+// FMA pipe waiting on shared memory (ncu: 66 % issue slots, 98 M shared wavefronts).  A thread's rows/columns are the two
+// float4 at 4*t and 32 + 4*t, so the 8 lanes that differ in tx read 32 consecutive floats: conflict-free.
+constexpr int kApTile = 64;  // 64 x 64 output tile
 constexpr int kApKc = 32;    // channels per shared-memory chunk
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
 corr1d_allpairs_kernel(const float *__restrict__ f1, const float *__restrict__ f2, float *__restrict__ out, int C,
                        int H, int W1, int W2) {
     __shared__ __align__(16) float sA[kApKc][kApTile];
@@ -24,37 +28,74 @@ corr1d_allpairs_kernel(const float *__restrict__ f1, const float *__restrict__ f
     const int by = blockIdx.z;  // b * H + y
     const int b = by / H, y = by % H;
     const int x1_0 = blockIdx.y * kApTile, x2_0 = blockIdx.x * kApTile;
-    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-    float acc[4][4] = {};
+    const int tx = threadIdx.x % 8, ty = threadIdx.x / 8;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    const float *a0 = f1 + (static_cast<int64_t>(b) * C * H + y) * W1;  // + c*H*W1 + x
+    const float *b0 = f2 + (static_cast<int64_t>(b) * C * H + y) * W2;
+    const bool vecA = (W1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15u) == 0) && x1_0 + kApTile <= W1;
+    const bool vecB = (W2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(f2) & 15u) == 0) && x2_0 + kApTile <= W2;
     for (int c0 = 0; c0 < C; c0 += kApKc) {
-        for (int e = threadIdx.x; e < kApKc * kApTile; e += 256) {
-            const int k = e / kApTile, j = e % kApTile;
+        // 32 x 64 floats per operand: thread t loads the float4 (k = e / 16, j4 = e % 16), e = t, t + 64, ...
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = threadIdx.x + 64 * u;
+            const int k = e / 16, j = (e % 16) * 4;
             const int c = c0 + k;
-            const int x1 = x1_0 + j, x2 = x2_0 + j;
-            sA[k][j] = (c < C && x1 < W1) ? f1[((static_cast<int64_t>(b) * C + c) * H + y) * W1 + x1] : 0.0f;
-            sB[k][j] = (c < C && x2 < W2) ? f2[((static_cast<int64_t>(b) * C + c) * H + y) * W2 + x2] : 0.0f;
+            float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va;
+            if (c < C) {
+                const float *pa = a0 + static_cast<int64_t>(c) * H * W1 + x1_0 + j;
+                const float *pb = b0 + static_cast<int64_t>(c) * H * W2 + x2_0 + j;
+                if (vecA) va = __ldg(reinterpret_cast<const float4 *>(pa));
+                else {
+                    va.x = x1_0 + j + 0 < W1 ? __ldg(pa + 0) : 0.0f; va.y = x1_0 + j + 1 < W1 ? __ldg(pa + 1) : 0.0f;
+                    va.z = x1_0 + j + 2 < W1 ? __ldg(pa + 2) : 0.0f; va.w = x1_0 + j + 3 < W1 ? __ldg(pa + 3) : 0.0f;
+                }
+                if (vecB) vb = __ldg(reinterpret_cast<const float4 *>(pb));
+                else {
+                    vb.x = x2_0 + j + 0 < W2 ? __ldg(pb + 0) : 0.0f; vb.y = x2_0 + j + 1 < W2 ? __ldg(pb + 1) : 0.0f;
+                    vb.z = x2_0 + j + 2 < W2 ? __ldg(pb + 2) : 0.0f; vb.w = x2_0 + j + 3 < W2 ? __ldg(pb + 3) : 0.0f;
+                }
+            }
+            *reinterpret_cast<float4 *>(&sA[k][j]) = va;
+            *reinterpret_cast<float4 *>(&sB[k][j]) = vb;
         }
         __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int k = 0; k < kApKc; ++k) {
-            const float4 a4 = *reinterpret_cast<const float4 *>(&sA[k][ty * 4]);
-            const float4 b4 = *reinterpret_cast<const float4 *>(&sB[k][tx * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float4 a_lo = *reinterpret_cast<const float4 *>(&sA[k][4 * ty]);
+            const float4 a_hi = *reinterpret_cast<const float4 *>(&sA[k][32 + 4 * ty]);
+            const float4 b_lo = *reinterpret_cast<const float4 *>(&sB[k][4 * tx]);
+            const float4 b_hi = *reinterpret_cast<const float4 *>(&sB[k][32 + 4 * tx]);
+            const float a[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+            const float bb[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
         }
         __syncthreads();
     }
+    const bool vecO = (W2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int x1 = x1_0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int x1 = x1_0 + (i < 4 ? 4 * ty + i : 32 + 4 * ty + i - 4);
         if (x1 >= W1) continue;
-        float *op = out + (static_cast<int64_t>(by) * W1 + x1) * W2 + x2_0 + tx * 4;
+        float *orow = out + (static_cast<int64_t>(by) * W1 + x1) * W2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (x2_0 + tx * 4 + j < W2) op[j] = acc[i][j];
+        for (int hh = 0; hh < 2; ++hh) {
+            const int x2 = x2_0 + 32 * hh + 4 * tx;
+            if (vecO && x2 + 3 < W2) {
+                *reinterpret_cast<float4 *>(orow + x2) = make_float4(acc[i][4 * hh], acc[i][4 * hh + 1], acc[i][4 * hh + 2], acc[i][4 * hh + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x2 + j < W2) orow[x2 + j] = acc[i][4 * hh + j];
+            }
+        }
     }
 }
 
@@ -551,7 +592,7 @@ extern "C" int dv_corr1d_allpairs_f32(const float *fmap1, const float *fmap2, fl
         }
         return DV_ERR_UNSUPPORTED;
     }
-    corr1d_allpairs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    corr1d_allpairs_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
         fmap1, fmap2, out, static_cast<int>(C), static_cast<int>(H), static_cast<int>(W1), static_cast<int>(W2));
     return finish_launch();
 }

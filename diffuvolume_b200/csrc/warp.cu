@@ -13,10 +13,14 @@
 
 namespace dv {
 
+constexpr int kWarpCg = 8;  // channels per thread: all 4 x 8 tap loads of a thread are issued before the first blend
+
 __global__ void __launch_bounds__(256)
-warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *__restrict__ out, int C, int H, int W) {
+warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *__restrict__ out, int C, int H, int W,
+            int cgroups) {
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, b = blockIdx.z;
+    const int y = blockIdx.y, b = blockIdx.z / cgroups, cbeg = (blockIdx.z % cgroups) * kWarpCg;
+    const int cend = min(cbeg + kWarpCg, C);
     if (px >= W) return;
     const int64_t HW = static_cast<int64_t>(H) * W;
     const float d = disp[static_cast<int64_t>(b) * HW + static_cast<int64_t>(y) * W + px];
@@ -40,17 +44,22 @@ warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *
     const float *xp = x + static_cast<int64_t>(b) * C * HW;
     float *op = out + static_cast<int64_t>(b) * C * HW + static_cast<int64_t>(y) * W + px;
     if (m == 0.0f) {
-        for (int c = 0; c < C; ++c) op[static_cast<int64_t>(c) * HW] = 0.0f;
+        for (int c = cbeg; c < cend; ++c) op[static_cast<int64_t>(c) * HW] = 0.0f;
         return;
     }
-#pragma unroll 4
-    for (int c = 0; c < C; ++c) {
-        const float *pc = xp + static_cast<int64_t>(c) * HW;
-        float v = __fmul_rn(__ldg(pc + o00), w00);
-        v = __fadd_rn(v, __fmul_rn(__ldg(pc + o01), w01));
-        v = __fadd_rn(v, __fmul_rn(__ldg(pc + o10), w10));
-        v = __fadd_rn(v, __fmul_rn(__ldg(pc + o11), w11));
-        op[static_cast<int64_t>(c) * HW] = v;
+    float t00[kWarpCg], t01[kWarpCg], t10[kWarpCg], t11[kWarpCg];
+#pragma unroll
+    for (int k = 0; k < kWarpCg; ++k) {
+        const float *pc = xp + static_cast<int64_t>(min(cbeg + k, C - 1)) * HW;
+        t00[k] = __ldg(pc + o00); t01[k] = __ldg(pc + o01); t10[k] = __ldg(pc + o10); t11[k] = __ldg(pc + o11);
+    }
+#pragma unroll
+    for (int k = 0; k < kWarpCg; ++k) {
+        float v = __fmul_rn(t00[k], w00);
+        v = __fadd_rn(v, __fmul_rn(t01[k], w01));
+        v = __fadd_rn(v, __fmul_rn(t10[k], w10));
+        v = __fadd_rn(v, __fmul_rn(t11[k], w11));
+        if (cbeg + k < cend) op[static_cast<int64_t>(cbeg + k) * HW] = v;
     }
 }
 
@@ -61,9 +70,10 @@ extern "C" int dv_warp_f32(const float *x, const float *disp, float *out, int64_
     using namespace dv;
     if (!x || !disp || !out) return DV_ERR_NULL;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
-    if (H * W > INT32_MAX || B > 65535 || H > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
-    dim3 grid(static_cast<unsigned>((W + 255) / 256), static_cast<unsigned>(H), static_cast<unsigned>(B));
+    const int64_t cgroups = (C + kWarpCg - 1) / kWarpCg;
+    if (H * W > INT32_MAX || B * cgroups > 65535 || H > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    dim3 grid(static_cast<unsigned>((W + 255) / 256), static_cast<unsigned>(H), static_cast<unsigned>(B * cgroups));
     warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, disp, out, static_cast<int>(C), static_cast<int>(H),
-                                                                   static_cast<int>(W));
+                                                                   static_cast<int>(W), static_cast<int>(cgroups));
     return finish_launch();
 }

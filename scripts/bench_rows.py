@@ -152,7 +152,11 @@ def main():
         Bc = min(B, 4)
         fl, fr = rn(Bc, 32, 384, 1248), rn(Bc, 32, 384, 1248)
         dsp = ru(Bc, 1, 384, 1248) * 100.0
-        R.time("f3 warp", f"pcw B={Bc} C=32 384x1248", lambda: ops.warp(fr, dsp), Bc * (2 * 32 + 1) * 384 * 1248 * F4)
+        R.time("f3 warp (random disparities: worst-case gather)", f"pcw B={Bc} C=32 384x1248", lambda: ops.warp(fr, dsp),
+               Bc * (2 * 32 + 1) * 384 * 1248 * F4)
+        dsm = (torch.linspace(2, 90, 1248, device=dev).view(1, 1, 1, -1).expand(Bc, 1, 384, 1248) + ru(Bc, 1, 384, 1248)).contiguous()
+        R.time("f3 warp (smooth disparities)", f"pcw B={Bc} C=32 384x1248", lambda: ops.warp(fr, dsm),
+               Bc * (2 * 32 + 1) * 384 * 1248 * F4)
         R.time("a5 corr_volume_2sided", f"pcw B={Bc} C=32 m=24 384x1248", lambda: ops.corr_volume_2sided(fl, fr, 24, 1),
                Bc * (2 * 32 + 49) * 384 * 1248 * F4, flops=2.0 * Bc * 32 * 49 * 384 * 1248)
         R.time("a2 gwc_volume C=32 G=1 D=25 (positive half of a5)", f"pcw B={Bc} 384x1248", lambda: ops.gwc_volume(fl, fr, 25, 1),
