@@ -99,6 +99,129 @@ corr1d_allpairs_kernel(const float *__restrict__ f1, const float *__restrict__ f
     }
 }
 
+// ---- a14 on the tensor cores: 3xTF32 ------------------------------------------------------------
+// ncu on the FFMA kernel: DRAM 9 %, issue slots 66 % — the one compute-bound op of the path (AI ~ 41 flop/B), so the
+// north_star's "tensor cores only if compute-bound" clause applies.  Plain TF32 (10-bit mantissa) misses the 1e-4 bound;
+// each fp32 operand is therefore split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and the product is accumulated as
+// lo*hi + hi*lo + hi*hi in fp32 (the dropped lo*lo term is ~2^-22 relative): fp32-level accuracy from three
+// mma.sync.m16n8k8 TF32 instructions.  K = C = 96 is far too short for a tcgen05/TMEM pipeline to amortise its
+// prologue on a 312 x 312 x 96 problem per row pair; warp-level MMA with register fragments fits the shape.
+// CTA = 64 x 64 output tile, 4 warps (2 x 2), warp tile 32 x 32 = 2 x 4 MMA tiles; operands staged [k][64 + 8] so that
+// the fragment reads (address = tig * pitch + gid) hit 32 distinct banks.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+constexpr int kApPitch = kApTile + 8;
+__global__ void __launch_bounds__(128)
+corr1d_allpairs_mma_kernel(const float *__restrict__ f1, const float *__restrict__ f2, float *__restrict__ out, int C,
+                           int H, int W1, int W2) {
+    __shared__ __align__(16) float sA[kApKc][kApPitch];
+    __shared__ __align__(16) float sB[kApKc][kApPitch];
+    const int by = blockIdx.z;
+    const int b = by / H, y = by % H;
+    const int x1_0 = blockIdx.y * kApTile, x2_0 = blockIdx.x * kApTile;
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int m_base = (warp >> 1) * 32, n_base = (warp & 1) * 32;
+    float acc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.0f;
+    const float *a0 = f1 + (static_cast<int64_t>(b) * C * H + y) * W1;
+    const float *b0 = f2 + (static_cast<int64_t>(b) * C * H + y) * W2;
+    const bool vecA = (W1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15u) == 0) && x1_0 + kApTile <= W1;
+    const bool vecB = (W2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(f2) & 15u) == 0) && x2_0 + kApTile <= W2;
+    for (int c0 = 0; c0 < C; c0 += kApKc) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = threadIdx.x + 128 * u;
+            const int k = e / 16, j = (e % 16) * 4;
+            const int c = c0 + k;
+            float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va;
+            if (c < C) {
+                const float *pa = a0 + static_cast<int64_t>(c) * H * W1 + x1_0 + j;
+                const float *pb = b0 + static_cast<int64_t>(c) * H * W2 + x2_0 + j;
+                if (vecA) va = __ldg(reinterpret_cast<const float4 *>(pa));
+                else {
+                    va.x = x1_0 + j + 0 < W1 ? __ldg(pa + 0) : 0.0f; va.y = x1_0 + j + 1 < W1 ? __ldg(pa + 1) : 0.0f;
+                    va.z = x1_0 + j + 2 < W1 ? __ldg(pa + 2) : 0.0f; va.w = x1_0 + j + 3 < W1 ? __ldg(pa + 3) : 0.0f;
+                }
+                if (vecB) vb = __ldg(reinterpret_cast<const float4 *>(pb));
+                else {
+                    vb.x = x2_0 + j + 0 < W2 ? __ldg(pb + 0) : 0.0f; vb.y = x2_0 + j + 1 < W2 ? __ldg(pb + 1) : 0.0f;
+                    vb.z = x2_0 + j + 2 < W2 ? __ldg(pb + 2) : 0.0f; vb.w = x2_0 + j + 3 < W2 ? __ldg(pb + 3) : 0.0f;
+                }
+            }
+            *reinterpret_cast<float4 *>(&sA[k][j]) = va;
+            *reinterpret_cast<float4 *>(&sB[k][j]) = vb;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k0 = 0; k0 < kApKc; k0 += 8) {
+            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int m = m_base + mt * 16 + gid;
+                const float v[4] = {sA[k0 + tig][m], sA[k0 + tig][m + 8], sA[k0 + tig + 4][m], sA[k0 + tig + 4][m + 8]};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ah[mt][i] = to_tf32(v[i]);
+                    al[mt][i] = to_tf32(__fsub_rn(v[i], __uint_as_float(ah[mt][i])));
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int n = n_base + nt * 8 + gid;
+                const float v[2] = {sB[k0 + tig][n], sB[k0 + tig + 4][n]};
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    bh[nt][i] = to_tf32(v[i]);
+                    bl[nt][i] = to_tf32(__fsub_rn(v[i], __uint_as_float(bh[nt][i])));
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    mma_tf32(acc[mt][nt], al[mt], bh[nt]);
+                    mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
+                    mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+                }
+        }
+        __syncthreads();
+    }
+    const bool vec2 = (W2 % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int x1 = x1_0 + m_base + mt * 16 + gid + 8 * hh;
+            if (x1 >= W1) continue;
+            float *orow = out + (static_cast<int64_t>(by) * W1 + x1) * W2;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int x2 = x2_0 + n_base + nt * 8 + 2 * tig;
+                const float v0 = acc[mt][nt][2 * hh], v1 = acc[mt][nt][2 * hh + 1];
+                if (vec2 && x2 + 1 < W2) *reinterpret_cast<float2 *>(orow + x2) = make_float2(v0, v1);
+                else {
+                    if (x2 < W2) orow[x2] = v0;
+                    if (x2 + 1 < W2) orow[x2 + 1] = v1;
+                }
+            }
+        }
+}
+
 // ---- geo [B,C,D,h,w] -> rows [B*h*w, C, D]  (permute(0,3,4,1,2), geometry_ddim.py:19) ---------
 __global__ void __launch_bounds__(256)
 geo_permute_kernel(const float *__restrict__ geo, float *__restrict__ rows, int C, int D, int hw) {
@@ -591,6 +714,11 @@ extern "C" int dv_corr1d_allpairs_f32(const float *fmap1, const float *fmap2, fl
             (void)z0;
         }
         return DV_ERR_UNSUPPORTED;
+    }
+    if (tune_variant("DV_ALLPAIRS_MMA", 1)) {
+        corr1d_allpairs_mma_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+            fmap1, fmap2, out, static_cast<int>(C), static_cast<int>(H), static_cast<int>(W1), static_cast<int>(W2));
+        return finish_launch();
     }
     corr1d_allpairs_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
         fmap1, fmap2, out, static_cast<int>(C), static_cast<int>(H), static_cast<int>(W1), static_cast<int>(W2));
