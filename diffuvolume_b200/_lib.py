@@ -75,11 +75,13 @@ SIGNATURES = {
     "dv_built_for_sm": (_I, []),
     "dv_groupwise_correlation_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_gwc_volume_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
+    "dv_gwc_volume_bf16": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_concat_volume_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _I, _P, _D, _P]),
     "dv_att_softmax_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _P]),
     "dv_filter_factor_f32": (_I, [_P, _I, _P, _D, _P, _I64, _I64, _I64, _I64, _P]),
     "dv_filter_factor": (_I, [_P, _I, _P, _D, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "dv_concat_volume_weighted_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P]),
+    "dv_concat_volume_weighted_bf16": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P]),
     "dv_volume_filter_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _I64, _P, _I, _P, _D, _P, _P]),
     "dv_corr_volume_2sided_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_softmax_regress_f32": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _F, _F, _P, _F, _I, _P]),

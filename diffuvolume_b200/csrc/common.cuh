@@ -1,6 +1,7 @@
 // common.cuh — shared device/host helpers for the DiffuVolume B200 hot-path kernels (sm_100a).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
@@ -140,6 +141,16 @@ __device__ __forceinline__ void stg_cs(float4 *p, const float4 &v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
+// 4 consecutive volume elements in the output dtype: fp32 = one 128-bit streaming store, bf16 (round-to-nearest-even,
+// what torch's .to(torch.bfloat16) does) = one 64-bit streaming store; a warp still writes one contiguous run.
+__device__ __forceinline__ void store4_cs(float *p, const float4 &v) { stg_cs(reinterpret_cast<float4 *>(p), v); }
+__device__ __forceinline__ void store4_cs(__nv_bfloat16 *p, const float4 &v) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(*reinterpret_cast<const uint32_t *>(&lo)),
+                 "r"(*reinterpret_cast<const uint32_t *>(&hi))
+                 : "memory");
+}
+
 __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"

@@ -43,11 +43,11 @@ struct CsStage {
     static constexpr int kFloats = 2 * kFactor + ((kFeat + 31) / 32) * 32;   // keep every stage 128-byte aligned
 };
 
-template <int CGT, bool HAS_W, bool HAS_N, int kCsStages, int MINB>
+template <int CGT, bool HAS_W, bool HAS_N, int kCsStages, int MINB, typename OutT>
 __global__ void __launch_bounds__(kCsThreads, MINB)
 concat_stream_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_n,
                      const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_tgt,
-                     float *__restrict__ out, int C, int HW, int W, int D, int mask_left, int spans, int ndchunks,
+                     OutT *__restrict__ out, int C, int HW, int W, int D, int mask_left, int spans, int ndchunks,
                      int ntiles, int slot, int sync_tiles) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t full_bar[kCsStages], empty_bar[kCsStages];
@@ -143,7 +143,7 @@ concat_stream_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             const bool left = c0 < C;
             const bool masked = !left || mask_left;
             const float *sf = st + 2 * kFactor;
-            float *op = out + ((static_cast<int64_t>(b) * 2 * C + c0) * D + d0) * HW + p;
+            OutT *op = out + ((static_cast<int64_t>(b) * 2 * C + c0) * D + d0) * HW + p;
             const int64_t cstride = static_cast<int64_t>(D) * HW;
 #pragma unroll 2
             for (int kc = 0; kc < CGT; ++kc) {
@@ -171,7 +171,7 @@ concat_stream_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         }
                         if (HAS_W) { o.x *= w4[j].x; o.y *= w4[j].y; o.z *= w4[j].z; o.w *= w4[j].w; }
                         if (HAS_N) { o.x *= n4[j].x; o.y *= n4[j].y; o.z *= n4[j].z; o.w *= n4[j].w; }
-                        stg_cs(reinterpret_cast<float4 *>(op + kc * cstride + static_cast<int64_t>(j) * HW), o);
+                        store4_cs(op + kc * cstride + static_cast<int64_t>(j) * HW, o);
                     }
                 }
             }
@@ -182,11 +182,11 @@ concat_stream_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     }
 }
 
-template <int CGT, bool HAS_W, bool HAS_N, int STAGES, int MINB>
-static int launch_cs2(const CUtensorMap &mw, const CUtensorMap &mn, const CUtensorMap &mr, const CUtensorMap &mt, float *out,
+template <int CGT, bool HAS_W, bool HAS_N, int STAGES, int MINB, typename OutT>
+static int launch_cs2(const CUtensorMap &mw, const CUtensorMap &mn, const CUtensorMap &mr, const CUtensorMap &mt, OutT *out,
                       int B, int C, int HW, int W, int D, int mask_left, cudaStream_t st) {
     const size_t smem = sizeof(float) * STAGES * CsStage<CGT>::kFloats;
-    auto kern = concat_stream_kernel<CGT, HAS_W, HAS_N, STAGES, MINB>;
+    auto kern = concat_stream_kernel<CGT, HAS_W, HAS_N, STAGES, MINB, OutT>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
         return DV_ERR_LAUNCH;
     const int spans = (HW + kCsSpan - 1) / kCsSpan;
@@ -203,9 +203,9 @@ template <int CGT, bool HAS_W, bool HAS_N>
 static int launch_cs(const CUtensorMap &mw, const CUtensorMap &mn, const CUtensorMap &mr, const CUtensorMap &mt, float *out,
                      int B, int C, int HW, int W, int D, int mask_left, cudaStream_t st) {
     const int v = tune_variant("DV_CS_SHAPE", 21);   // stages*10 + CTAs per SM
-    if (v == 22) return launch_cs2<CGT, HAS_W, HAS_N, 2, 2>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st);
-    if (v == 31) return launch_cs2<CGT, HAS_W, HAS_N, 3, 1>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st);
-    return launch_cs2<CGT, HAS_W, HAS_N, 2, 1>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st);
+    if (v == 22) return launch_cs2<CGT, HAS_W, HAS_N, 2, 2, float>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st);
+    if (v == 31) return launch_cs2<CGT, HAS_W, HAS_N, 3, 1, float>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st);
+    return launch_cs2<CGT, HAS_W, HAS_N, 2, 1, float>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st);
 }
 
 // Returns DV_ERR_UNSUPPORTED when the tensor maps cannot be built (the caller then takes the LDG kernel).
@@ -241,4 +241,48 @@ int launch_concat_stream(const float *ref, const float *tgt, float *out, int B, 
 #undef DV_CS
 }
 
+// bf16 volume: the same producer with one rounding at the store (channel groups of 8 or 4 only)
+int launch_concat_stream_bf16(const float *ref, const float *tgt, __nv_bfloat16 *out, int B, int C, int HW, int W, int D,
+                              int mask_left, const float *wts, const float *nf, cudaStream_t st) {
+    CUtensorMap mw, mn, mr, mt;
+    const uint64_t fdims[3] = {static_cast<uint64_t>(HW), static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
+    const uint32_t fbox[3] = {kCsSpan, static_cast<uint32_t>(D < kCsDC ? D : kCsDC), 1u};
+    const uint64_t cdims[3] = {static_cast<uint64_t>(HW), static_cast<uint64_t>(C), static_cast<uint64_t>(B)};
+    int cgt = 8;
+    while (cgt > 1 && C % cgt != 0) cgt /= 2;
+    if (cgt != 8 && cgt != 4) return DV_ERR_UNSUPPORTED;
+    const uint32_t lbox[3] = {kCsSpan, static_cast<uint32_t>(cgt), 1u};
+    const uint32_t rbox[3] = {kCsWin, static_cast<uint32_t>(cgt), 1u};
+    if (!make_tensor_map_f32(&mr, ref, 3, cdims, lbox) || !make_tensor_map_f32(&mt, tgt, 3, cdims, rbox))
+        return DV_ERR_UNSUPPORTED;
+    mw = mr;
+    mn = mr;
+    if (wts && !make_tensor_map_f32(&mw, wts, 3, fdims, fbox)) return DV_ERR_UNSUPPORTED;
+    if (nf && !make_tensor_map_f32(&mn, nf, 3, fdims, fbox)) return DV_ERR_UNSUPPORTED;
+#define DV_CSB(CG)                                                                                                          \
+    (wts && nf ? launch_cs2<CG, true, true, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st)        \
+     : wts     ? launch_cs2<CG, true, false, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st)       \
+     : nf      ? launch_cs2<CG, false, true, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st)       \
+               : launch_cs2<CG, false, false, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st))
+    return cgt == 8 ? DV_CSB(8) : DV_CSB(4);
+#undef DV_CSB
+}
+
 }  // namespace dv
+
+extern "C" int dv_concat_volume_weighted_bf16(const float *ref, const float *tgt, void *out, int64_t B, int64_t C, int64_t H,
+                                              int64_t W, int64_t D, int mask_left, const float *att_weights, const float *n,
+                                              void *stream) {
+    using namespace dv;
+    if (!ref || !tgt || !out) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || 2 * C > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    auto ok16 = [](const void *p) { return !p || aligned16(p); };
+    if (!((HW % 4 == 0) && W >= 4 && aligned16(ref) && aligned16(tgt) && (reinterpret_cast<uintptr_t>(out) & 7u) == 0 &&
+          ok16(att_weights) && ok16(n)))
+        return DV_ERR_MISALIGNED;
+    return launch_concat_stream_bf16(ref, tgt, static_cast<__nv_bfloat16 *>(out), static_cast<int>(B), static_cast<int>(C),
+                                     static_cast<int>(HW), static_cast<int>(W), static_cast<int>(D), mask_left, att_weights, n,
+                                     static_cast<cudaStream_t>(stream));
+}

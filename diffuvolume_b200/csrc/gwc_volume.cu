@@ -23,9 +23,9 @@
 
 namespace dv {
 
-template <int CPG, int DC, int SQ, int NCH, int MINB>
+template <int CPG, int DC, int SQ, int NCH, int MINB, typename OutT>
 __global__ void __launch_bounds__(SQ * NCH, MINB)
-gwc_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out,
+gwc_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, OutT *__restrict__ out,
                   int C, int HW, int W, int D, int G, int Dpad, int Dtot, int dofs, int tiles_per_cta) {
     // Dtot = planes per (b,g) in `out`, dofs = slot of shift 0 (plain gwc: Dtot = D, dofs = 0;
     // two-sided correlation volume: Dtot = 2m+1, dofs = m).
@@ -127,7 +127,7 @@ gwc_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, 
                         for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(l[i], rw[DC + i - j], acc[j][i]);
                 }
 
-                float *op = out + ((static_cast<int64_t>(b) * G + g) * Dtot + dofs + d0) * HW + p;
+                OutT *op = out + ((static_cast<int64_t>(b) * G + g) * Dtot + dofs + d0) * HW + p;
 #pragma unroll
                 for (int j = 0; j < DC; ++j) {
                     const int d = d0 + j;
@@ -137,7 +137,7 @@ gwc_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, 
                         v.y = xs[1] >= d ? acc[j][1] * inv : 0.0f;
                         v.z = xs[2] >= d ? acc[j][2] * inv : 0.0f;
                         v.w = xs[3] >= d ? acc[j][3] * inv : 0.0f;
-                        stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(j) * HW), v);
+                        store4_cs(op + static_cast<int64_t>(j) * HW, v);
                     }
                 }
             }
@@ -379,8 +379,8 @@ static int dispatch_gwc_kchunk(const float *ref, const float *tgt, float *out, i
     }
 }
 
-template <int CPG, int DC, int SQ, int NCH, int MINB>
-static int launch_gwc(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int G,
+template <int CPG, int DC, int SQ, int NCH, int MINB, typename OutT>
+static int launch_gwc(const float *ref, const float *tgt, OutT *out, int B, int C, int HW, int W, int D, int G,
                       int Dtot, int dofs, cudaStream_t st) {
     constexpr int SPAN = SQ * 4;
     const int Dpad = ((D + DC - 1) / DC) * DC;
@@ -391,7 +391,7 @@ static int launch_gwc(const float *ref, const float *tgt, float *out, int B, int
     const int stages = tpc > 1 ? 2 : 1;
     const size_t smem = sizeof(float) * stages * (static_cast<size_t>(CPG) * SPAN + static_cast<size_t>(CPG) * (SPAN + Dpad));
     if (smem > 200 * 1024) return DV_ERR_UNSUPPORTED;
-    auto kern = gwc_volume_kernel<CPG, DC, SQ, NCH, MINB>;
+    auto kern = gwc_volume_kernel<CPG, DC, SQ, NCH, MINB, OutT>;
     if (smem > 48 * 1024) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
             return DV_ERR_LAUNCH;
@@ -401,18 +401,18 @@ static int launch_gwc(const float *ref, const float *tgt, float *out, int B, int
     return finish_launch();
 }
 
-template <int CPG>
-static int dispatch_gwc(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int G,
+template <int CPG, typename OutT>
+static int dispatch_gwc(const float *ref, const float *tgt, OutT *out, int B, int C, int HW, int W, int D, int G,
                         int Dtot, int dofs, cudaStream_t st) {
     constexpr int DC = 12, SQ = 64;
     const int nch = (D + DC - 1) / DC;
     if (nch >= 4) {
         if (tune_variant("DV_GWC_MINB", 2) == 2)
-            return launch_gwc<CPG, DC, SQ, 4, 2>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
-        return launch_gwc<CPG, DC, SQ, 4, 3>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+            return launch_gwc<CPG, DC, SQ, 4, 2, OutT>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+        return launch_gwc<CPG, DC, SQ, 4, 3, OutT>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
     }
-    if (nch >= 2) return launch_gwc<CPG, DC, SQ, 2, 4>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
-    return launch_gwc<CPG, DC, SQ, 1, 8>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+    if (nch >= 2) return launch_gwc<CPG, DC, SQ, 2, 4, OutT>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
+    return launch_gwc<CPG, DC, SQ, 1, 8, OutT>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
 }
 
 static int gwc_volume_impl(const float *ref, const float *tgt, float *out, int64_t B, int64_t C, int64_t H, int64_t W,
@@ -430,11 +430,11 @@ static int gwc_volume_impl(const float *ref, const float *tgt, float *out, int64
             rc = dispatch_gwc_kchunk(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
         if (rc != DV_ERR_UNSUPPORTED) return rc;
         switch (cpg) {
-            case 4: rc = dispatch_gwc<4>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
-            case 8: rc = dispatch_gwc<8>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
-            case 12: rc = dispatch_gwc<12>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
-            case 16: rc = dispatch_gwc<16>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
-            case 32: rc = dispatch_gwc<32>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            case 4: rc = dispatch_gwc<4, float>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            case 8: rc = dispatch_gwc<8, float>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            case 12: rc = dispatch_gwc<12, float>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            case 16: rc = dispatch_gwc<16, float>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
+            case 32: rc = dispatch_gwc<32, float>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st); break;
             default: break;
         }
         if (rc != DV_ERR_UNSUPPORTED) return rc;
@@ -449,7 +449,31 @@ static int gwc_volume_impl(const float *ref, const float *tgt, float *out, int64
     return finish_launch();
 }
 
+// bf16 volume (fp32 features in, fp32 accumulate, one rounding at the store): the 128-bit-path shapes only
+static int gwc_volume_bf16_impl(const float *ref, const float *tgt, __nv_bfloat16 *out, int64_t B, int64_t C, int64_t H,
+                                int64_t W, int64_t D, int64_t G, cudaStream_t st) {
+    if (!ref || !tgt || !out) return DV_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0 || G <= 0 || C % G != 0) return DV_ERR_BAD_SHAPE;
+    const int64_t HW = H * W;
+    if (HW > INT32_MAX || B > 65535 || G > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    if (!((HW % 4 == 0) && aligned16(ref) && aligned16(tgt) && (reinterpret_cast<uintptr_t>(out) & 7u) == 0)) return DV_ERR_MISALIGNED;
+    if (!(HW >= 64 && D <= 512 && W >= 4)) return DV_ERR_UNSUPPORTED;
+    const int Bi = static_cast<int>(B), Ci = static_cast<int>(C), HWi = static_cast<int>(HW), Wi = static_cast<int>(W),
+              Di = static_cast<int>(D), Gi = static_cast<int>(G);
+    switch (C / G) {
+        case 8: return dispatch_gwc<8, __nv_bfloat16>(ref, tgt, out, Bi, Ci, HWi, Wi, Di, Gi, Di, 0, st);
+        case 12: return dispatch_gwc<12, __nv_bfloat16>(ref, tgt, out, Bi, Ci, HWi, Wi, Di, Gi, Di, 0, st);
+        default: return DV_ERR_UNSUPPORTED;   // reference configurations: cpg = 8 (ACVNet, PCWNet), 12 (IGEV)
+    }
+}
+
 }  // namespace dv
+
+extern "C" int dv_gwc_volume_bf16(const float *ref, const float *tgt, void *out, int64_t B, int64_t C, int64_t H, int64_t W,
+                                  int64_t D, int64_t G, void *stream) {
+    return dv::gwc_volume_bf16_impl(ref, tgt, static_cast<__nv_bfloat16 *>(out), B, C, H, W, D, G,
+                                    static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int dv_gwc_volume_f32(const float *ref, const float *tgt, float *out, int64_t B, int64_t C, int64_t H,
                                  int64_t W, int64_t D, int64_t G, void *stream) {

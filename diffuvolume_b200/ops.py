@@ -80,19 +80,28 @@ def groupwise_correlation(fea1: torch.Tensor, fea2: torch.Tensor, num_groups: in
 
 
 def gwc_volume(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, num_groups: int,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """a2 — build_gwc_volume, SceneFlow/models/submodule.py:228-238 -> [B,G,maxdisp,H,W]."""
+               out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """a2 — build_gwc_volume, SceneFlow/models/submodule.py:228-238 -> [B,G,maxdisp,H,W].
+    out_dtype=torch.bfloat16: fp32 features and accumulation, one round-to-nearest-even at the store (half the write
+    traffic; 8 or 12 channels per group, H*W % 4 == 0)."""
     B, Cc, H, W = ref.shape
     assert Cc % num_groups == 0
     _need_cuda(ref, tgt)
     ref, tgt = _f32c(ref, "refimg_fea"), _f32c(tgt, "targetimg_fea")
     if tgt.shape != ref.shape:
         raise RuntimeError(f"The size of tensor a {tuple(ref.shape)} must match the size of tensor b {tuple(tgt.shape)}")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise DvLibraryError(f"gwc_volume: out_dtype must be float32 or bfloat16, got {out_dtype}")
     if out is None:
-        out = torch.empty((B, num_groups, maxdisp, H, W), dtype=torch.float32, device=ref.device)
+        out = torch.empty((B, num_groups, maxdisp, H, W), dtype=out_dtype, device=ref.device)
     else:
-        assert out.shape == (B, num_groups, maxdisp, H, W) and out.dtype == torch.float32 and out.is_contiguous()
+        assert out.shape == (B, num_groups, maxdisp, H, W) and out.dtype == out_dtype and out.is_contiguous()
     if out.numel() == 0:
+        return out
+    if out_dtype == torch.bfloat16:
+        with torch.cuda.device(ref.device):
+            check(_lib.lib().dv_gwc_volume_bf16(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp, num_groups,
+                                                _stream(ref)), "dv_gwc_volume_bf16")
         return out
     with torch.cuda.device(ref.device):
         check(_lib.lib().dv_gwc_volume_f32(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp, num_groups,
@@ -196,7 +205,7 @@ def filter_factor_pair(xt: torch.Tensor, shift: Optional[torch.Tensor] = None, s
 
 def concat_volume_weighted(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, *, mask_left: bool,
                            att_weights: Optional[torch.Tensor] = None, n: Optional[torch.Tensor] = None,
-                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                           out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """a3 (+a4 +a9) with PRECOMPUTED fp32 factor maps (`att_softmax`, `filter_factor` / ddim_step's n_next):
     out = (concat * att_weights) * n — the same values as `concat_volume(att_logits=..., xt=...)`.
     Needs H*W % 4 == 0 (every reference shape); raises DvLibraryError(DV_ERR_MISALIGNED) otherwise."""
@@ -208,11 +217,20 @@ def concat_volume_weighted(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, *
     for name, t in (("att_weights", att_weights), ("n", n)):
         if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != B * maxdisp * H * W):
             raise RuntimeError(f"{name} must be a contiguous float32 [B,{maxdisp},{H},{W}] map")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise DvLibraryError(f"concat_volume_weighted: out_dtype must be float32 or bfloat16, got {out_dtype}")
     if out is None:
-        out = torch.empty((B, 2 * Cc, maxdisp, H, W), dtype=torch.float32, device=ref.device)
+        out = torch.empty((B, 2 * Cc, maxdisp, H, W), dtype=out_dtype, device=ref.device)
     else:
-        assert out.shape == (B, 2 * Cc, maxdisp, H, W) and out.dtype == torch.float32 and out.is_contiguous()
+        assert out.shape == (B, 2 * Cc, maxdisp, H, W) and out.dtype == out_dtype and out.is_contiguous()
     if out.numel() == 0:
+        return out
+    if out_dtype == torch.bfloat16:
+        # fp32 operands and products, one round-to-nearest-even at the store (half the write traffic of the filter pass)
+        with torch.cuda.device(ref.device):
+            check(_lib.lib().dv_concat_volume_weighted_bf16(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp,
+                                                            int(mask_left), _ptr(att_weights), _ptr(n), _stream(ref)),
+                  "dv_concat_volume_weighted_bf16")
         return out
     with torch.cuda.device(ref.device):
         check(_lib.lib().dv_concat_volume_weighted_f32(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp,

@@ -301,6 +301,18 @@ int dv_depthwise3x3_chain_f32(const float *in, const float *w1, const float *w2,
                               int64_t B, int64_t C, int64_t D, int64_t H, int64_t W, int64_t c0, int64_t c1,
                               int dil1, int dil2, void *stream);
 
+/* ---- bf16 volumes (north_star: "volume writes ... bf16/fp32"): the two volume PRODUCERS with a bfloat16 output.
+ * Features, factor maps, products and accumulation stay fp32; the result is rounded to nearest-even once, at the store
+ * (identical to the fp32 entry point followed by torch's .to(torch.bfloat16)), so the volume-sized write — the
+ * dominant traffic of a2 / a3+a4 / a9 — is halved.  Stated tolerance: 2^-8 relative per element.  `out` is
+ * [B,G,D,H,W] / [B,2C,D,H,W] bfloat16, 8-byte aligned; H*W % 4 == 0; gwc: 8 or 12 channels per group (every reference
+ * configuration); else DV_ERR_UNSUPPORTED / DV_ERR_MISALIGNED.                                                          */
+int dv_gwc_volume_bf16(const float *ref, const float *tgt, void *out,
+                       int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int64_t G, void *stream);
+int dv_concat_volume_weighted_bf16(const float *ref, const float *tgt, void *out,
+                                   int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int mask_left,
+                                   const float *att_weights, const float *n, void *stream);
+
 /* ---- f1: backward passes of the volume ops — the reference's training scripts differentiate through them
  *          (SceneFlow/main.py:154 -> models/acv_ddim.py:424-482; KITTI12/main.py; KITTI15/train_stereo.py).
  * Gradients of the functions above with respect to their feature inputs; grad_out has the forward output's shape.

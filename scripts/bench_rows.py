@@ -93,6 +93,9 @@ def main():
         fl, fr = rn(B, C, h, w), rn(B, C, h, w)
         R.time("a2 gwc_volume", f"acv B={B} C=320 G=40 D=48 135x240", lambda: ops.gwc_volume(fl, fr, D, G),
                B * (2 * C * hw + G * D * hw) * F4, flops=2.0 * B * C * D * hw)
+        R.time("a2 gwc_volume -> bf16 volume", f"acv B={B} C=320 G=40 D=48 135x240",
+               lambda: ops.gwc_volume(fl, fr, D, G, out_dtype=torch.bfloat16), B * (2 * C * hw * F4 + G * D * hw * 2),
+               note="bytes = fp32 features in + bf16 volume out")
         R.time("a1 groupwise_correlation", f"acv B={B} C=320 G=40 135x240", lambda: ops.groupwise_correlation(fl, fr, G),
                B * (2 * C * hw + G * hw) * F4)
         gv = rn(B, G, D, h, w)
@@ -105,6 +108,14 @@ def main():
         att = rn(B, 1, D, h, w)
         R.time("a3+a4 concat+ACV", f"acv B={B}", lambda: ops.concat_volume(cl, cr, D, mask_left=False, att_logits=att),
                B * (2 * Cc * hw + D * hw + 2 * Cc * D * hw) * F4)
+        attw, nf = ops.att_softmax(att), ru(B, D, h, w)
+        R.time("a9 filter, regenerate mode (features + 2 factor maps -> volume)", f"acv B={B}",
+               lambda: ops.concat_volume_weighted(cl, cr, D, mask_left=False, att_weights=attw, n=nf),
+               B * (2 * Cc * hw + 2 * D * hw + 2 * Cc * D * hw) * F4)
+        R.time("a9 filter, regenerate mode -> bf16 volume", f"acv B={B}",
+               lambda: ops.concat_volume_weighted(cl, cr, D, mask_left=False, att_weights=attw, n=nf, out_dtype=torch.bfloat16),
+               B * ((2 * Cc * hw + 2 * D * hw) * F4 + 2 * Cc * D * hw * 2), note="bytes = fp32 inputs + bf16 volume out")
+        del attw, nf
         gvol = rn(B, 2 * Cc, D, h, w)
         R.time("f1 concat_volume_bwd", f"acv B={B}", lambda: ops.concat_volume_bwd(gvol, False),
                B * (2 * Cc * D * hw + 2 * Cc * hw) * F4)

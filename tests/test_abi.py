@@ -49,7 +49,17 @@ def test_library_is_sm100a_and_uses_the_tma_engine(lib):
     assert "sm_100a" in sass
     assert "UBLKCP" in sass          # cp.async.bulk (TMA engine) in the gwc kernel
     assert "SYNCS" in sass           # mbarrier
-    assert "HMMA" not in sass        # no legacy tensor-core path anywhere
+    assert "UTMALDG" in sass         # tensor-map TMA loads (streaming producers)
+    # tensor cores appear in exactly one kernel: the compute-bound all-pairs correlation (a14, 3xTF32 mma.sync);
+    # every HBM-bound volume kernel stays on plain FFMA
+    fn = None
+    owners = set()
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif "HMMA" in line:
+            owners.add(fn)
+    assert owners and all("corr1d_allpairs_mma" in o for o in owners), owners
 
 
 def test_argument_validation_without_a_gpu(lib):

@@ -487,6 +487,46 @@ def test_kitti15_geo_class_matches_oracle(ops):
     assert rel_max_err(host(fn.geo_volume_pyramid[1]), vol.geo_volume_pyramid[1].reshape(B * h * w, Cg, 1, D // 2)) < 1e-6
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 8, 48, 27, 240), (1, 96, 8, 48, 12, 312), (1, 320, 40, 24, 48, 156)])
+def test_gwc_volume_bf16_is_the_rounded_fp32_volume(ops, shape):
+    """bf16 output = the fp32 kernel's result rounded to nearest-even once (bit-exact), hence within 2^-8 relative of
+    the oracle per element; the zero region stays exactly zero."""
+    B, C, G, D, H, W = shape
+    ref, tgt = synth.normal((B, C, H, W), 401), synth.normal((B, C, H, W), 402)
+    f32 = ops.gwc_volume(cu(ref), cu(tgt), D, G)
+    b16 = ops.gwc_volume(cu(ref), cu(tgt), D, G, out_dtype=torch.bfloat16)
+    assert b16.dtype == torch.bfloat16 and b16.shape == f32.shape
+    assert torch.equal(b16, f32.to(torch.bfloat16))
+    want = O.build_gwc_volume(ref, tgt, D, G)
+    got = b16.float().cpu().numpy()
+    # stated bf16 tolerance: 2^-8 relative per element (+ the fp32 kernel's own 1e-6 * max floor near zero crossings)
+    assert np.all(np.abs(got - want) <= 2.0 ** -8 * np.abs(want) + 1e-6 * np.abs(want).max())
+    for d in range(1, min(D, W)):
+        assert not got[:, :, d, :, :d].any()
+
+
+@pytest.mark.parametrize("mask_left", [False, True])
+@pytest.mark.parametrize("shape", [(2, 32, 48, 27, 240), (1, 12, 24, 48, 156)])
+def test_weighted_producer_bf16_is_the_rounded_fp32_volume(ops, shape, mask_left):
+    B, C, D, H, W = shape
+    ref, tgt = synth.normal((B, C, H, W), 411), synth.normal((B, C, H, W), 412)
+    att = ops.att_softmax(cu(synth.normal((B, 1, D, H, W), 413)))
+    n = ops.filter_factor(cu(synth.normal((B, D, H, W), 414, dtype=np.float64)), None, 1.0)
+    for aw, nn in ((None, None), (att, None), (att, n)):
+        f32 = ops.concat_volume_weighted(cu(ref), cu(tgt), D, mask_left=mask_left, att_weights=aw, n=nn)
+        b16 = ops.concat_volume_weighted(cu(ref), cu(tgt), D, mask_left=mask_left, att_weights=aw, n=nn,
+                                         out_dtype=torch.bfloat16)
+        assert b16.dtype == torch.bfloat16 and torch.equal(b16, f32.to(torch.bfloat16))
+
+
+def test_bf16_volumes_reject_unsupported_layouts(ops):
+    ref = cu(synth.normal((1, 16, 6, 20), 421))          # 4 channels per group: not a reference configuration
+    with pytest.raises(Exception):
+        ops.gwc_volume(ref, ref, 6, 4, out_dtype=torch.bfloat16)
+    with pytest.raises(Exception):
+        ops.gwc_volume(ref, ref, 6, 2, out_dtype=torch.float16)
+
+
 # ------------------------------------------------------------------------------------------------
 # loud failure on CPU tensors (no fallback)
 # ------------------------------------------------------------------------------------------------
