@@ -269,6 +269,43 @@ def run_ours(args):
             "kernels": kernels,
             "checksum": checksum,
         }
+    # ---- the same step replayed from a CUDA graph (no per-kernel events possible inside a graph, hence a separate
+    # leg): at B = 8 the step is bandwidth-bound and the two agree; at B = 1 — the reference's own evaluation batch —
+    # issuing 21 launches from Python takes longer than executing them
+    graph_leg = None
+    if not args.no_graph:
+        graph_leg = {}
+        for gb in sorted({1, B}):
+            ginp = inp if gb == B else make_inputs(gb, dev, seed=4321 + rank, regress=args.regress)
+            gpath = path if gb == B else AcvHotPath(filter_mode=args.filter, regress_mode=regress)
+            # eager first: capturing moves the allocator's cached blocks into the graph's private pool, and the eager
+            # calls that follow would pay fresh cudaMallocs
+            for _ in range(args.warmup):
+                gpath(**ginp)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                gpath(**ginp)
+            e1.record()
+            barrier()
+            ems = e0.elapsed_time(e1) / args.steps
+            replay, _ = gpath.graphed(**ginp)
+            for _ in range(args.warmup):
+                replay()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                replay()
+            g1.record()
+            barrier()
+            gms = g0.elapsed_time(g1) / args.steps
+            graph_leg[f"batch_{gb}"] = {"graph_ms_per_step": round(gms, 4), "eager_ms_per_step": round(ems, 4),
+                                        "graph_pairs_per_s": round(gb / (gms / 1e3), 1),
+                                        "eager_pairs_per_s": round(gb / (ems / 1e3), 1)}
+            del replay
+        graph_leg["note"] = "rank 0's GPU, AcvHotPath.graphed(): one captured launch sequence per step"
     # ---- e2e: the same step through the public API with HOST buffers ------------------------
     e2e = None if args.no_e2e else run_e2e(args, path, inp, dev, barrier, dist, world)
     # ---- SURVEY.md §8f row f2, reported beside the headline: the same step with F.upsample(trilinear) fused into the
@@ -300,6 +337,8 @@ def run_ours(args):
                          "per-step input [B,1,48,135,240] instead of [B,192,540,960]"}
     if rank == 0:
         result["e2e"] = e2e
+        if graph_leg is not None:
+            result["cuda_graph"] = graph_leg
         if fused is not None:
             result["fused_upsample"] = fused
         if world == 1 and not args.no_cpu_baseline:
@@ -459,6 +498,7 @@ def main():
                          "fused: trilinear x4 upsample fused in, input [B,1,48,h,w] (SURVEY.md 8f row f2)")
     ap.add_argument("--no-fused", action="store_true", help="skip the extra fused-upsample measurement")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay leg")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")

@@ -194,6 +194,28 @@ class AcvHotPath:
             out.update(gwc=gwc, ac=ac, vol_f=vol_f)
         return out
 
+    def graphed(self, **inputs):
+        """Capture one call into a CUDA graph (B200 rule: launch-bound loops are replayed, not re-issued).  At batch 1
+        — the reference's own evaluation batch (SceneFlow/test_sceneflow_ddim.py:48) — the 21 launches of a pair take
+        longer to issue from Python than to execute.  Returns (replay, outputs): `replay()` re-runs the captured
+        sequence on the current stream reading the SAME input tensors (update them in place), `outputs` are the
+        tensors every replay overwrites.  The C-ABI is capture-safe: no allocation, no synchronisation, the tile
+        counters of the persistent kernels re-arm themselves on the device.  (A captured launch keeps its counter
+        slot, so replays must not overlap launches of the same kernels on other streams.)"""
+        if callable(inputs.get("costs")):
+            raise ValueError("graphed() needs device-resident cost tensors, not a staging callback")
+        dev = inputs["feat_l"].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):          # warm-up outside the capture: output buffers, function attributes
+                self(**inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self(**inputs)
+        return graph.replay, out
+
     def launches_per_call(self) -> int:
         T = self.sched.sampling_timesteps
         return (6 if self.filter_mode == "regenerate" else 4) + 3 * T

@@ -528,6 +528,47 @@ def test_bf16_volumes_reject_unsupported_layouts(ops):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: size-independent properties (the oracle cannot run these in seconds)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_batch_independence_and_linearity(ops):
+    """configs[1] at B = 8 (gwc C=320 G=40 D=48 @135x240, concat/ACV/filter C=32, softmax-regress over [B,192,540,960]):
+    every op is per-sample, so sample b of the batched launch must be bit-identical to a B = 1 launch of that sample
+    (different grids, tile schedules and batch strides), and the linear ops must scale exactly by powers of two."""
+    g = torch.Generator(device="cuda"); g.manual_seed(77)
+    B, h, w, D = 8, 135, 240, 48
+    rn = lambda *sh: torch.randn(*sh, generator=g, device="cuda")
+    fl, fr = rn(B, 320, h, w), rn(B, 320, h, w)
+    vol = ops.gwc_volume(fl, fr, D, 40)
+    for b in (0, 5, 7):
+        assert torch.equal(vol[b:b + 1], ops.gwc_volume(fl[b:b + 1].contiguous(), fr[b:b + 1].contiguous(), D, 40))
+    assert torch.equal(ops.gwc_volume(fl * 2, fr * 4, D, 40), vol * 8)          # bilinear, exact in binary fp
+    for d in (1, 17, 47):
+        assert not vol[:, :, d, :, :d].any()                                    # the zero region is exact zeros
+    del vol
+    cl, cr, att = rn(B, 32, h, w), rn(B, 32, h, w), rn(B, 1, D, h, w)
+    xt = torch.randn(B, D, h, w, generator=g, device="cuda", dtype=torch.float64)
+    aw, n = ops.att_softmax(att), ops.filter_factor(xt, None, 1.0)
+    filt = ops.concat_volume_weighted(cl, cr, D, mask_left=False, att_weights=aw, n=n)
+    for b in (0, 3, 7):
+        one = ops.concat_volume_weighted(cl[b:b + 1].contiguous(), cr[b:b + 1].contiguous(), D, mask_left=False,
+                                         att_weights=aw[b:b + 1].contiguous(), n=n[b:b + 1].contiguous())
+        assert torch.equal(filt[b:b + 1], one)
+    # the regenerated filtered volume == filter multiply applied to the materialised ACV volume (same rounding order)
+    ac = ops.concat_volume(cl, cr, D, mask_left=False, att_logits=att)
+    assert torch.equal(ops.volume_filter(ac, xt, None), filt)
+    del ac, filt
+    cost = rn(B, 192, 540, 960) * 4.0
+    r = ops.softmax_regress(cost, want_unc=True)
+    for b in (0, 6):
+        rb = ops.softmax_regress(cost[b:b + 1].contiguous(), want_unc=True)
+        assert torch.equal(r["disp"][b:b + 1], rb["disp"]) and torch.equal(r["unc"][b:b + 1], rb["unc"])
+    assert float(r["disp"].min()) >= 0.0 and float(r["disp"].max()) <= 191.0     # an expectation over d in [0, 191]
+    # softmax is shift-invariant: adding a per-pixel constant changes nothing beyond rounding
+    r2 = ops.softmax_regress(cost + rn(B, 1, 540, 960))
+    assert float((r2["disp"] - r["disp"]).abs().max()) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
 # loud failure on CPU tensors (no fallback)
 # ------------------------------------------------------------------------------------------------
 # ------------------------------------------------------------------------------------------------

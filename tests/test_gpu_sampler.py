@@ -139,3 +139,40 @@ def test_uncertainty_vote_matches_oracle():
     want = O.renewal_vote(refined, used, unc_o, 1.0, thr)
     near = (np.abs(np.abs(refined - used) - 1.0) < 1e-3) | (np.abs(unc_o - thr) < 1e-3)
     assert np.array_equal(vote.cpu().numpy()[~near], want[~near])
+
+
+@pytest.mark.gpu
+def test_hot_path_cuda_graph_replay_matches_eager():
+    """The whole ACV hot path captured in a CUDA graph: replays are bit-identical to eager calls, also after the
+    inputs were updated in place, and issue no new launches from the host."""
+    import torch
+    from diffuvolume_b200 import _lib
+    from diffuvolume_b200.pipeline import AcvHotPath
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    B, H, W, D = 2, 64, 128, 48
+    h, w = H // 4, W // 4
+    rn = lambda *s, dt=torch.float32: torch.randn(*s, generator=g, device=dev, dtype=dt)
+    ru = lambda *s, dt=torch.float32: torch.rand(*s, generator=g, device=dev, dtype=dt)
+    inp = dict(feat_l=rn(B, 64, h, w), feat_r=rn(B, 64, h, w), cfeat_l=rn(B, 8, h, w), cfeat_r=rn(B, 8, h, w),
+               att_logits=rn(B, 1, D, h, w), costs=[rn(B, 192, H, W) * 4.0], used=ru(B, H, W) * 191.0,
+               disp_q=ru(B, h, w) * 47.75, shifts=[rn(B, D) * 0.1 for _ in range(5)],
+               step_noises=[rn(B, D, h, w, dt=torch.float32 if i == 0 else torch.float64) for i in range(4)],
+               renoises=[ru(B, D, h, w, dt=torch.float64) for _ in range(4)])
+    path = AcvHotPath(num_groups=8)
+    want = {k: v.clone() for k, v in path(**inp).items()}
+    replay, out = path.graphed(**inp)
+    n0 = _lib.launch_count()
+    replay()
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == n0                       # nothing was issued through the C-ABI: the graph ran
+    for k in want:
+        assert torch.equal(out[k], want[k]), k
+    inp["feat_l"].mul_(0.5); inp["used"].add_(1.0); inp["costs"][0].mul_(-1.0)
+    replay()
+    torch.cuda.synchronize()
+    got = {k: v.clone() for k, v in out.items()}
+    want2 = path(**inp)
+    for k in want2:
+        assert torch.equal(got[k], want2[k]), k
+    assert not torch.equal(got["pred"], want["pred"])
