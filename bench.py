@@ -39,6 +39,27 @@ METRIC = "volume+DDIM-filter pairs/s @540x960 D=192"
 H, W, MAXDISP, C_GWC, G, C_CAT, T_STEPS = 540, 960, 192, 320, 40, 32, 5
 
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version on communicator creation),
+# so fd 1 is pointed at stderr for the whole run and the result line is written to the saved original stdout.
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def measured_peak_gbs():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -343,7 +364,7 @@ def run_ours(args):
             result["fused_upsample"] = fused
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_reference(steps=args.cpu_steps, warmup=1, regress=args.regress)
-        print(json.dumps(result))
+        emit(result)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -474,7 +495,7 @@ def run_reference(args):
         return
     cb = cpu_reference(steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)), regress=args.regress)
     v = cb["value"]
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 / v, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -482,7 +503,7 @@ def run_reference(args):
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def main():
@@ -503,6 +524,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
+    protect_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
