@@ -127,6 +127,131 @@ __device__ __forceinline__ void stencil_quad(const float *__restrict__ row0, int
     }
 }
 
+// Row-blocked variant for compile-time dilations: a thread owns R vertically adjacent quads.  It walks the R + 2*DIL
+// source rows once (3 LDS.128 each) and every source row feeds the up to three output rows it is a tap row of, so the
+// shared-memory traffic per output quad drops from 9 LDS.128 to 3 (R + 2 DIL) / R (4.5 at DIL = 1, R = 4) and the index
+// arithmetic is amortised over R quads — the runtime-dilation kernel below is issue-bound at 171 instructions per quad.
+template <int DIL, int R>
+__device__ __forceinline__ void stencil_rows(const float *__restrict__ row0, int pitch, const float (&k)[9], float (&acc)[R][4]) {
+    // row0: column m of source row (first output row - DIL); outputs sit at columns m+4 .. m+7
+#pragma unroll
+    for (int sr = 0; sr < R + 2 * DIL; ++sr) {
+        const float *r = row0 + sr * pitch;
+        const float4 a = *reinterpret_cast<const float4 *>(r), b = *reinterpret_cast<const float4 *>(r + 4),
+                     c = *reinterpret_cast<const float4 *>(r + 8);
+        const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int orow = sr - ky * DIL;          // source row sr is tap row ky of output row sr - ky*DIL
+            if (orow < 0 || orow >= R) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[orow][i] = fmaf(k[ky * 3 + kx], v[4 + i + (kx - 1) * DIL], acc[orow][i]);
+        }
+    }
+}
+
+template <bool CHAIN, int D1, int D2>
+__global__ void __launch_bounds__(256)
+depthwise_chain_rows_kernel(const float *__restrict__ in, const float *__restrict__ w1, const float *__restrict__ w2,
+                            float *__restrict__ out, int C, int D, int H, int W, int c0, int th, int tw, int tiles_x) {
+    constexpr int R = 4;
+    extern __shared__ __align__(16) float sm[];
+    constexpr int r2 = CHAIN ? D2 : 0;
+    // tile heights are rounded up to whole row blocks in shared memory so that no thread reads outside its tile
+    const int out_rb = (th + R - 1) / R, mid_rb = (th + 2 * r2 + R - 1) / R;
+    // (the last output row block may look 2*D2 rows past the last whole mid row block: rows that only feed unstored outputs)
+    const int mh = CHAIN ? max(mid_rb * R, out_rb * R + 2 * r2) : 0, mpitch = tw + 8;
+    const int ih = (CHAIN ? mh : out_rb * R) + 2 * D1, ipitch = tw + (CHAIN ? 16 : 8);
+    float *s_in = sm, *s_mid = sm + ih * ipitch;
+    const int tile = blockIdx.x, ty0 = (tile / tiles_x) * th, tx0 = (tile % tiles_x) * tw;
+    const int cd = blockIdx.y;
+    const int c = c0 + cd / D, d = cd % D, b = blockIdx.z;
+    const int64_t plane = ((static_cast<int64_t>(b) * C + c) * D + d) * H * W;
+    const float *ip = in + plane;
+    float k1[9], k2[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        k1[i] = __ldg(w1 + c * 9 + i);
+        k2[i] = CHAIN ? __ldg(w2 + c * 9 + i) : 0.0f;
+    }
+    {
+        const int qpr = ipitch / 4, xl = tx0 - (CHAIN ? 8 : 4), yt = ty0 - D1 - r2;
+        for (int e = threadIdx.x; e < ih * qpr; e += 256) {
+            const int yy = e / qpr, qx = e - yy * qpr;
+            const int y = yt + yy, x = xl + 4 * qx;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const float4 *>(ip + static_cast<int64_t>(y) * W + x));
+            *reinterpret_cast<float4 *>(s_in + e * 4) = v;
+        }
+    }
+    __syncthreads();
+    if (CHAIN) {
+        const int qpr = mpitch / 4;
+        for (int e = threadIdx.x; e < mid_rb * qpr; e += 256) {
+            const int rb = e / qpr, qx = e - rb * qpr;
+            const int x = tx0 - 4 + 4 * qx;
+            float acc[R][4];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r][i] = 0.0f;
+            // mid row rb*R + r  <->  input-tile row rb*R + r + D1 (centre); source rows start D1 above the first centre
+            stencil_rows<D1, R>(s_in + (rb * R) * ipitch + 4 * qx, ipitch, k1, acc);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int y = ty0 - r2 + rb * R + r;
+                const bool inside = y >= 0 && y < H && x >= 0 && x < W;   // the intermediate is ZERO outside the image
+                *reinterpret_cast<float4 *>(s_mid + (rb * R + r) * mpitch + 4 * qx) =
+                    inside ? make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        __syncthreads();
+    }
+    float *op = out + plane;
+    const int qpr = tw / 4;
+    for (int e = threadIdx.x; e < out_rb * qpr; e += 256) {
+        const int rb = e / qpr, qx = e - rb * qpr;
+        const int x = tx0 + 4 * qx;
+        if (x >= W) continue;
+        float acc[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[r][i] = 0.0f;
+        if (CHAIN) stencil_rows<(CHAIN ? D2 : 1), R>(s_mid + (rb * R) * mpitch + 4 * qx, mpitch, k2, acc);
+        else stencil_rows<D1, R>(s_in + (rb * R) * ipitch + 4 * qx, ipitch, k1, acc);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int yy = rb * R + r, y = ty0 + yy;
+            if (yy < th && y < H)
+                *reinterpret_cast<float4 *>(op + static_cast<int64_t>(y) * W + x) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        }
+    }
+}
+
+template <bool CHAIN, int D1, int D2>
+static int launch_rows(const float *in, const float *w1, const float *w2, float *out, int B, int C, int D, int H, int W, int c0,
+                       int c1, cudaStream_t st) {
+    constexpr int R = 4, r2 = CHAIN ? D2 : 0;
+    const int tiles_y = (H + 31) / 32, tiles_x = (W + 127) / 128;
+    const int th = (H + tiles_y - 1) / tiles_y;
+    const int tw = (((W + tiles_x - 1) / tiles_x) + 3) / 4 * 4;
+    const int tiles_x2 = (W + tw - 1) / tw;
+    const int out_rb = (th + R - 1) / R, mid_rb = (th + 2 * r2 + R - 1) / R;
+    const int mh = CHAIN ? (mid_rb * R > out_rb * R + 2 * r2 ? mid_rb * R : out_rb * R + 2 * r2) : 0;
+    const int ih = (CHAIN ? mh : out_rb * R) + 2 * D1;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(ih) * (tw + (CHAIN ? 16 : 8)) + static_cast<size_t>(mh) * (tw + 8));
+    auto kern = depthwise_chain_rows_kernel<CHAIN, D1, D2>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return DV_ERR_LAUNCH;
+    dim3 grid(static_cast<unsigned>(tiles_y * tiles_x2), static_cast<unsigned>((c1 - c0) * D), static_cast<unsigned>(B));
+    kern<<<grid, 256, smem, st>>>(in, w1, w2, out, C, D, H, W, c0, th, tw, tiles_x2);
+    return finish_launch();
+}
+
 template <bool CHAIN>
 __global__ void __launch_bounds__(256)
 depthwise_chain_quad_kernel(const float *__restrict__ in, const float *__restrict__ w1, const float *__restrict__ w2,
@@ -196,6 +321,17 @@ extern "C" int dv_depthwise3x3_chain_f32(const float *in, const float *w1, const
     if (B > 65535 || (c1 - c0) * D > 65535 || H * W > INT32_MAX) return DV_ERR_BAD_SHAPE;
     if (in == out) return DV_ERR_UNSUPPORTED;  // tiles read their neighbours' inputs
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (W % 4 == 0 && aligned16(in) && aligned16(out) && tune_variant("DV_PATCH_ROWS", 1)) {
+        // compile-time dilations (everything ACVNet uses): the row-blocked kernel
+        const int Bi = static_cast<int>(B), Ci = static_cast<int>(C), Di = static_cast<int>(D), Hi = static_cast<int>(H),
+                  Wi = static_cast<int>(W), a = static_cast<int>(c0), z = static_cast<int>(c1);
+        if (w2 && dil1 == 1 && dil2 == 1) return launch_rows<true, 1, 1>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
+        if (w2 && dil1 == 1 && dil2 == 2) return launch_rows<true, 1, 2>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
+        if (w2 && dil1 == 1 && dil2 == 3) return launch_rows<true, 1, 3>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
+        if (!w2 && dil1 == 1) return launch_rows<false, 1, 1>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
+        if (!w2 && dil1 == 2) return launch_rows<false, 2, 1>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
+        if (!w2 && dil1 == 3) return launch_rows<false, 3, 1>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
+    }
     if (W % 4 == 0 && aligned16(in) && aligned16(out) && dil1 <= 4 && (!w2 || dil2 <= 4) && tune_variant("DV_PATCH_QUAD", 1)) {
         // tiles: up to 32 rows x 128 columns, balanced to the plane, widths in quads
         const int tiles_y = static_cast<int>((H + 31) / 32), tiles_x = static_cast<int>((W + 127) / 128);
