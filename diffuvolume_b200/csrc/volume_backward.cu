@@ -95,7 +95,7 @@ template <int CK, int SQ>
 __global__ void __launch_bounds__(2 * SQ)
 gwc_bwd_quad_kernel(const float *__restrict__ go, const float *__restrict__ ref, const float *__restrict__ tgt,
                     float *__restrict__ gref, float *__restrict__ gtgt, int C, int HW, int W, int D, int G, int cpg, int Dpad,
-                    int64_t go_elems) {
+                    int Dtot, int dofs, int64_t go_elems) {
     constexpr int SPAN = SQ * 4;
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -156,8 +156,9 @@ gwc_bwd_quad_kernel(const float *__restrict__ go, const float *__restrict__ ref,
     for (int k = 0; k < CK; ++k)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[k][i] = 0.0f;
-    const float *gp = go + (static_cast<int64_t>(b) * G + g) * D * HW + p;
-    const int64_t gbase = (static_cast<int64_t>(b) * G + g) * D * HW + p;   // flat index of gp[0]
+    // non-negative shifts live at planes dofs .. dofs+D-1 of the Dtot planes of (b, g) (two-sided volume: dofs = m)
+    const int64_t gbase = ((static_cast<int64_t>(b) * G + g) * Dtot + dofs) * HW + p;   // flat index of gp[0]
+    const float *gp = go + gbase;
     const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (!tgt_pass) {
         for (int d0 = 0; d0 < D; d0 += 4) {
@@ -214,9 +215,46 @@ gwc_bwd_quad_kernel(const float *__restrict__ go, const float *__restrict__ ref,
             make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
 }
 
+// Negative shifts of the two-sided volume (slot s <-> k = m - s pairs ref[x] with tgt[x + W - k] for x < k, KITTI12/models/
+// submodule.py:128-131): only the first m columns of d_ref and the last m columns of d_tgt receive terms.  One thread per
+// (b, c, y, j < m) ADDS them to the gradients the quad kernel has written (same stream, one owner per element).
+__global__ void __launch_bounds__(128)
+corr_negative_bwd_kernel(const float *__restrict__ go, const float *__restrict__ ref, const float *__restrict__ tgt,
+                         float *__restrict__ gref, float *__restrict__ gtgt, int C, int H, int W, int m, int G, int cpg,
+                         int64_t total) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= total) return;
+    const int j = static_cast<int>(idx % m);
+    int64_t t = idx / m;
+    const int y = static_cast<int>(t % H);
+    t /= H;
+    const int c = static_cast<int>(t % C);
+    const int64_t b = t / C;
+    const int g = c / cpg;
+    const int64_t HW = static_cast<int64_t>(H) * W;
+    const float inv = 1.0f / static_cast<float>(cpg);
+    const float *gp = go + (b * G + g) * (2 * m + 1) * HW + static_cast<int64_t>(y) * W;   // row y of slot 0
+    const int64_t frow = (b * C + c) * HW + static_cast<int64_t>(y) * W;
+    if (gref) {       // d_ref[x = j] += sum_{k > j} g[slot m-k][x] * tgt[x + W - k]
+        float acc = 0.0f;
+        for (int k = j + 1; k <= m; ++k)
+            acc = fmaf(__ldg(gp + static_cast<int64_t>(m - k) * HW + j), __ldg(tgt + frow + j + W - k), acc);
+        gref[frow + j] += acc * inv;
+    }
+    if (gtgt) {       // d_tgt[x' = W - m + j] += sum_{k >= m - j} g[slot m-k][x' - (W - k)] * ref[x' - (W - k)]
+        const int xp = W - m + j;
+        float acc = 0.0f;
+        for (int k = max(1, m - j); k <= m; ++k) {
+            const int xs = xp - (W - k);   // = k - m + j in [0, k)
+            acc = fmaf(__ldg(gp + static_cast<int64_t>(m - k) * HW + xs), __ldg(ref + frow + xs), acc);
+        }
+        gtgt[frow + xp] += acc * inv;
+    }
+}
+
 template <int CK>
 static int launch_gwc_bwd_quad(const float *go, const float *ref, const float *tgt, float *gref, float *gtgt, int B, int C,
-                               int HW, int W, int D, int G, int cpg, cudaStream_t st) {
+                               int HW, int W, int D, int G, int cpg, int Dtot, int dofs, cudaStream_t st) {
     constexpr int SQ = 64, SPAN = SQ * 4;
     const int Dpad = (D + 3) / 4 * 4 + 4;  // the last block of 4 disparities reads up to d0 + 7 floats past a quad
     const size_t smem = sizeof(float) * 2 * CK * (SPAN + Dpad);
@@ -225,7 +263,8 @@ static int launch_gwc_bwd_quad(const float *go, const float *ref, const float *t
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
         return DV_ERR_LAUNCH;
     dim3 grid((HW + SPAN - 1) / SPAN, G * (cpg / CK), B);
-    kern<<<grid, 2 * SQ, smem, st>>>(go, ref, tgt, gref, gtgt, C, HW, W, D, G, cpg, Dpad, static_cast<int64_t>(B) * G * D * HW);
+    kern<<<grid, 2 * SQ, smem, st>>>(go, ref, tgt, gref, gtgt, C, HW, W, D, G, cpg, Dpad, Dtot, dofs,
+                                     static_cast<int64_t>(B) * G * Dtot * HW);
     return finish_launch();
 }
 
@@ -268,14 +307,24 @@ static int gwc_bwd_impl(const float *go, const float *ref, const float *tgt, flo
     const int64_t HW = H * W;
     if (HW > INT32_MAX || B > 65535 || G > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
     const int cpg = static_cast<int>(C / G);
-    if (mneg == 0 && dofs == 0 && Dtot == D && HW % 4 == 0 && W >= 4 && D <= 256 && aligned16(go) && aligned16(ref) &&
-        aligned16(tgt) && (!gref || aligned16(gref)) && (!gtgt || aligned16(gtgt)) && G * static_cast<int64_t>(cpg) <= 65535 &&
-        tune_variant("DV_GWC_BWD_QUAD", 1)) {
+    // quad kernel: plain gwc volumes, and two-sided volumes (non-negative slots) when every row holds both m-column bands
+    const bool two_sided_ok = mneg > 0 && dofs == mneg && Dtot == 2 * mneg + 1 && W >= 2 * mneg;
+    if ((mneg == 0 ? (dofs == 0 && Dtot == D) : two_sided_ok) && HW % 4 == 0 && W >= 4 && D <= 256 && aligned16(go) &&
+        aligned16(ref) && aligned16(tgt) && (!gref || aligned16(gref)) && (!gtgt || aligned16(gtgt)) &&
+        G * static_cast<int64_t>(cpg) <= 65535 && tune_variant("DV_GWC_BWD_QUAD", 1)) {
         const int Bi = static_cast<int>(B), Ci = static_cast<int>(C), HWi = static_cast<int>(HW), Wi = static_cast<int>(W),
-                  Di = static_cast<int>(D), Gi = static_cast<int>(G);
-        if (cpg % 8 == 0) return launch_gwc_bwd_quad<8>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, st);
-        if (cpg % 6 == 0) return launch_gwc_bwd_quad<6>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, st);
-        if (cpg % 4 == 0) return launch_gwc_bwd_quad<4>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, st);
+                  Di = static_cast<int>(D), Gi = static_cast<int>(G), Dt = static_cast<int>(Dtot), Do = static_cast<int>(dofs);
+        int rc = DV_ERR_UNSUPPORTED;
+        if (cpg % 8 == 0) rc = launch_gwc_bwd_quad<8>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, Dt, Do, st);
+        else if (cpg % 6 == 0) rc = launch_gwc_bwd_quad<6>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, Dt, Do, st);
+        else if (cpg % 4 == 0) rc = launch_gwc_bwd_quad<4>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, Dt, Do, st);
+        if (rc == DV_OK && mneg > 0) {
+            const int64_t total = B * C * H * mneg;
+            corr_negative_bwd_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, st>>>(
+                go, ref, tgt, gref, gtgt, Ci, static_cast<int>(H), Wi, static_cast<int>(mneg), Gi, cpg, total);
+            return finish_launch();
+        }
+        if (rc != DV_ERR_UNSUPPORTED) return rc;
     }
     dim3 grid(static_cast<unsigned>((HW + 127) / 128), static_cast<unsigned>(G), static_cast<unsigned>(B));
 #define DV_GB(CPGV)                                                                                                   \
