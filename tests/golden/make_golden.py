@@ -258,6 +258,73 @@ def gen_sceneflow():
     print("sceneflow:", len(out), "arrays")
 
 
+def _pcw_sampler_trace(out):
+    """Trace of the REFERENCE's PWCNet_ddim.ddim_sample / model_predictions (KITTI12/models/pwcnet_ddim.py:466-602): its
+    unmodified sampler methods bound onto tests/pcw_mock.py:MockPCW (conv stacks replaced by cheap stand-ins); the
+    reference's own warp / build_corrleation_volume / disparity_regression run underneath.  torch.randn / randn_like
+    return seeded synthetic noise so that the CUDA path can be fed the same tensors."""
+    import torch
+    import models.pwcnet_ddim as M
+    from pcw_mock import PCW_TRACE, MockPCW, pcw_trace_inputs
+    sys.path.insert(0, str(HERE.parent.parent))
+    from oracle import dv_oracle as O
+
+    inp = pcw_trace_inputs("cpu")
+    net = MockPCW(O.Schedule(), inp["shifts"])
+    for name in ("q_sample", "predict_noise_from_start", "model_predictions", "ddim_sample"):
+        setattr(MockPCW, name, getattr(M.PWCNet_ddim, name))
+    # asd = x_start volume of the quarter-res initial disparity: the reference's inline code (pwcnet_ddim.py:738-754)
+    b, h, w = inp["gt_q"].shape
+    dn = inp["gt_q"].reshape(b, 1, 1, h, w)
+    dv = torch.zeros([b, 48, h, w], dtype=torch.float32)
+    real = torch.floor(dn).long()
+    mask = real == 47
+    coff = real - dn + 1
+    dv = dv.view(b, 48, -1).scatter_(1, real.view(b, 1, -1), coff.view(b, 1, -1)).reshape(b, 48, h, w)
+    dv = dv.view(b, 48, -1).scatter_(1, torch.clamp(real + 1, 0, 47).view(b, 1, -1), (1 - coff).view(b, 1, -1)).reshape(b, 48, h, w)
+    fuzhi = torch.zeros([b, 48, h, w], dtype=torch.float32)
+    fuzhi[:, -1] = 1
+    asd = net.scale * (torch.where(mask.squeeze(1) == True, fuzhi, dv) * 2 - 1.)  # noqa: E712
+    asd = torch.clamp(asd, min=-net.scale, max=net.scale)
+    out["pcw.asd"] = asd.numpy()
+
+    rec = {"img": [], "eps": [], "x0": [], "disp": [], "prob": []}
+    orig_mp = net.model_predictions
+
+    def mp(volume, img, t, fl, fr):
+        rec["img"].append(img.detach().clone())
+        r = orig_mp(volume, img, t, fl, fr)
+        for key, v in zip(("eps", "x0", "disp", "prob"), r):
+            rec[key].append(v.detach().clone())
+        return r
+    net.model_predictions = mp
+    k = {"n": 0}
+    seeds = []
+    o_randn_like, o_randn = torch.randn_like, torch.randn
+
+    def randn_like(x, **kw):
+        seed = 5100 + k["n"]; k["n"] += 1
+        seeds.append((seed, 1 if x.dtype == torch.float64 else 0))
+        return _t(synth.normal(tuple(x.shape), seed, dtype=np.float64)).to(x.dtype)
+
+    def randn(*shape, **kw):
+        shape = tuple(shape[0]) if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)) else tuple(shape)
+        return _t(synth.normal(shape, 5000))
+    torch.randn_like, torch.randn = randn_like, randn
+    try:
+        with torch.no_grad():
+            final, prob = net.ddim_sample(inp["volume"], inp["used"], asd, inp["fl"], inp["fr"])
+    finally:
+        torch.randn_like, torch.randn = o_randn_like, o_randn
+    out["pcw.final"] = final.numpy()
+    for key, lst in rec.items():
+        for i, v in enumerate(lst):
+            out[f"pcw.{key}.{i}"] = _sample(v.numpy()) if key == "prob" else v.numpy()
+    out["pcw.randn_like_seeds"] = np.array(seeds, dtype=np.int64)
+    print("pcw trace: steps", len(rec["disp"]), "randn_like draws", k["n"],
+          "final range", float(final.min()), float(final.max()))
+
+
 def gen_kitti12():
     import torch
     sys.path.insert(0, str(REF / "KITTI12"))
@@ -275,6 +342,7 @@ def gen_kitti12():
         x = synth.normal(shape, seed)
         disp = synth.uniform((shape[0], 1, shape[2], shape[3]), seed + 1, dtype=np.float32) * np.float32(amp) - np.float32(3)
         out["k12.warp." + key] = sub.warp(_t(x), _t(disp)).detach().numpy()
+    _pcw_sampler_trace(out)
     np.savez_compressed(HERE / "kitti12.npz", **out)
     print("kitti12:", len(out), "arrays")
 
