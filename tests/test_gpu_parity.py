@@ -611,3 +611,44 @@ def test_cpu_tensor_raises(ops):
     x = torch.zeros(1, 8, 4, 8)
     with pytest.raises(DvLibraryError):
         ops.gwc_volume(x, x, 4, 2)
+
+
+def test_concurrent_host_threads_and_streams(ops):
+    """nn.DataParallel drives the ops from one host thread per replica (SceneFlow/main.py:67).  Four threads, each on its
+    own CUDA stream, hammer the kernels that keep device-side tile counters (the streaming concat producer, the TMA
+    softmax-regression) plus gwc; every result must equal the single-threaded one."""
+    import threading
+    g = torch.Generator(device="cuda"); g.manual_seed(91)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")
+    B, h, w, D = 2, 27, 240, 48
+    jobs = []
+    for _ in range(4):
+        fl, fr, cl, cr = rn(B, 64, h, w), rn(B, 64, h, w), rn(B, 16, h, w), rn(B, 16, h, w)
+        att, cost = ops.att_softmax(rn(B, 1, D, h, w)), rn(B, 192, 4 * 9, 4 * 60) * 4.0
+        want = (ops.gwc_volume(fl, fr, D, 8), ops.concat_volume_weighted(cl, cr, D, mask_left=False, att_weights=att),
+                ops.softmax_regress(cost)["disp"])
+        jobs.append(((fl, fr, cl, cr, att, cost), want))
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(args, want):
+        try:
+            fl, fr, cl, cr, att, cost = args
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(25):
+                    got = (ops.gwc_volume(fl, fr, D, 8), ops.concat_volume_weighted(cl, cr, D, mask_left=False, att_weights=att),
+                           ops.softmax_regress(cost)["disp"])
+                    for a, b in zip(got, want):
+                        if not torch.equal(a, b):
+                            errors.append("mismatch")
+            st.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
