@@ -114,9 +114,10 @@ def fuse_acv_patch(model) -> bool:
     forward or its state_dict: the four Conv3d modules keep their parameters; `patch.forward` returns the finished
     patch volume and `patch_l*.forward` pass the slices of that tensor through, so the reference's own
     `torch.cat((patch_l1, patch_l2, patch_l3), dim=1)` reassembles it.  Only taken when autograd is off (inference);
-    with gradients enabled the original cuDNN convolutions run.  Returns False when `model` has no such modules."""
-    import types
-
+    with gradients enabled the original cuDNN convolutions run.  The four instances are re-classed to dynamic
+    subclasses of their own class (not given instance-level `forward` attributes), so `nn.DataParallel` replicas — which
+    are shallow copies of the instance `__dict__` — run the fused forward with THEIR parameters on THEIR device.
+    Returns False when `model` has no such modules."""
     import torch
     import torch.nn.functional as F
 
@@ -127,24 +128,31 @@ def fuse_acv_patch(model) -> bool:
     if not all(hasattr(model, n) for n in names):
         return False
     patch, l1, l2, l3 = (getattr(model, n) for n in names)
+    siblings = (l1, l2, l3)                          # the originals: their (tiny) weights are moved to x.device per call
 
     def conv(self, x):
         return F.conv3d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
 
-    def patch_forward(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad) or not x.is_cuda:
-            return conv(self, x)
-        out = ops.acv_patch_volume(x, self.weight, l1.weight, l2.weight, l3.weight).to(x.dtype)
-        out._dv_fused_patch = True
-        return out
+    class FusedPatchConv(type(patch)):
+        def forward(self, x):
+            if (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad)) or not x.is_cuda:
+                return conv(self, x)
+            w = [m.weight.detach().to(x.device) for m in siblings]
+            out = ops.acv_patch_volume(x, self.weight.detach(), w[0], w[1], w[2]).to(x.dtype)
+            out._dv_fused_patch = True
+            return out
 
-    def slice_forward(self, x):
-        base = x._base if x._base is not None else x
-        if getattr(base, "_dv_fused_patch", False):
-            return x                                  # already patch_l*(patch(gwc)[:, slice])
-        return conv(self, x)
+    def make_slice_class(base):
+        class PatchSliceConv(base):
+            def forward(self, x):
+                src = x._base if x._base is not None else x
+                if getattr(src, "_dv_fused_patch", False):
+                    return x                              # already patch_l*(patch(gwc)[:, slice])
+                return conv(self, x)
+        return PatchSliceConv
 
-    _bind(patch, "forward", types.MethodType(patch_forward, patch))
-    for m in (l1, l2, l3):
-        _bind(m, "forward", types.MethodType(slice_forward, m))
+    for m, cls in ((patch, FusedPatchConv), (l1, make_slice_class(type(l1))), (l2, make_slice_class(type(l2))),
+                   (l3, make_slice_class(type(l3)))):
+        _undo.append((m, "__class__", m.__class__, True))
+        m.__class__ = cls
     return True

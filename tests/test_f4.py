@@ -171,6 +171,11 @@ def test_fuse_acv_patch_drop_in_matches_cudnn_and_keeps_state_dict():
             got = model(vol)
         assert _lib.launch_count() - n0 == 3                      # one launch per dilation class
         assert float((got - want).abs().max() / want.abs().max()) < 1e-5
+        # nn.DataParallel replicas are shallow copies of the instance: the fused forward must use the REPLICA's parameters
+        rep = model.patch._replicate_for_data_parallel()
+        rep._parameters["weight"] = torch.zeros_like(model.patch.weight)
+        with torch.no_grad():
+            assert not rep(vol).any() and model.patch(vol).any()
         # with autograd on the original convolutions run (weights receive gradients)
         n0 = _lib.launch_count()
         model(vol).sum().backward()
