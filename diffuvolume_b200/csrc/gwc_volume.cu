@@ -151,13 +151,18 @@ gwc_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, 
 // staging buffer is 17 KB per stage whatever cpg is (the one-shot kernel above needs cpg x 2.2 KB: 140 KB at cpg = 32,
 // one 128-thread CTA per SM).  Used by PCWNet's refinement correlation (C = 32, G = 1, KITTI12/models/pwcnet_ddim.py:494).
 // Every thread owns ONE disparity chunk (NCH = number of chunks), pipeline stage = (span, k-chunk).
-template <int KC, int DC, int SQ, int NCH, int MINB>
+template <int KC, int DC, int SQ, int NCH, int MINB, int STAGES>
 __global__ void __launch_bounds__(SQ * NCH, MINB)
 gwc_volume_kchunk_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out,
                          int C, int HW, int W, int D, int G, int cpg, int Dpad, int Dtot, int dofs, int tiles_per_cta) {
+    // STAGES-deep ring with full / empty mbarriers (no CTA-wide barrier per stage: ncu on the __syncthreads version showed
+    // the barrier as the top stall, each stage being only KC x 48 FMA per thread).  Thread 0 is the producer: before it
+    // computes stage st it refills the slot of stage st-1 with stage st+STAGES-1, which needs every warp to have released
+    // that slot — they are at most one stage behind.
     constexpr int SPAN = SQ * 4;
+    constexpr int NWARPS = SQ * NCH / 32;
     extern __shared__ __align__(16) float smem[];
-    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
     const int rpitch = SPAN + Dpad;
     const int stage_floats = KC * SPAN + KC * rpitch;
     const int b = blockIdx.z, g = blockIdx.y;
@@ -169,41 +174,50 @@ gwc_volume_kchunk_kernel(const float *__restrict__ ref, const float *__restrict_
     const int64_t plane0 = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * cpg) * HW;
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], NWARPS);
+        }
         fence_mbar_init();
     }
     __syncthreads();
 
-    auto issue = [&](int st) {  // warp 0 only
-        float *sL = smem + (st & 1) * stage_floats;
+    auto issue = [&](int st) {  // thread 0 only
+        const int slot = st % STAGES;
+        float *sL = smem + slot * stage_floats;
         float *sR = sL + KC * SPAN;
         const int p0 = (t0 + st / nkc) * SPAN;
         const int k0 = (st % nkc) * KC;
         const int len = min(SPAN, HW - p0);
         const int64_t roff0 = plane0 + static_cast<int64_t>(k0) * HW + p0 - Dpad;
         const int skip0 = roff0 < 0 ? static_cast<int>(-roff0) : 0;  // only the very first plane of the tensor
-        if (threadIdx.x == 0)
-            mbar_expect_tx(&bar[st & 1], static_cast<uint32_t>(KC) * (2u * len + Dpad) * 4u - 4u * skip0);
-        __syncwarp();
-        for (int k = threadIdx.x; k < KC; k += 32) {
-            bulk_g2s(sL + k * SPAN, ref + plane0 + static_cast<int64_t>(k0 + k) * HW + p0, 4u * len, &bar[st & 1]);
+        mbar_expect_tx(&full_bar[slot], static_cast<uint32_t>(KC) * (2u * len + Dpad) * 4u - 4u * skip0);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            bulk_g2s(sL + k * SPAN, ref + plane0 + static_cast<int64_t>(k0 + k) * HW + p0, 4u * len, &full_bar[slot]);
             const int skip = k == 0 ? skip0 : 0;
             bulk_g2s(sR + k * rpitch + skip, tgt + roff0 + static_cast<int64_t>(k) * HW + skip, 4u * (len + Dpad - skip),
-                     &bar[st & 1]);
+                     &full_bar[slot]);
         }
     };
-    if (threadIdx.x < 32) issue(0);
+    if (threadIdx.x == 0)
+        for (int st = 0; st < STAGES - 1 && st < nstages; ++st) issue(st);
 
     const int q = threadIdx.x % SQ;
     const int d0 = (threadIdx.x / SQ) * DC;
     const float inv = 1.0f / static_cast<float>(cpg);
     float acc[DC][4];
     for (int st = 0; st < nstages; ++st) {
-        if (threadIdx.x < 32 && st + 1 < nstages) issue(st + 1);
-        mbar_wait(&bar[st & 1], (st >> 1) & 1);
+        const int slot = st % STAGES;
+        if (threadIdx.x == 0 && st + STAGES - 1 < nstages) {
+            const int nxt = st + STAGES - 1;              // goes into the slot stage st-1 used
+            if (st >= 1) mbar_wait(&empty_bar[nxt % STAGES], ((st - 1) / STAGES) & 1);
+            issue(nxt);
+        }
+        mbar_wait(&full_bar[slot], (st / STAGES) & 1);
         const int kc = st % nkc;
-        const float *sL = smem + (st & 1) * stage_floats;
+        const float *sL = smem + slot * stage_floats;
         const float *sR = sL + KC * SPAN;
         const int p = (t0 + st / nkc) * SPAN + 4 * q;
         if (p < HW && d0 < D) {
@@ -230,30 +244,32 @@ gwc_volume_kchunk_kernel(const float *__restrict__ ref, const float *__restrict_
 #pragma unroll
                     for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(l[i], rw[DC + i - j], acc[j][i]);
             }
-            if (kc == nkc - 1) {
-                int xs[4];
-                xs[0] = p % W;
+        }
+        // this warp is done reading the slot
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[slot]);
+        if (p < HW && d0 < D && kc == nkc - 1) {
+            int xs[4];
+            xs[0] = p % W;
 #pragma unroll
-                for (int i = 1; i < 4; ++i) {
-                    xs[i] = xs[i - 1] + 1;
-                    if (xs[i] >= W) xs[i] -= W;
-                }
-                float *op = out + ((static_cast<int64_t>(b) * G + g) * Dtot + dofs + d0) * HW + p;
+            for (int i = 1; i < 4; ++i) {
+                xs[i] = xs[i - 1] + 1;
+                if (xs[i] >= W) xs[i] -= W;
+            }
+            float *op = out + ((static_cast<int64_t>(b) * G + g) * Dtot + dofs + d0) * HW + p;
 #pragma unroll
-                for (int j = 0; j < DC; ++j) {
-                    const int d = d0 + j;
-                    if (d < D) {
-                        float4 v;
-                        v.x = xs[0] >= d ? acc[j][0] * inv : 0.0f;
-                        v.y = xs[1] >= d ? acc[j][1] * inv : 0.0f;
-                        v.z = xs[2] >= d ? acc[j][2] * inv : 0.0f;
-                        v.w = xs[3] >= d ? acc[j][3] * inv : 0.0f;
-                        stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(j) * HW), v);
-                    }
+            for (int j = 0; j < DC; ++j) {
+                const int d = d0 + j;
+                if (d < D) {
+                    float4 v;
+                    v.x = xs[0] >= d ? acc[j][0] * inv : 0.0f;
+                    v.y = xs[1] >= d ? acc[j][1] * inv : 0.0f;
+                    v.z = xs[2] >= d ? acc[j][2] * inv : 0.0f;
+                    v.w = xs[3] >= d ? acc[j][3] * inv : 0.0f;
+                    stg_cs(reinterpret_cast<float4 *>(op + static_cast<int64_t>(j) * HW), v);
                 }
             }
         }
-        if (st + 1 < nstages) __syncthreads();
     }
 }
 
@@ -356,8 +372,9 @@ static int launch_gwc_kchunk(const float *ref, const float *tgt, float *out, int
     const int nspans = (HW + SPAN - 1) / SPAN;
     int tpc = tune_variant("DV_GWC_TPC", 8);
     while (tpc > 1 && static_cast<int64_t>((nspans + tpc - 1) / tpc) * G * B < 4LL * kNumSMs * MINB) tpc /= 2;
-    const size_t smem = sizeof(float) * 2 * (static_cast<size_t>(KC) * SPAN + static_cast<size_t>(KC) * (SPAN + Dpad));
-    auto kern = gwc_volume_kchunk_kernel<KC, DC, SQ, NCH, MINB>;
+    constexpr int STAGES = 3;
+    const size_t smem = sizeof(float) * STAGES * (static_cast<size_t>(KC) * SPAN + static_cast<size_t>(KC) * (SPAN + Dpad));
+    auto kern = gwc_volume_kchunk_kernel<KC, DC, SQ, NCH, MINB, STAGES>;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
         return DV_ERR_LAUNCH;

@@ -13,11 +13,20 @@
 
 namespace dv {
 
-constexpr int kWarpCg = 8;  // channels per thread: all 4 x 8 tap loads of a thread are issued before the first blend
+constexpr int kWarpCg = 16;  // channels per thread: all 4 x 16 tap loads of a thread are issued before the first blend
+
+// a / b for an integer-valued b <= 4096 from y = RN(1/b): RN(a*y) corrected by one FMA step equals __fdiv_rn(a, b) for every
+// normal a (exhaustively checked per divisor, see geo_lookup.cu) — the kernel was issue-bound (ncu: 81 % issue slots) and
+// the IEEE division sequence with its slow-path branches was a third of the per-pixel header.
+__device__ __forceinline__ float warp_div(float a, float b, float y, bool use_rcp) {
+    if (!use_rcp) return __fdiv_rn(a, b);
+    const float q = __fmul_rn(a, y);
+    return __fmaf_rn(__fmaf_rn(-q, b, a), y, q);
+}
 
 __global__ void __launch_bounds__(256)
 warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *__restrict__ out, int C, int H, int W,
-            int cgroups) {
+            int cgroups, float rcp_w, float rcp_h, int use_rcp) {
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z / cgroups, cbeg = (blockIdx.z % cgroups) * kWarpCg;
     const int cend = min(cbeg + kWarpCg, C);
@@ -25,10 +34,10 @@ warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *
     const int64_t HW = static_cast<int64_t>(H) * W;
     const float d = disp[static_cast<int64_t>(b) * HW + static_cast<int64_t>(y) * W + px];
     // the reference's op sequence in fp32 (no contraction across its separate tensor ops)
-    const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(static_cast<float>(px), d)), static_cast<float>(max(W - 1, 1))), 1.0f);
-    const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, static_cast<float>(y)), static_cast<float>(max(H - 1, 1))), 1.0f);
-    const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), static_cast<float>(W)), 1.0f), 2.0f);
-    const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), static_cast<float>(H)), 1.0f), 2.0f);
+    const float gx = __fsub_rn(warp_div(__fmul_rn(2.0f, __fsub_rn(static_cast<float>(px), d)), static_cast<float>(max(W - 1, 1)), rcp_w, use_rcp), 1.0f);
+    const float gy = __fsub_rn(warp_div(__fmul_rn(2.0f, static_cast<float>(y)), static_cast<float>(max(H - 1, 1)), rcp_h, use_rcp), 1.0f);
+    const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), static_cast<float>(W)), 1.0f), 0.5f);   // "/ 2": exact
+    const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), static_cast<float>(H)), 1.0f), 0.5f);
     const float x0f = floorf(ix), y0f = floorf(iy);
     const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f), x1 = x0 + 1, y1 = y0 + 1;
     const float wx1 = ix - x0f, wx0 = (x0f + 1.0f) - ix, wy1 = iy - y0f, wy0 = (y0f + 1.0f) - iy;
@@ -39,8 +48,7 @@ warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *
     const float m = msum < 0.999f ? 0.0f : 1.0f;
     const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
     const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
-    const int64_t o00 = static_cast<int64_t>(cy0) * W + cx0, o01 = static_cast<int64_t>(cy0) * W + cx1;
-    const int64_t o10 = static_cast<int64_t>(cy1) * W + cx0, o11 = static_cast<int64_t>(cy1) * W + cx1;
+    const int o00 = cy0 * W + cx0, o01 = cy0 * W + cx1, o10 = cy1 * W + cx0, o11 = cy1 * W + cx1;   // H*W < 2^31
     const float *xp = x + static_cast<int64_t>(b) * C * HW;
     float *op = out + static_cast<int64_t>(b) * C * HW + static_cast<int64_t>(y) * W + px;
     if (m == 0.0f) {
@@ -73,7 +81,10 @@ extern "C" int dv_warp_f32(const float *x, const float *disp, float *out, int64_
     const int64_t cgroups = (C + kWarpCg - 1) / kWarpCg;
     if (H * W > INT32_MAX || B * cgroups > 65535 || H > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
     dim3 grid(static_cast<unsigned>((W + 255) / 256), static_cast<unsigned>(H), static_cast<unsigned>(B * cgroups));
+    const int use_rcp = (W - 1 <= 4096 && H - 1 <= 4096) ? 1 : 0;     // the range the reciprocal division was verified on
+    const float rcp_w = 1.0f / static_cast<float>(W > 1 ? W - 1 : 1), rcp_h = 1.0f / static_cast<float>(H > 1 ? H - 1 : 1);
     warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, disp, out, static_cast<int>(C), static_cast<int>(H),
-                                                                   static_cast<int>(W), static_cast<int>(cgroups));
+                                                                   static_cast<int>(W), static_cast<int>(cgroups), rcp_w, rcp_h,
+                                                                   use_rcp);
     return finish_launch();
 }
