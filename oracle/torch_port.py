@@ -1,5 +1,6 @@
-"""CPU baseline port of the reference hot path with the reference's own op sequence, on torch CPU
-tensors — TEST / BASELINE INFRASTRUCTURE, NOT PRODUCT.
+"""CPU baseline port of the reference hot path with the reference's own op sequence, on torch
+tensors — TEST / BASELINE INFRASTRUCTURE, NOT PRODUCT.  (Device-agnostic: bench.py times it on the host CPU; the GPU
+parity tests also run it on CUDA tensors as a full-size checker, which is what the reference itself does on a GPU box.)
 
 The reference is a PyTorch program; on a host CPU it runs as a chain of ATen kernels (one memset
 plus three launches per disparity for a gwc volume, a materialised softmax, broadcast multiplies,
@@ -61,7 +62,7 @@ def softmax_regress(cost: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """acv_ddim.py:269-270 + SceneFlow/models/submodule.py:173-177."""
     D = cost.shape[1]
     prob = F.softmax(cost, dim=1)
-    dv = torch.arange(0, D, dtype=prob.dtype).view(1, D, 1, 1)
+    dv = torch.arange(0, D, dtype=prob.dtype, device=prob.device).view(1, D, 1, 1)
     return torch.sum(prob * dv, 1, keepdim=False), prob
 
 
@@ -69,7 +70,7 @@ def renewal_vote(disp, used, prob, thr_dif=1.0, thr_unc=3.0):
     """acv_ddim.py:320-331."""
     D = prob.shape[1]
     m1 = torch.where(torch.abs(disp - used) < thr_dif, 1, 0)
-    dv = torch.arange(0, D, dtype=disp.dtype).view(1, D, 1, 1)
+    dv = torch.arange(0, D, dtype=disp.dtype, device=disp.device).view(1, D, 1, 1)
     unc = torch.sum(torch.abs(disp.unsqueeze(1) - dv) * prob, dim=1)
     m2 = torch.where(unc < thr_unc, 1, 0)
     return (m2 * m1).float()
@@ -83,11 +84,11 @@ def xstart_from_pred(pred: torch.Tensor, maxdisp: int = 192, D: int = 48, scale:
     h, w = dn.shape[-2:]
     real = torch.floor(dn).long()
     coff = real - dn + 1
-    vol = torch.zeros([b, D, h * w], dtype=torch.float32)
+    vol = torch.zeros([b, D, h * w], dtype=torch.float32, device=pred.device)
     vol.scatter_(1, real.view(b, 1, -1), coff.view(b, 1, -1))
     vol.scatter_(1, torch.clamp(real + 1, 0, D - 1).view(b, 1, -1), (1 - coff).view(b, 1, -1))
     vol = vol.view(b, D, h, w)
-    last = torch.zeros([b, D, h, w], dtype=torch.float32)
+    last = torch.zeros([b, D, h, w], dtype=torch.float32, device=pred.device)
     last[:, -1] = 1
     x0 = torch.where((real == D - 1).expand(b, D, h, w), last, vol)
     return torch.clamp(scale * (x0 * 2 - 1.0), min=-scale, max=scale)
@@ -108,7 +109,7 @@ def hot_path_pair(feat_l, feat_r, cfeat_l, cfeat_r, att_logits, costs: Sequence[
     B, _, _, h, w = ac.shape
     img = asd
     final = [used]
-    mask = torch.zeros([B, h, w], dtype=torch.float32)
+    mask = torch.zeros([B, h, w], dtype=torch.float32, device=ac.device)
     pairs = sched.time_pairs()
     for i, (t, t_next) in enumerate(pairs):
         vol_f, n = filter_volume(ac, img, shifts[i], sched.scale)
@@ -129,5 +130,5 @@ def hot_path_pair(feat_l, feat_r, cfeat_l, cfeat_r, att_logits, costs: Sequence[
         img = x0 * san + c * eps + sigma * step_noises[i]
         img = torch.where(mask.unsqueeze(1) == 0, renoises[i], img)
     stack = torch.stack(final, 0)
-    cf = torch.tensor(cof, dtype=torch.float32).view(-1, 1, 1, 1)
-    return torch.sum(stack * cf, dim=0), [gwc, img]
+    cf = torch.tensor(cof, dtype=torch.float32, device=stack.device).view(-1, 1, 1, 1)
+    return torch.sum(stack * cf, dim=0), [gwc, img, mask]

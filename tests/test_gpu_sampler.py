@@ -176,3 +176,44 @@ def test_hot_path_cuda_graph_replay_matches_eager():
     for k in want2:
         assert torch.equal(got[k], want2[k]), k
     assert not torch.equal(got["pred"], want["pred"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("filter_mode,regress_mode", [("regenerate", "logits"), ("volume", "logits"), ("regenerate", "fused_upsample")])
+def test_full_size_hot_path_vs_reference_op_sequence_on_cuda(filter_mode, regress_mode):
+    """BASELINE.json's headline size (540x960, D=192, C=320/G=40, T=5), one pair: the fused hot path against the
+    reference's own op sequence (oracle/torch_port.py — pinned on the CPU against the oracle and the reference-minted
+    fixtures) executed on CUDA tensors, which is what the reference does on a GPU box.  North-star gates: volume
+    max relative error <= 1e-4, disparity EPE <= 0.01 px; the renewal mask may differ only where a vote sits on a threshold."""
+    import torch
+    from diffuvolume_b200 import ops
+    from diffuvolume_b200.pipeline import AcvHotPath
+    from oracle import torch_port as P
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(2024)
+    B, H, W, D = 1, 540, 960, 48
+    h, w = H // 4, W // 4
+    rn = lambda *s, dt=torch.float32: torch.randn(*s, generator=g, device=dev, dtype=dt)
+    ru = lambda *s, dt=torch.float32: torch.rand(*s, generator=g, device=dev, dtype=dt)
+    fl, fr, cl, cr = rn(B, 320, h, w), rn(B, 320, h, w), rn(B, 32, h, w), rn(B, 32, h, w)
+    att = rn(B, 1, D, h, w)
+    fused = regress_mode == "fused_upsample"
+    costs = [(rn(B, 1, D, h, w) if fused else rn(B, 192, H, W)) * 4.0 for _ in range(5)]
+    used = ru(B, H, W) * 191.0
+    disp_q = ru(B, h, w) * 47.75
+    shifts = [rn(B, D) * 0.1 for _ in range(5)]
+    sn = [rn(B, D, h, w, dt=torch.float32 if i == 0 else torch.float64) for i in range(4)]
+    rz = [ru(B, D, h, w, dt=torch.float64) for _ in range(4)]
+    path = AcvHotPath(filter_mode=filter_mode, regress_mode=regress_mode)
+    out = path(fl, fr, cl, cr, att, costs, used, disp_q, shifts, sn, rz, keep_volumes=True)
+    asd = ops.xstart_from_disp(disp_q, D, 1.0)
+    want_pred, (want_gwc, want_img, want_mask) = P.hot_path_pair(fl, fr, cl, cr, att, costs, used, asd, shifts, sn, rz,
+                                                                 sched=O.Schedule(), upsample_to=(192, H, W) if fused else None)
+    assert float((out["gwc"] - want_gwc).abs().max() / want_gwc.abs().max()) < 1e-4
+    want_ac = P.acv_volume(att, P.concat_volume(cl, cr, D, mask_left=False))
+    assert float((out["ac"] - want_ac).abs().max() / want_ac.abs().max()) < 1e-4
+    epe = float((out["pred"] - want_pred).abs().mean())
+    assert epe < 0.01 and float((out["pred"] - want_pred).abs().max()) < 0.05, epe
+    assert float((out["mask"] == want_mask).float().mean()) > 0.999
+    close = (out["x_last"].double() - want_img.double()).abs() < 5e-3        # 2-tap x_start: discontinuous at integer crossings
+    assert float(close.float().mean()) > 0.999

@@ -50,7 +50,7 @@ def test_hot_path_pair_matches_oracle_trace():
     vol = O.acv_attention_volume(att, O.build_concat_volume(cl, cr, D, False))
     pred_o, _ = O.ddim_sample_acv(sched, vol, used, asd, lambda tt: shifts[[999, 799, 599, 399, 199].index(tt)],
                                   lambda v, i: costs[i], sn, rz)
-    pred_p, (gwc, _) = P.hot_path_pair(t(fl), t(fr), t(cl), t(cr), t(att), [t(c) for c in costs], t(used), t(asd),
+    pred_p, (gwc, _, _) = P.hot_path_pair(t(fl), t(fr), t(cl), t(cr), t(att), [t(c) for c in costs], t(used), t(asd),
                                        [t(s) for s in shifts], [t(s) for s in sn], [t(r) for r in rz], sched, G=G)
     assert np.abs(pred_p.numpy() - pred_o).max() < 1e-3
     assert rel_max_err(gwc.numpy(), O.build_gwc_volume(fl, fr, D, G)) < 1e-6
