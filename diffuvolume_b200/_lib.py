@@ -94,6 +94,7 @@ SIGNATURES = {
     "dv_downsample_bilinear_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _I64, _F, _F, _F, _P]),
     "dv_ddim_step": (_I, [C.POINTER(DdimStepArgs), _P]),
     "dv_corr1d_allpairs_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P]),
+    "dv_corr1d_allpairs_pooled_f32": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_geo_permute_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_avgpool_w2_f32": (_I, [_P, _P, _I64, _I64, _P]),
     "dv_geo_lookup_f32": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),

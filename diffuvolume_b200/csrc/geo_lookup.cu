@@ -121,8 +121,10 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 constexpr int kApPitch = kApTile + 8;
 __global__ void __launch_bounds__(128)
-corr1d_allpairs_mma_kernel(const float *__restrict__ f1, const float *__restrict__ f2, float *__restrict__ out, int C,
-                           int H, int W1, int W2) {
+corr1d_allpairs_mma_kernel(const float *__restrict__ f1, const float *__restrict__ f2, float *__restrict__ out,
+                           float *__restrict__ pooled, int C, int H, int W1, int W2) {
+    // pooled (optional): level 1 of the correlation pyramid, avg_pool2d([1,2]) of `out` (geometry_ddim.py:27-30), written
+    // from the accumulators — a thread's fragment holds the two columns of a pair, (a + b) / 2 as the pooling kernel does
     __shared__ __align__(16) float sA[kApKc][kApPitch];
     __shared__ __align__(16) float sB[kApKc][kApPitch];
     const int by = blockIdx.z;
@@ -218,6 +220,8 @@ corr1d_allpairs_mma_kernel(const float *__restrict__ f1, const float *__restrict
                     if (x2 < W2) orow[x2] = v0;
                     if (x2 + 1 < W2) orow[x2 + 1] = v1;
                 }
+                if (pooled && x2 + 1 < W2)
+                    pooled[(static_cast<int64_t>(by) * W1 + x1) * (W2 / 2) + x2 / 2] = __fadd_rn(v0, v1) / 2.0f;
             }
         }
 }
@@ -700,29 +704,35 @@ geo_lookup_packed_kernel(const GeoLookupPackedArgs a) {
 
 }  // namespace dv
 
-extern "C" int dv_corr1d_allpairs_f32(const float *fmap1, const float *fmap2, float *out, int64_t B, int64_t C,
-                                      int64_t H, int64_t W1, int64_t W2, void *stream) {
+static int corr1d_allpairs_impl(const float *fmap1, const float *fmap2, float *out, float *pooled, int64_t B, int64_t C,
+                                int64_t H, int64_t W1, int64_t W2, void *stream) {
     using namespace dv;
     if (!fmap1 || !fmap2 || !out) return DV_ERR_NULL;
     if (B <= 0 || C <= 0 || H <= 0 || W1 <= 0 || W2 <= 0 || B * H > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    if (pooled && W2 < 2) return DV_ERR_BAD_SHAPE;
     dim3 grid(static_cast<unsigned>((W2 + kApTile - 1) / kApTile), static_cast<unsigned>((W1 + kApTile - 1) / kApTile),
               static_cast<unsigned>(B * H));
-    if (grid.y > 65535 || B * H > 65535 * 1LL) {
-        // z is limited to 65535: fold (b, y) planes in chunks
-        for (int64_t z0 = 0; z0 < B * H; z0 += 65535) {
-            // not reached for any reference configuration (B*H = 96 per pair); keep it simple
-            (void)z0;
-        }
-        return DV_ERR_UNSUPPORTED;
-    }
-    if (tune_variant("DV_ALLPAIRS_MMA", 1)) {
-        corr1d_allpairs_mma_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-            fmap1, fmap2, out, static_cast<int>(C), static_cast<int>(H), static_cast<int>(W1), static_cast<int>(W2));
+    if (grid.y > 65535 || B * H > 65535 * 1LL) return DV_ERR_UNSUPPORTED;   // B*H = 96 per pair in every reference configuration
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (tune_variant("DV_ALLPAIRS_MMA", 1) || pooled) {
+        corr1d_allpairs_mma_kernel<<<grid, 128, 0, st>>>(fmap1, fmap2, out, pooled, static_cast<int>(C), static_cast<int>(H),
+                                                         static_cast<int>(W1), static_cast<int>(W2));
         return finish_launch();
     }
-    corr1d_allpairs_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        fmap1, fmap2, out, static_cast<int>(C), static_cast<int>(H), static_cast<int>(W1), static_cast<int>(W2));
+    corr1d_allpairs_kernel<<<grid, 64, 0, st>>>(fmap1, fmap2, out, static_cast<int>(C), static_cast<int>(H),
+                                                static_cast<int>(W1), static_cast<int>(W2));
     return finish_launch();
+}
+
+extern "C" int dv_corr1d_allpairs_f32(const float *fmap1, const float *fmap2, float *out, int64_t B, int64_t C,
+                                      int64_t H, int64_t W1, int64_t W2, void *stream) {
+    return corr1d_allpairs_impl(fmap1, fmap2, out, nullptr, B, C, H, W1, W2, stream);
+}
+
+extern "C" int dv_corr1d_allpairs_pooled_f32(const float *fmap1, const float *fmap2, float *out, float *pooled, int64_t B,
+                                             int64_t C, int64_t H, int64_t W1, int64_t W2, void *stream) {
+    if (!pooled) return DV_ERR_NULL;
+    return corr1d_allpairs_impl(fmap1, fmap2, out, pooled, B, C, H, W1, W2, stream);
 }
 
 extern "C" int dv_geo_permute_f32(const float *geo, float *rows, int64_t B, int64_t C, int64_t D, int64_t h, int64_t w,

@@ -31,7 +31,11 @@ class Combined_Geo_Encoding_Volume:
         self.num_levels = num_levels
         self.radius = radius
         self.init_corr_pyramid = []
-        init_corr = Combined_Geo_Encoding_Volume.corr(init_fmap1, init_fmap2)
+        if num_levels >= 2 and init_fmap2.shape[-1] >= 2:
+            # level 1 of the correlation pyramid comes out of the same launch (pooled from the accumulators)
+            init_corr, pooled = ops.corr1d_allpairs(init_fmap1.float(), init_fmap2.float(), return_pooled=True)
+        else:
+            init_corr, pooled = Combined_Geo_Encoding_Volume.corr(init_fmap1, init_fmap2), None
         b, h, w, _, w2 = init_corr.shape
         b, c, d, h, w = geo_volume.shape
         self.channel = c
@@ -42,8 +46,8 @@ class Combined_Geo_Encoding_Volume:
         self._geo_packed = ops.geo_pack(self._geo_volume, num_levels)
         init_corr = init_corr.reshape(b * h * w, 1, 1, w2)
         self.init_corr_pyramid.append(init_corr)
-        for _ in range(self.num_levels - 1):
-            init_corr = ops.avgpool_w2(init_corr)
+        for lvl in range(1, self.num_levels):
+            init_corr = pooled.reshape(b * h * w, 1, 1, w2 // 2) if (lvl == 1 and pooled is not None) else ops.avgpool_w2(init_corr)
             self.init_corr_pyramid.append(init_corr)
 
     @property

@@ -648,14 +648,20 @@ def disparity_regression_bwd(grad_out: torch.Tensor, maxdisp: int) -> torch.Tens
 # --------------------------------------------------------------------------------------------
 # IGEV geometry
 # --------------------------------------------------------------------------------------------
-def corr1d_allpairs(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:
-    """a14 — Combined_Geo_Encoding_Volume.corr (geometry_ddim.py:72-80) -> [B,H,W1,1,W2]."""
+def corr1d_allpairs(fmap1: torch.Tensor, fmap2: torch.Tensor, return_pooled: bool = False):
+    """a14 — Combined_Geo_Encoding_Volume.corr (geometry_ddim.py:72-80) -> [B,H,W1,1,W2]; with return_pooled also level 1
+    of the correlation pyramid ([B,H,W1,1,W2//2], avg_pool2d([1,2]), geometry_ddim.py:27-30) from the same launch."""
     B, D, H, W1 = fmap1.shape
     _, _, _, W2 = fmap2.shape
     _need_cuda(fmap1, fmap2)
     fmap1, fmap2 = _f32c(fmap1, "fmap1"), _f32c(fmap2, "fmap2")
     out = torch.empty((B, H, W1, 1, W2), dtype=torch.float32, device=fmap1.device)
     with torch.cuda.device(fmap1.device):
+        if return_pooled:
+            pooled = torch.empty((B, H, W1, 1, W2 // 2), dtype=torch.float32, device=fmap1.device)
+            check(_lib.lib().dv_corr1d_allpairs_pooled_f32(_ptr(fmap1), _ptr(fmap2), _ptr(out), _ptr(pooled), B, D, H, W1, W2,
+                                                           _stream(out)), "dv_corr1d_allpairs_pooled_f32")
+            return out, pooled
         check(_lib.lib().dv_corr1d_allpairs_f32(_ptr(fmap1), _ptr(fmap2), _ptr(out), B, D, H, W1, W2, _stream(out)),
               "dv_corr1d_allpairs_f32")
     return out

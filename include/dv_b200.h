@@ -235,6 +235,10 @@ int dv_ddim_step(const dv_ddim_step_args *args, void *stream);
  * out[b,y,x1,x2] = sum_c fmap1[b,c,y,x1] * fmap2[b,c,y,x2]   ([B,H,W1,W2], no 1/sqrt(C))     */
 int dv_corr1d_allpairs_f32(const float *fmap1, const float *fmap2, float *out,
                            int64_t B, int64_t C, int64_t H, int64_t W1, int64_t W2, void *stream);
+/* the same, also writing level 1 of the correlation pyramid (geometry_ddim.py:27-30: avg_pool2d([1,2]) of `out`,
+ * pooled [B,H,W1,W2/2]) from the accumulators — bit-identical to dv_avgpool_w2_f32 applied to `out`                  */
+int dv_corr1d_allpairs_pooled_f32(const float *fmap1, const float *fmap2, float *out, float *pooled,
+                                  int64_t B, int64_t C, int64_t H, int64_t W1, int64_t W2, void *stream);
 
 /* ---- a14: pyramid helpers (geometry_ddim.py:18-30)
  * geo [B,C,D,h,w] -> geo_rows [B*h*w, C, D] (permute(0,3,4,1,2));

@@ -462,6 +462,19 @@ def test_geo_pack_and_packed_lookup_match_reference_layout(ops, shape, levels):
         assert rel_max_err(host(got), vol(disp, coords, noisy)) < VOL_TOL
 
 
+@pytest.mark.parametrize("shape", [(1, 96, 12, 312), (2, 16, 3, 37), (1, 8, 2, 64), (1, 5, 1, 2)])
+def test_corr1d_allpairs_pooled_epilogue(ops, shape):
+    """Level 1 of the correlation pyramid written from the accumulators == avg_pool2d([1,2]) of the stored level 0
+    (bit-exact), and level 0 is unchanged by the extra output."""
+    B, C, H, W = shape
+    f1, f2 = synth.normal(shape, 431), synth.normal(shape, 432)
+    plain = ops.corr1d_allpairs(cu(f1), cu(f2))
+    out, pooled = ops.corr1d_allpairs(cu(f1), cu(f2), return_pooled=True)
+    assert torch.equal(out, plain) and pooled.shape == (B, H, W, 1, W // 2)
+    assert torch.equal(pooled.reshape(B * H * W, 1, 1, W // 2), ops.avgpool_w2(out.reshape(B * H * W, 1, 1, W)))
+    assert rel_max_err(host(out), O.corr1d_allpairs(f1, f2).reshape(out.shape)) < VOL_TOL
+
+
 def test_kitti15_geo_class_matches_oracle(ops):
     """The drop-in class (packed pyramid inside) against the oracle class, both call conventions; the reference-layout
     attribute is still available."""
