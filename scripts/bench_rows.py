@@ -139,6 +139,31 @@ def main():
         R.time("f4 acv_patch_volume (2 chained depth-wise 3x3 + cat)", f"acv B={B} [B,40,48,135,240]",
                lambda: ops.acv_patch_volume(gwcv, wp, wl[:8], wl[8:24], wl[24:]), 2 * B * G * D * hw * F4)
         del gwcv
+        # the [B,48,h,w] sampler-state ops (a7, a8, a10, a11, a12, a13) as stand-alone entry points
+        x0 = ru(B, D, h, w) * 2.0 - 1.0
+        nz64, xt64 = rn(B, D, h, w, dt=torch.float64), rn(B, D, h, w, dt=torch.float64)
+        st_b = D * hw
+        R.time("a7 q_sample (fp32 x_start, fp32 noise -> fp64)", f"acv B={B} [B,48,135,240]",
+               lambda: ops.q_sample(x0, x0, 0.7, 0.7), B * st_b * (4 + 4 + 8))
+        R.time("a8 predict_noise_from_start (fp64)", f"acv B={B}", lambda: ops.predict_noise_from_start(xt64, x0, 1.5, 1.1),
+               B * st_b * (8 + 4 + 8))
+        dq = ru(B, h, w) * 47.75
+        R.time("a10 xstart_from_disp", f"acv B={B}", lambda: ops.xstart_from_disp(dq, D, 1.0), B * (hw + st_b) * F4)
+        dfull = ru(B, 540, 960) * 191.0
+        R.time("a10 downsample_bilinear (x1/4, clamp, /4)", f"acv B={B} 540x960", lambda: ops.downsample_bilinear(dfull, (h, w), clamp=(0, 191), post_scale=0.25),
+               B * (540 * 960 // 4 + hw) * F4, note="reads the 2x2 centre of every 4x4 block")
+        R.time("a9 filter_factor (fp64 x_t -> fp32 n)", f"acv B={B}", lambda: ops.filter_factor(xt64, shift, 1.0), B * st_b * (8 + 4))
+        R.time("a4 att_softmax", f"acv B={B}", lambda: ops.att_softmax(att), 2 * B * st_b * F4)
+        maps = [ru(B, 540, 960) for _ in range(6)]
+        R.time("a13 ensemble (6 maps)", f"acv B={B} 540x960", lambda: ops.ensemble(maps, [0.5, 0.0, 0.0, 0.0, 0.2, 0.3]),
+               7 * B * 540 * 960 * F4)
+        vote, mask = ru(B, 540, 960).round(), torch.zeros(B, h, w, device=dev)
+        R.time("a8+a10+a11+a12 ddim_step (fp64 state, re-noise)", f"acv B={B}",
+               lambda: ops.ddim_step(disp=dfull, xt=xt64, shift=shift, scale=1.0, sqrt_recip=1.5, sqrt_recipm1=1.1, last_step=False,
+                                     disp_clamp_hi=191.0, vote=vote, mask=mask, sqrt_alpha_next=0.8, c=0.3, sigma=0.5,
+                                     step_noise=nz64, renoise=nz64, shift_next=shift, want_n_next=True),
+               B * (2 * 540 * 960 * F4 // 4 * 2 + st_b * (8 + 8 + 8 + 4 + 8 + 4)))
+        del maps, dfull, vote, x0, nz64, xt64
         cq = rn(B, 1, D, h, w) * 4.0
         R.time("f2 upsample_softmax_regress", f"acv B={B} [B,1,48,135,240]->540x960",
                lambda: ops.upsample_softmax_regress(cq, (192, 540, 960)), B * (D * hw + 540 * 960) * F4,
