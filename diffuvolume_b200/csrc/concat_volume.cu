@@ -333,6 +333,33 @@ att_softmax_kernel(const float *__restrict__ att, float *__restrict__ wts, int D
         *reinterpret_cast<float4 *>(wp + static_cast<int64_t>(d) * HW) = o;
     }
 }
+// D known at compile time: thread = one pixel, the D logits are loaded ONCE (D independent coalesced loads in flight) and
+// stay in registers for the max / exp-sum / normalise passes — the three-pass kernel above issues 3 D dependent loads per
+// thread with 14 warps per SM and ran at 2 TB/s.  Same arithmetic in the same order (exp(v - max) / sum, sum accumulated in
+// d order), so the result is bit-identical.
+template <int DT>
+__global__ void __launch_bounds__(128)
+att_softmax_reg_kernel(const float *__restrict__ att, float *__restrict__ wts, int HW) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const float *ap = att + static_cast<int64_t>(b) * DT * HW + p;
+    float *wp = wts + static_cast<int64_t>(b) * DT * HW + p;
+    float v[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) v[d] = __ldg(ap + static_cast<int64_t>(d) * HW);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) mx = fmaxf(mx, v[d]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+        v[d] = expf(v[d] - mx);
+        sum += v[d];
+    }
+#pragma unroll
+    for (int d = 0; d < DT; ++d) wp[static_cast<int64_t>(d) * HW] = v[d] / sum;
+}
 __global__ void att_softmax_generic_kernel(const float *__restrict__ att, float *__restrict__ wts, int D, int HW,
                                            int64_t total) {
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -358,6 +385,36 @@ __global__ void filter_factor_kernel(const XT *__restrict__ xt, const float *__r
         const XT n = filter_n<XT>(xt[idx], shift ? shift[bd] : 0.0f, scale);
         if (nf) nf[idx] = static_cast<float>(n);
         if (n_native) n_native[idx] = n;
+    }
+}
+
+// 4 consecutive pixels of one (b, d) plane per thread, (b, d) in blockIdx.y: no 64-bit division, 128-bit accesses
+template <typename XT>
+__global__ void __launch_bounds__(256)
+filter_factor_quad_kernel(const XT *__restrict__ xt, const float *__restrict__ shift, XT scale, float *__restrict__ nf,
+                          XT *__restrict__ n_native, int HW) {
+    const int bd = blockIdx.y;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (p >= HW) return;
+    const float sh = shift ? __ldg(shift + bd) : 0.0f;
+    const int64_t o = static_cast<int64_t>(bd) * HW + p;
+    XT x[4];
+    if constexpr (sizeof(XT) == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(xt + o));
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+        const double2 a = *reinterpret_cast<const double2 *>(xt + o), b = *reinterpret_cast<const double2 *>(xt + o + 2);
+        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+    }
+    XT n[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) n[i] = filter_n<XT>(x[i], sh, scale);
+    if (nf)
+        *reinterpret_cast<float4 *>(nf + o) = make_float4(static_cast<float>(n[0]), static_cast<float>(n[1]),
+                                                          static_cast<float>(n[2]), static_cast<float>(n[3]));
+    if (n_native) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n_native[o + i] = n[i];
     }
 }
 
@@ -487,7 +544,10 @@ extern "C" int dv_att_softmax_f32(const float *att_logits, float *weights, int64
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
     const int64_t HW = H * W;
     if (HW > INT32_MAX || B > 65535 || D > INT32_MAX) return DV_ERR_BAD_SHAPE;
-    if ((HW % 4 == 0) && aligned16(att_logits) && aligned16(weights)) {
+    if (D == 48 && tune_variant("DV_ATT_REG", 1)) {          // every reference configuration: maxdisp / 4
+        dim3 grid(static_cast<unsigned>((HW + 127) / 128), static_cast<unsigned>(B));
+        att_softmax_reg_kernel<48><<<grid, 128, 0, st>>>(att_logits, weights, static_cast<int>(HW));
+    } else if ((HW % 4 == 0) && aligned16(att_logits) && aligned16(weights)) {
         dim3 grid(static_cast<unsigned>((HW / 4 + 127) / 128), static_cast<unsigned>(B));
         att_softmax_kernel<<<grid, 128, 0, st>>>(att_logits, weights, static_cast<int>(D), static_cast<int>(HW));
     } else {
@@ -509,6 +569,17 @@ extern "C" int dv_filter_factor(const void *xt, int xt_is_f64, const float *shif
     const int64_t HW = H * W;
     if (HW > INT32_MAX) return DV_ERR_BAD_SHAPE;
     const int64_t total = B * D * HW;
+    auto al = [](const void *p, uintptr_t m) { return !p || (reinterpret_cast<uintptr_t>(p) & m) == 0; };
+    if (HW % 4 == 0 && B * D <= 65535 && al(xt, 15) && al(n_out_f32, 15) && al(n_out_native, 15) && tune_variant("DV_FF_QUAD", 1)) {
+        dim3 qgrid(static_cast<unsigned>((HW / 4 + 255) / 256), static_cast<unsigned>(B * D));
+        if (xt_is_f64)
+            filter_factor_quad_kernel<double><<<qgrid, 256, 0, st>>>(static_cast<const double *>(xt), shift, scale, n_out_f32,
+                                                                   static_cast<double *>(n_out_native), static_cast<int>(HW));
+        else
+            filter_factor_quad_kernel<float><<<qgrid, 256, 0, st>>>(static_cast<const float *>(xt), shift, static_cast<float>(scale),
+                                                                  n_out_f32, static_cast<float *>(n_out_native), static_cast<int>(HW));
+        return finish_launch();
+    }
     const int64_t blocks = (total + 255) / 256;
     const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 16 ? blocks : static_cast<int64_t>(kNumSMs) * 16);
     if (xt_is_f64)
