@@ -386,6 +386,13 @@ static int launch_gwc_kchunk(const float *ref, const float *tgt, float *out, int
 static int dispatch_gwc_kchunk(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int G,
                                int cpg, int Dtot, int dofs, cudaStream_t st) {
     constexpr int KC = 8, DC = 12, SQ = 64;
+    // 24 < D <= 32 (the +-24 refinement volume: D = 25): one 28-wide (or two 16-wide) disparity chunks instead of three 12-wide
+    // ones, the third of which would hold a single plane — the kernel is shared-memory-bandwidth bound (5 LDS.128 per 48 FMA
+    // per thread and chunk), and the wide tile needs 9 LDS.128 per 112 FMA: 0.190 -> 0.137 ms at B = 4, 384x1248.
+    // (The same widening does nothing for the cpg = 8, D = 48 volume, which is not LDS-bound: measured 0.463 vs 0.456 ms.)
+    const int wide = tune_variant("DV_KCHUNK_WIDE", 28);
+    if (D > 24 && D <= 28 && wide == 28) return launch_gwc_kchunk<KC, 28, SQ, 1, 4>(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+    if (D > 24 && D <= 32 && wide != 0) return launch_gwc_kchunk<KC, 16, SQ, 2, 3>(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
     const int nch = (D + DC - 1) / DC;
     switch (nch) {
         case 1: return launch_gwc_kchunk<KC, DC, SQ, 1, 8>(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
