@@ -204,7 +204,13 @@ def main():
         cost = rn(B, 192, 384, 1248) * 4.0
         R.time("a6 softmax_regress (disp only)", f"pcw B={B} [B,192,384,1248]", lambda: ops.softmax_regress(cost),
                B * 193 * 384 * 1248 * F4)
-        del cost
+        usedp = ru(B, 384, 1248) * 191.0
+        R.time("a6 softmax_regress (+ prob volume out, the tier-2 model_predictions boundary)", f"pcw B={B}",
+               lambda: ops.softmax_regress(cost, return_prob=True), B * (2 * 192 + 1) * 384 * 1248 * F4)
+        rr = ops.softmax_regress(cost, return_prob=True)
+        R.time("a11 uncertainty_vote (refined disparity vs prob volume)", f"pcw B={B}",
+               lambda: ops.uncertainty_vote(rr["disp"], rr["prob"], usedp, 1.0, 1.0), B * (192 + 3) * 384 * 1248 * F4)
+        del cost, rr, usedp
 
     # ---------------- configs[3]: IGEV 384x1248 (1/4 = 96x312) --------------------------------------------------
     if want("igev"):
