@@ -275,9 +275,9 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 2), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]/[4]: gwc G=40 D=48 @135x240 + concat/ACV + T=5 DDIM filter + "
-                                   + ("softmax/regression over [B,192,540,960]" if args.regress == "logits" else
-                                      "trilinear x4 upsample fused into softmax/regression (input [B,1,48,135,240])"),
+            "config": {"workload": f"configs[1]/[4]: gwc G=40 D=48 @{H // 4}x{W // 4} + concat/ACV + T=5 DDIM filter + "
+                                   + (f"softmax/regression over [B,192,{H},{W}]" if args.regress == "logits" else
+                                      f"trilinear x4 upsample fused into softmax/regression (input [B,1,48,{H // 4},{W // 4}])"),
                        "pairs_per_gpu": B, "global_batch": B * world, "filter_mode": args.filter, "regress": args.regress,
                        "l2": "inputs larger than L2 (3.2 GB logits, 3.2 GB volumes per step)",
                        "parallelism": f"batch-sharded x{world}"},
@@ -484,7 +484,7 @@ def cpu_reference(steps: int, warmup: int, regress: str = "logits"):
             ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
     return {"value": round(1.0 / sec, 4), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} x 1 pair (B=1, all T=5 steps, 540x960 D=192{'' if regress == 'logits' else ', incl. F.upsample trilinear per step'}), "
+            "sample": f"{steps} x 1 pair (B=1, all T=5 steps, {H}x{W} D=192{'' if regress == 'logits' else ', incl. F.upsample trilinear per step'}), "
                       f"torch CPU op-for-op port of the reference (oracle/torch_port.py), {sec:.2f} s/pair",
             "seconds_per_pair": round(sec, 3)}
 
@@ -518,6 +518,9 @@ def main():
                     help="logits: softmax/regression reads the full-res [B,192,H,W] logits (the metric's op boundary); "
                          "fused: trilinear x4 upsample fused in, input [B,1,48,h,w] (SURVEY.md 8f row f2)")
     ap.add_argument("--no-fused", action="store_true", help="skip the extra fused-upsample measurement")
+    ap.add_argument("--size", default="540x960",
+                    help="full-resolution HxW of the synthetic pairs (multiples of 4): 540x960 is BASELINE.json's metric; "
+                         "384x1248 (KITTI, 376 padded) is the north_star's second resolution")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay leg")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -525,6 +528,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     protect_stdout()
+    global H, W, METRIC
+    H, W = (int(v) for v in args.size.lower().split("x"))
+    if H % 4 or W % 4 or H <= 0 or W <= 0:
+        raise SystemExit("--size HxW must be positive multiples of 4")
+    if (H, W) != (540, 960):
+        METRIC = f"volume+DDIM-filter pairs/s @{H}x{W} D=192"
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
