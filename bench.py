@@ -363,7 +363,9 @@ def run_ours(args):
         if fused is not None:
             result["fused_upsample"] = fused
         if world == 1 and not args.no_cpu_baseline:
-            result["cpu_baseline"] = cpu_reference(steps=args.cpu_steps, warmup=1, regress=args.regress)
+            cb, cpu_in, cpu_pred0, cpu_out = cpu_reference(steps=args.cpu_steps, warmup=1, regress=args.regress, keep_io=True)
+            result["cpu_baseline"] = cb
+            result["parity"] = parity_against_cpu_leg(cpu_in, cpu_pred0, cpu_out, args.filter, args.regress, dev)
         emit(result)
     if dist is not None:
         dist.destroy_process_group()
@@ -455,8 +457,9 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(steps: int, warmup: int, regress: str = "logits"):
-    """The reference's op sequence on the host CPU (oracle/torch_port.py), one pair (B=1) per step."""
+def cpu_reference(steps: int, warmup: int, regress: str = "logits", keep_io: bool = False):
+    """The reference's op sequence on the host CPU (oracle/torch_port.py), one pair (B=1) per step.  keep_io: also return
+    the leg's inputs and its outputs, so that the GPU path can be checked against what this leg computed."""
     from oracle import dv_oracle as O
     from oracle import torch_port as P
     ncpu = os.cpu_count() or 1
@@ -469,10 +472,13 @@ def cpu_reference(steps: int, warmup: int, regress: str = "logits"):
              att_logits=rn(1, 1, D, h, w),
              costs=([rn(1, MAXDISP, H, W) * 4.0] if regress == "logits" else [rn(1, 1, D, h, w) * 4.0]) * T_STEPS,
              used=torch.rand(1, H, W, generator=g) * 191.0,
-             asd=P.xstart_from_pred(torch.rand(1, H, W, generator=g) * 191.0),
+             asd=None,
+
              shifts=[rn(1, D) * 0.1 for _ in range(T_STEPS)],
              step_noises=[rn(1, D, h, w, dt=torch.float32 if i == 0 else torch.float64) for i in range(T_STEPS - 1)],
              renoises=[torch.rand(1, D, h, w, generator=g, dtype=torch.float64) for _ in range(T_STEPS - 1)])
+    pred0 = torch.rand(1, H, W, generator=g) * 191.0          # the origin model's disparity the sampler starts from
+    a["asd"] = P.xstart_from_pred(pred0)
     up = None if regress == "logits" else (MAXDISP, H, W)
     with torch.no_grad():
         for _ in range(warmup):
@@ -480,13 +486,40 @@ def cpu_reference(steps: int, warmup: int, regress: str = "logits"):
         ts = []
         for _ in range(steps):
             t0 = time.perf_counter()
-            P.hot_path_pair(**a, sched=sched, upsample_to=up)
+            out = P.hot_path_pair(**a, sched=sched, upsample_to=up)
             ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
+    res = _cpu_result(steps, sec, regress)
+    return (res, a, pred0, out) if keep_io else res
+
+
+def _cpu_result(steps, sec, regress):
     return {"value": round(1.0 / sec, 4), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{steps} x 1 pair (B=1, all T=5 steps, {H}x{W} D=192{'' if regress == 'logits' else ', incl. F.upsample trilinear per step'}), "
                       f"torch CPU op-for-op port of the reference (oracle/torch_port.py), {sec:.2f} s/pair",
             "seconds_per_pair": round(sec, 3)}
+
+
+def parity_against_cpu_leg(a, pred0, cpu_out, filter_mode, regress, dev):
+    """The fused GPU path on the very inputs the cpu_baseline leg just ran (B = 1, full size), compared with that leg's
+    outputs: SURVEY.md §8d "parity gates reported with every timing" (volume max rel error, disparity EPE in px)."""
+    from diffuvolume_b200 import ops
+    from diffuvolume_b200.pipeline import AcvHotPath
+    cpu_pred, (cpu_gwc, _, cpu_mask) = cpu_out
+    to = lambda t: t.to(dev)
+    h, w = H // 4, W // 4
+    disp_q = ops.downsample_bilinear(to(pred0), (h, w), clamp=(0, MAXDISP - 1), post_scale=0.25)
+    path = AcvHotPath(filter_mode=filter_mode, regress_mode="logits" if regress == "logits" else "fused_upsample")
+    out = path(to(a["feat_l"]), to(a["feat_r"]), to(a["cfeat_l"]), to(a["cfeat_r"]), to(a["att_logits"]), [to(a["costs"][0])],
+               to(a["used"]), disp_q, [to(t) for t in a["shifts"]], [to(t) for t in a["step_noises"]],
+               [to(t) for t in a["renoises"]], keep_volumes=True)
+    err = (out["pred"].cpu() - cpu_pred).abs()
+    gwc = out["gwc"].cpu()
+    return {"epe_px": float(err.mean()), "max_err_px": float(err.max()),
+            "gwc_volume_max_rel_err": float((gwc - cpu_gwc).abs().max() / cpu_gwc.abs().max()),
+            "renewal_mask_agreement": float((out["mask"].cpu() == cpu_mask).float().mean()),
+            "gates": {"epe_px": 0.01, "volume_max_rel_err": 1e-4},
+            "checker": "the cpu_baseline leg's own outputs (oracle/torch_port.py on the host), same inputs, B=1"}
 
 
 def run_reference(args):
