@@ -127,3 +127,40 @@ def test_shard_range_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_fuse_acv_patch_is_transparent_on_cpu_and_restores_classes():
+    """install.fuse_acv_patch re-classes the four Conv3d instances; off the GPU (or with autograd on) the original
+    convolutions run, state_dict keys are untouched, and uninstall() restores the original classes."""
+    import torch
+    from diffuvolume_b200 import install
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            nn = torch.nn
+            self.patch = nn.Conv3d(40, 40, kernel_size=(1, 3, 3), stride=1, dilation=1, groups=40, padding=(0, 1, 1), bias=False)
+            self.patch_l1 = nn.Conv3d(8, 8, kernel_size=(1, 3, 3), stride=1, dilation=1, groups=8, padding=(0, 1, 1), bias=False)
+            self.patch_l2 = nn.Conv3d(16, 16, kernel_size=(1, 3, 3), stride=1, dilation=2, groups=16, padding=(0, 2, 2), bias=False)
+            self.patch_l3 = nn.Conv3d(16, 16, kernel_size=(1, 3, 3), stride=1, dilation=3, groups=16, padding=(0, 3, 3), bias=False)
+
+        def forward(self, v):
+            v = self.patch(v)
+            return torch.cat((self.patch_l1(v[:, :8]), self.patch_l2(v[:, 8:24]), self.patch_l3(v[:, 24:40])), dim=1)
+
+    torch.manual_seed(0)
+    net = Net().eval()
+    x = torch.randn(1, 40, 2, 6, 9)
+    with torch.no_grad():
+        want = net(x)
+    keys, classes = sorted(net.state_dict()), [type(m) for m in (net.patch, net.patch_l1, net.patch_l2, net.patch_l3)]
+    assert install.fuse_acv_patch(net)
+    try:
+        assert sorted(net.state_dict()) == keys
+        assert isinstance(net.patch, torch.nn.Conv3d) and type(net.patch) is not classes[0]
+        with torch.no_grad():
+            assert torch.equal(net(x), want)                     # CPU tensors: the cuDNN/ATen path, no CUDA needed
+    finally:
+        install.uninstall()
+    assert [type(m) for m in (net.patch, net.patch_l1, net.patch_l2, net.patch_l3)] == classes
+    assert not install.fuse_acv_patch(torch.nn.Linear(2, 2))     # nothing to fuse
