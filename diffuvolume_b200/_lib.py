@@ -80,11 +80,11 @@ SIGNATURES = {
     "dv_att_softmax_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _P]),
     "dv_filter_factor_f32": (_I, [_P, _I, _P, _D, _P, _I64, _I64, _I64, _I64, _P]),
     "dv_filter_factor": (_I, [_P, _I, _P, _D, _P, _P, _I64, _I64, _I64, _I64, _P]),
-    "dv_concat_volume_weighted_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P]),
-    "dv_concat_volume_weighted_bf16": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P]),
+    "dv_concat_volume_weighted_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P, _P]),
+    "dv_concat_volume_weighted_bf16": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P, _P]),
     "dv_volume_filter_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _I64, _P, _I, _P, _D, _P, _P]),
     "dv_corr_volume_2sided_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
-    "dv_softmax_regress_f32": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _F, _F, _P, _F, _I, _P]),
+    "dv_softmax_regress_f32": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _F, _F, _P, _F, _I, _P, _P]),
     "dv_upsample_softmax_regress_f32": (_I, [_P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P, _P, _F, _F, _P, _F, _I, _P]),
     "dv_uncertainty_vote_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _F, _F, _P, _P, _P]),
     "dv_disparity_regression_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _P]),

@@ -17,15 +17,32 @@ inline int finish_launch(int nlaunches = 1) {
     return cudaGetLastError() == cudaSuccess ? DV_OK : DV_ERR_LAUNCH;
 }
 
-// Kernel-variant switches for tuning runs (scripts/tune_kernels.py); unset = the shipped default.
-inline int tune_variant(const char *name, int dflt) {
+// Kernel-variant switches for tuning runs (scripts/tune_kernels.py); unset = the shipped default.  The environment is
+// read ONCE per process and call site (function-local static), never on the launch path.
+inline int read_env_int(const char *name, int dflt) {
     const char *v = std::getenv(name);
     return v ? std::atoi(v) : dflt;
 }
+#define DV_TUNE(name, dflt)                                      \
+    ([&]() -> int {                                              \
+        static const int dv_tune_v = ::dv::read_env_int(name, dflt); \
+        return dv_tune_v;                                        \
+    }())
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// SM count of the current device (B200: 148 = 2 dies x 74), queried once per device ordinal.
+inline int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 
 // ---- mbarrier + bulk async copy (TMA engine, SASS: UBLKCP / SYNCS) --------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -196,6 +213,6 @@ __device__ __forceinline__ double div_by_const(double x, double b, double inv) {
 
 // concat_stream.cu: TMA-fed streaming producer; DV_ERR_UNSUPPORTED when tensor maps cannot be built
 int launch_concat_stream(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int mask_left,
-                         const float *wts, const float *nf, cudaStream_t st);
+                         const float *wts, const float *nf, int *tile_counters, cudaStream_t st);
 
 }  // namespace dv

@@ -32,8 +32,11 @@ constexpr int kCsConsumerWarps = kCsDC / 4;   // 12: one warp per group of 4 dis
 constexpr int kCsThreads = 32 * (kCsConsumerWarps + 1);
 constexpr int kCsSlots = 256;      // concurrent launches per device that may share the counter pool
 
-static __device__ int g_cs_next[kCsSlots];
-static __device__ int g_cs_done[kCsSlots];
+// Tile counters {next, done}.  The caller normally owns them (the `tile_counters` argument of the C-ABI: 2 zeroed ints in
+// device memory, one pair per stream that may run this kernel concurrently; the kernel re-arms them to zero before it
+// exits).  With tile_counters == NULL the launch draws a pair from this library-owned pool round-robin: at most
+// kCsSlots launches of this kernel may then overlap on a device, and a captured CUDA graph keeps its slot forever.
+static __device__ int g_cs_ctr[kCsSlots][2];
 static std::atomic<unsigned> g_cs_slot{0};
 
 template <int CGT>
@@ -48,13 +51,14 @@ __global__ void __launch_bounds__(kCsThreads, MINB)
 concat_stream_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_n,
                      const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_tgt,
                      OutT *__restrict__ out, int C, int HW, int W, int D, int mask_left, int spans, int ndchunks,
-                     int ntiles, int slot, int sync_tiles) {
+                     int ntiles, int *ctr_arg, int slot, int sync_tiles) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t full_bar[kCsStages], empty_bar[kCsStages];
     __shared__ int tile_id[kCsStages];
     constexpr int kStageFloats = CsStage<CGT>::kFloats;
     constexpr int kFactor = CsStage<CGT>::kFactor;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *const ctr = ctr_arg ? ctr_arg : g_cs_ctr[slot];
     const int ngroups = (2 * C) / CGT;
     const int dcbox = D < kCsDC ? D : kCsDC;     // rows of the factor boxes
 
@@ -74,14 +78,14 @@ concat_stream_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         for (int it = 0;; ++it) {
             const int s = it % kCsStages, k = it / kCsStages;
             if (k > 0) mbar_wait(&empty_bar[s], (k & 1) ^ 1);
-            const int t = atomicAdd(&g_cs_next[slot], 1);
+            const int t = atomicAdd(&ctr[0], 1);
             if (t >= ntiles) {
                 tile_id[s] = -1;
                 mbar_arrive(&full_bar[s]);
                 // the last CTA to run dry re-arms the counter pair for the next launch that draws this slot
-                if (atomicAdd(&g_cs_done[slot], 1) == static_cast<int>(gridDim.x) - 1) {
-                    g_cs_next[slot] = 0;
-                    g_cs_done[slot] = 0;
+                if (atomicAdd(&ctr[1], 1) == static_cast<int>(gridDim.x) - 1) {
+                    ctr[0] = 0;
+                    ctr[1] = 0;
                     __threadfence();
                 }
                 return;
@@ -184,7 +188,7 @@ concat_stream_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 
 template <int CGT, bool HAS_W, bool HAS_N, int STAGES, int MINB, typename OutT>
 static int launch_cs2(const CUtensorMap &mw, const CUtensorMap &mn, const CUtensorMap &mr, const CUtensorMap &mt, OutT *out,
-                      int B, int C, int HW, int W, int D, int mask_left, cudaStream_t st) {
+                      int B, int C, int HW, int W, int D, int mask_left, int *ctr, cudaStream_t st) {
     const size_t smem = sizeof(float) * STAGES * CsStage<CGT>::kFloats;
     auto kern = concat_stream_kernel<CGT, HAS_W, HAS_N, STAGES, MINB, OutT>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
@@ -192,30 +196,30 @@ static int launch_cs2(const CUtensorMap &mw, const CUtensorMap &mn, const CUtens
     const int spans = (HW + kCsSpan - 1) / kCsSpan;
     const int ndchunks = (D + kCsDC - 1) / kCsDC;
     const int64_t ntiles = static_cast<int64_t>(B) * ((2 * C) / CGT) * ndchunks * spans;
-    if (ntiles > INT32_MAX - 4 * kNumSMs) return DV_ERR_UNSUPPORTED;
-    const int grid = static_cast<int>(ntiles < MINB * kNumSMs ? ntiles : MINB * kNumSMs);
+    if (ntiles > INT32_MAX - 4 * num_sms()) return DV_ERR_UNSUPPORTED;
+    const int grid = static_cast<int>(ntiles < MINB * num_sms() ? ntiles : MINB * num_sms());
     const int slot = static_cast<int>(g_cs_slot.fetch_add(1, std::memory_order_relaxed) % kCsSlots);
     kern<<<grid, kCsThreads, smem, st>>>(mw, mn, mr, mt, out, C, HW, W, D, mask_left, spans, ndchunks,
-                                        static_cast<int>(ntiles), slot, tune_variant("DV_CS_BAR", 1));
+                                        static_cast<int>(ntiles), ctr, slot, DV_TUNE("DV_CS_BAR", 1));
     return finish_launch();
 }
 template <int CGT, bool HAS_W, bool HAS_N>
 static int launch_cs(const CUtensorMap &mw, const CUtensorMap &mn, const CUtensorMap &mr, const CUtensorMap &mt, float *out,
-                     int B, int C, int HW, int W, int D, int mask_left, cudaStream_t st) {
-    const int v = tune_variant("DV_CS_SHAPE", 21);   // stages*10 + CTAs per SM
-    if (v == 22) return launch_cs2<CGT, HAS_W, HAS_N, 2, 2, float>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st);
-    if (v == 31) return launch_cs2<CGT, HAS_W, HAS_N, 3, 1, float>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st);
-    return launch_cs2<CGT, HAS_W, HAS_N, 2, 1, float>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st);
+                     int B, int C, int HW, int W, int D, int mask_left, int *ctr, cudaStream_t st) {
+    const int v = DV_TUNE("DV_CS_SHAPE", 21);   // stages*10 + CTAs per SM
+    if (v == 22) return launch_cs2<CGT, HAS_W, HAS_N, 2, 2, float>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st);
+    if (v == 31) return launch_cs2<CGT, HAS_W, HAS_N, 3, 1, float>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st);
+    return launch_cs2<CGT, HAS_W, HAS_N, 2, 1, float>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st);
 }
 
 // Returns DV_ERR_UNSUPPORTED when the tensor maps cannot be built (the caller then takes the LDG kernel).
 int launch_concat_stream(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int mask_left,
-                         const float *wts, const float *nf, cudaStream_t st) {
+                         const float *wts, const float *nf, int *ctr, cudaStream_t st) {
     CUtensorMap mw, mn, mr, mt;
     const uint64_t fdims[3] = {static_cast<uint64_t>(HW), static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
     const uint32_t fbox[3] = {kCsSpan, static_cast<uint32_t>(D < kCsDC ? D : kCsDC), 1u};
     const uint64_t cdims[3] = {static_cast<uint64_t>(HW), static_cast<uint64_t>(C), static_cast<uint64_t>(B)};
-    int cgt = tune_variant("DV_CS_CGT", 8);
+    int cgt = DV_TUNE("DV_CS_CGT", 8);
     while (cgt > 1 && C % cgt != 0) cgt /= 2;
     const uint32_t lbox[3] = {kCsSpan, static_cast<uint32_t>(cgt), 1u};
     const uint32_t rbox[3] = {kCsWin, static_cast<uint32_t>(cgt), 1u};
@@ -227,10 +231,10 @@ int launch_concat_stream(const float *ref, const float *tgt, float *out, int B, 
     if (wts && !make_tensor_map_f32(&mw, wts, 3, fdims, fbox)) return DV_ERR_UNSUPPORTED;
     if (nf && !make_tensor_map_f32(&mn, nf, 3, fdims, fbox)) return DV_ERR_UNSUPPORTED;
 #define DV_CS(CG)                                                                                              \
-    (wts && nf ? launch_cs<CG, true, true>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st)                  \
-     : wts     ? launch_cs<CG, true, false>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st)                 \
-     : nf      ? launch_cs<CG, false, true>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st)                 \
-               : launch_cs<CG, false, false>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st))
+    (wts && nf ? launch_cs<CG, true, true>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st)                  \
+     : wts     ? launch_cs<CG, true, false>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st)                 \
+     : nf      ? launch_cs<CG, false, true>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st)                 \
+               : launch_cs<CG, false, false>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st))
     switch (cgt) {
         case 16: return DV_CS(16);
         case 8: return DV_CS(8);
@@ -243,7 +247,7 @@ int launch_concat_stream(const float *ref, const float *tgt, float *out, int B, 
 
 // bf16 volume: the same producer with one rounding at the store (channel groups of 8 or 4 only)
 int launch_concat_stream_bf16(const float *ref, const float *tgt, __nv_bfloat16 *out, int B, int C, int HW, int W, int D,
-                              int mask_left, const float *wts, const float *nf, cudaStream_t st) {
+                              int mask_left, const float *wts, const float *nf, int *ctr, cudaStream_t st) {
     CUtensorMap mw, mn, mr, mt;
     const uint64_t fdims[3] = {static_cast<uint64_t>(HW), static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
     const uint32_t fbox[3] = {kCsSpan, static_cast<uint32_t>(D < kCsDC ? D : kCsDC), 1u};
@@ -260,10 +264,10 @@ int launch_concat_stream_bf16(const float *ref, const float *tgt, __nv_bfloat16 
     if (wts && !make_tensor_map_f32(&mw, wts, 3, fdims, fbox)) return DV_ERR_UNSUPPORTED;
     if (nf && !make_tensor_map_f32(&mn, nf, 3, fdims, fbox)) return DV_ERR_UNSUPPORTED;
 #define DV_CSB(CG)                                                                                                          \
-    (wts && nf ? launch_cs2<CG, true, true, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st)        \
-     : wts     ? launch_cs2<CG, true, false, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st)       \
-     : nf      ? launch_cs2<CG, false, true, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st)       \
-               : launch_cs2<CG, false, false, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, st))
+    (wts && nf ? launch_cs2<CG, true, true, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st)        \
+     : wts     ? launch_cs2<CG, true, false, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st)       \
+     : nf      ? launch_cs2<CG, false, true, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st)       \
+               : launch_cs2<CG, false, false, 2, 1, __nv_bfloat16>(mw, mn, mr, mt, out, B, C, HW, W, D, mask_left, ctr, st))
     return cgt == 8 ? DV_CSB(8) : DV_CSB(4);
 #undef DV_CSB
 }
@@ -272,7 +276,7 @@ int launch_concat_stream_bf16(const float *ref, const float *tgt, __nv_bfloat16 
 
 extern "C" int dv_concat_volume_weighted_bf16(const float *ref, const float *tgt, void *out, int64_t B, int64_t C, int64_t H,
                                               int64_t W, int64_t D, int mask_left, const float *att_weights, const float *n,
-                                              void *stream) {
+                                              void *tile_counters, void *stream) {
     using namespace dv;
     if (!ref || !tgt || !out) return DV_ERR_NULL;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return DV_ERR_BAD_SHAPE;
@@ -284,5 +288,5 @@ extern "C" int dv_concat_volume_weighted_bf16(const float *ref, const float *tgt
         return DV_ERR_MISALIGNED;
     return launch_concat_stream_bf16(ref, tgt, static_cast<__nv_bfloat16 *>(out), static_cast<int>(B), static_cast<int>(C),
                                      static_cast<int>(HW), static_cast<int>(W), static_cast<int>(D), mask_left, att_weights, n,
-                                     static_cast<cudaStream_t>(stream));
+                                     static_cast<int *>(tile_counters), static_cast<cudaStream_t>(stream));
 }

@@ -422,13 +422,13 @@ template <int CG, bool HAS_W, bool HAS_N>
 static int launch_weighted(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D,
                            int mask_left, const float *wts, const float *nf, cudaStream_t st) {
     dim3 grid((HW / 4 + 31) / 32, (2 * C + CG - 1) / CG, B);
-    if (tune_variant("DV_CONCAT_V", 0) == 1) {
+    if (DV_TUNE("DV_CONCAT_V", 0) == 1) {
         int slots = (D + 3) / 4;
         if (slots > 12) slots = 12;
         concat_weighted4_kernel<CG, HAS_W, HAS_N><<<grid, 32 * slots, 0, st>>>(ref, tgt, out, C, HW, W, D, mask_left, wts, nf);
         return finish_launch();
     }
-    const int minb = tune_variant("DV_CONCAT_MINB", 4);
+    const int minb = DV_TUNE("DV_CONCAT_MINB", 4);
     if (minb == 8)
         concat_weighted_kernel<CG, HAS_W, HAS_N, 8><<<grid, 256, 0, st>>>(ref, tgt, out, C, HW, W, D, mask_left, wts, nf);
     else if (minb == 6)
@@ -487,8 +487,8 @@ static int launch_concat(const float *ref, const float *tgt, float *out, int B, 
     }
     const int spans = (HW + kConcatSpan - 1) / kConcatSpan;
     // channels per CTA: amortise the per-CTA factor build, keep >= ~8 waves of CTAs
-    int cpc = tune_variant("DV_CONCAT_CPC", HAS_N ? 16 : 8);
-    while (cpc > 8 && static_cast<int64_t>(spans) * B * ((2 * C + cpc - 1) / cpc) < 8LL * kNumSMs * 4) cpc /= 2;
+    int cpc = DV_TUNE("DV_CONCAT_CPC", HAS_N ? 16 : 8);
+    while (cpc > 8 && static_cast<int64_t>(spans) * B * ((2 * C + cpc - 1) / cpc) < 8LL * num_sms() * 4) cpc /= 2;
     dim3 grid(spans, (2 * C + cpc - 1) / cpc, B);
     kern<<<grid, kConcatThreads, smem, st>>>(ref, tgt, out, C, HW, W, D, mask_left, cpc, att, xt, xt_is_f64, shift,
                                             scale);
@@ -524,7 +524,7 @@ extern "C" int dv_concat_volume_f32(const float *ref, const float *tgt, float *o
     const int64_t total = B * 2 * C * D * HW;
     const int threads = 256;
     const int64_t blocks = (total + threads - 1) / threads;
-    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
     if (xt && xt_is_f64)
         concat_volume_generic_kernel<double><<<grid, threads, 0, st>>>(
             ref, tgt, out, static_cast<int>(C), static_cast<int>(HW), static_cast<int>(W), static_cast<int>(D), mask_left,
@@ -544,7 +544,7 @@ extern "C" int dv_att_softmax_f32(const float *att_logits, float *weights, int64
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
     const int64_t HW = H * W;
     if (HW > INT32_MAX || B > 65535 || D > INT32_MAX) return DV_ERR_BAD_SHAPE;
-    if (D == 48 && tune_variant("DV_ATT_REG", 1)) {          // every reference configuration: maxdisp / 4
+    if (D == 48 && DV_TUNE("DV_ATT_REG", 1)) {          // every reference configuration: maxdisp / 4
         dim3 grid(static_cast<unsigned>((HW + 127) / 128), static_cast<unsigned>(B));
         att_softmax_reg_kernel<48><<<grid, 128, 0, st>>>(att_logits, weights, static_cast<int>(HW));
     } else if ((HW % 4 == 0) && aligned16(att_logits) && aligned16(weights)) {
@@ -553,7 +553,7 @@ extern "C" int dv_att_softmax_f32(const float *att_logits, float *weights, int64
     } else {
         const int64_t total = B * HW;
         const int64_t blocks = (total + 255) / 256;
-        const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+        const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
         att_softmax_generic_kernel<<<grid, 256, 0, st>>>(att_logits, weights, static_cast<int>(D), static_cast<int>(HW), total);
     }
     return finish_launch();
@@ -570,7 +570,7 @@ extern "C" int dv_filter_factor(const void *xt, int xt_is_f64, const float *shif
     if (HW > INT32_MAX) return DV_ERR_BAD_SHAPE;
     const int64_t total = B * D * HW;
     auto al = [](const void *p, uintptr_t m) { return !p || (reinterpret_cast<uintptr_t>(p) & m) == 0; };
-    if (HW % 4 == 0 && B * D <= 65535 && al(xt, 15) && al(n_out_f32, 15) && al(n_out_native, 15) && tune_variant("DV_FF_QUAD", 1)) {
+    if (HW % 4 == 0 && B * D <= 65535 && al(xt, 15) && al(n_out_f32, 15) && al(n_out_native, 15) && DV_TUNE("DV_FF_QUAD", 1)) {
         dim3 qgrid(static_cast<unsigned>((HW / 4 + 255) / 256), static_cast<unsigned>(B * D));
         if (xt_is_f64)
             filter_factor_quad_kernel<double><<<qgrid, 256, 0, st>>>(static_cast<const double *>(xt), shift, scale, n_out_f32,
@@ -581,7 +581,7 @@ extern "C" int dv_filter_factor(const void *xt, int xt_is_f64, const float *shif
         return finish_launch();
     }
     const int64_t blocks = (total + 255) / 256;
-    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 16 ? blocks : static_cast<int64_t>(kNumSMs) * 16);
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 16 ? blocks : static_cast<int64_t>(num_sms()) * 16);
     if (xt_is_f64)
         filter_factor_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double *>(xt), shift, scale, n_out_f32,
                                                            static_cast<double *>(n_out_native), static_cast<int>(HW), total);
@@ -598,7 +598,7 @@ extern "C" int dv_filter_factor_f32(const void *xt, int xt_is_f64, const float *
 
 extern "C" int dv_concat_volume_weighted_f32(const float *ref, const float *tgt, float *out, int64_t B, int64_t C,
                                              int64_t H, int64_t W, int64_t D, int mask_left, const float *att_weights,
-                                             const float *n, void *stream) {
+                                             const float *n, void *tile_counters, void *stream) {
     using namespace dv;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!ref || !tgt || !out) return DV_ERR_NULL;
@@ -608,12 +608,13 @@ extern "C" int dv_concat_volume_weighted_f32(const float *ref, const float *tgt,
     auto ok16 = [](const void *p) { return !p || aligned16(p); };
     if (!((HW % 4 == 0) && W >= 4 && aligned16(ref) && aligned16(tgt) && aligned16(out) && ok16(att_weights) && ok16(n)))
         return DV_ERR_MISALIGNED;   // callers fall back to dv_concat_volume_f32 + dv_volume_filter_f32
-    if (tune_variant("DV_CONCAT_STREAM", 1)) {
+    if (DV_TUNE("DV_CONCAT_STREAM", 1)) {
         const int rc = launch_concat_stream(ref, tgt, out, static_cast<int>(B), static_cast<int>(C), static_cast<int>(HW),
-                                            static_cast<int>(W), static_cast<int>(D), mask_left, att_weights, n, st);
+                                            static_cast<int>(W), static_cast<int>(D), mask_left, att_weights, n,
+                                            static_cast<int *>(tile_counters), st);
         if (rc != DV_ERR_UNSUPPORTED) return rc;
     }
-    const int cg = tune_variant("DV_CONCAT_CG", 2);
+    const int cg = DV_TUNE("DV_CONCAT_CG", 2);
 #define DV_W(CGV)                                                                                                      \
     (att_weights && n ? launch_weighted<CGV, true, true>(ref, tgt, out, B, C, HW, W, D, mask_left, att_weights, n, st)  \
      : att_weights   ? launch_weighted<CGV, true, false>(ref, tgt, out, B, C, HW, W, D, mask_left, att_weights, n, st) \

@@ -281,8 +281,8 @@ __global__ void ensemble_kernel(const EnsembleArgs a, float *__restrict__ out, i
 
 static inline int ew_grid(int64_t n) {
     const int64_t blocks = (n + 255) / 256;
-    return static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 16 ? (blocks > 0 ? blocks : 1)
-                                                                        : static_cast<int64_t>(kNumSMs) * 16);
+    return static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 16 ? (blocks > 0 ? blocks : 1)
+                                                                        : static_cast<int64_t>(num_sms()) * 16);
 }
 
 }  // namespace dv
@@ -304,7 +304,7 @@ extern "C" int dv_ddim_step(const dv_ddim_step_args *args, void *stream) {
     if (a.xt_is_f64 != 0 && a.xt_is_f64 != 1) return DV_ERR_BAD_DTYPE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // block shape: 128x2 measured best of {32x8, 64x4, 128x2, 256x1} (scripts/bench_ddim.py); 32x8 kept as a switch
-    const int shape = tune_variant("DV_DDIM_SHAPE", 2);
+    const int shape = DV_TUNE("DV_DDIM_SHAPE", 2);
 #define DV_DDIM3(PX, DG, MODE, LAST)                                                                                   \
     {                                                                                                                \
         dim3 grid(static_cast<unsigned>((a.h * a.w + PX - 1) / PX), static_cast<unsigned>(a.B));                     \

@@ -714,7 +714,7 @@ static int corr1d_allpairs_impl(const float *fmap1, const float *fmap2, float *o
               static_cast<unsigned>(B * H));
     if (grid.y > 65535 || B * H > 65535 * 1LL) return DV_ERR_UNSUPPORTED;   // B*H = 96 per pair in every reference configuration
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (tune_variant("DV_ALLPAIRS_MMA", 1) || pooled) {
+    if (DV_TUNE("DV_ALLPAIRS_MMA", 1) || pooled) {
         corr1d_allpairs_mma_kernel<<<grid, 128, 0, st>>>(fmap1, fmap2, out, pooled, static_cast<int>(C), static_cast<int>(H),
                                                          static_cast<int>(W1), static_cast<int>(W2));
         return finish_launch();
@@ -754,7 +754,7 @@ extern "C" int dv_avgpool_w2_f32(const float *rows, float *pooled, int64_t N, in
     if (N <= 0 || L < 2 || L > INT32_MAX) return DV_ERR_BAD_SHAPE;
     const int64_t total = N * (L / 2);
     const int64_t blocks = (total + 255) / 256;
-    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 16 ? blocks : static_cast<int64_t>(kNumSMs) * 16);
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 16 ? blocks : static_cast<int64_t>(num_sms()) * 16);
     if (L % 2 == 0 && (reinterpret_cast<uintptr_t>(rows) & 7u) == 0)
         avgpool_w2_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, pooled, N, static_cast<int>(L));
     else
@@ -844,12 +844,12 @@ extern "C" int dv_geo_lookup_packed_f32(const float *const *geo_pyr, const float
         a.rcpW[i] = wm1 > 0 ? 1.0f / static_cast<float>(wm1) : 0.0f;
         if (i < num_levels && (dm1 > 4096 || wm1 > 4096)) small_divisors = false;  // range div_by_rcp was verified on
     }
-    if (al16 && C == 8 && radius == 4 && small_divisors && !noisy && tune_variant("DV_GEO_WINDOW", 1)) {  // IGEV
+    if (al16 && C == 8 && radius == 4 && small_divisors && !noisy && DV_TUNE("DV_GEO_WINDOW", 1)) {  // IGEV
         const int64_t wblocks = (a.N + 63) / 64;  // 64 pixels x 2 lanes per block
         if (wblocks > INT32_MAX) return DV_ERR_BAD_SHAPE;
         const size_t smem = 0;
         const dim3 wgrid(static_cast<unsigned>(wblocks), static_cast<unsigned>(num_levels));
-        const int minb = tune_variant("DV_GEO_MINB", 6);
+        const int minb = DV_TUNE("DV_GEO_MINB", 6);
         if (minb == 4) geo_lookup_window_kernel<2, 4, 4><<<wgrid, 128, smem, st>>>(a);
         else if (minb == 8) geo_lookup_window_kernel<2, 4, 8><<<wgrid, 128, smem, st>>>(a);
         else geo_lookup_window_kernel<2, 4, 6><<<wgrid, 128, smem, st>>>(a);
@@ -876,7 +876,7 @@ extern "C" int dv_geo_filter_packed_f32(const float *const *rows_in, const float
     a.noisy = noisy; a.C = static_cast<int>(C); a.D = static_cast<int>(D); a.levels = num_levels; a.N = N;
     const int64_t work = (N * D * C + 3) / 4;
     const int64_t blocks = (work + 255) / 256;
-    const unsigned gx = static_cast<unsigned>(blocks < static_cast<int64_t>(kNumSMs) * 16 ? blocks : static_cast<int64_t>(kNumSMs) * 16);
+    const unsigned gx = static_cast<unsigned>(blocks < static_cast<int64_t>(num_sms()) * 16 ? blocks : static_cast<int64_t>(num_sms()) * 16);
     geo_filter_packed_kernel<<<dim3(gx, static_cast<unsigned>(num_levels)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return finish_launch();
 }

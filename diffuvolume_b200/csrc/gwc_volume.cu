@@ -56,20 +56,27 @@ gwc_volume_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, 
         float *sR = sL + CPG * SPAN;  // element Dpad of a row is flat index p0
         const int p0 = (t0 + i) * SPAN;
         const int len = min(SPAN, HW - p0);  // multiple of 4 (HW % 4 == 0)
-        // The tgt window starts Dpad floats before the span; only the very first plane of the tensor can
-        // make that negative (those values are never used: x < d there).
+        // The tgt window of channel k starts Dpad floats before the span: roff0 + k*HW.  For (b=0, g=0) that lies before
+        // the tensor while k*HW + p0 < Dpad (the first plane; several planes when HW < Dpad): each copy is clipped to the
+        // tensor (the skipped values are never used: x < d there, and the forward only selects).
         const int64_t roff0 = plane0 + p0 - Dpad;
-        const int skip0 = roff0 < 0 ? static_cast<int>(-roff0) : 0;
+        auto skip_of = [&](int k) -> int {
+            const int64_t o = roff0 + static_cast<int64_t>(k) * HW;
+            return o < 0 ? static_cast<int>(o < -(len + Dpad) ? len + Dpad : -o) : 0;
+        };
         if (threadIdx.x == 0) {
-            const uint32_t bytes = static_cast<uint32_t>(CPG) * (2u * len + Dpad) * 4u - 4u * skip0;
+            int skipped = 0;
+            for (int k = 0; k < CPG; ++k) skipped += skip_of(k);
+            const uint32_t bytes = static_cast<uint32_t>(CPG) * (2u * len + Dpad) * 4u - 4u * skipped;
             mbar_expect_tx(&bar[i & 1], bytes);
         }
         __syncwarp();
         for (int k = threadIdx.x; k < CPG; k += 32) {
             bulk_g2s(sL + k * SPAN, ref + plane0 + static_cast<int64_t>(k) * HW + p0, 4u * len, &bar[i & 1]);
-            const int skip = k == 0 ? skip0 : 0;
-            bulk_g2s(sR + k * rpitch + skip, tgt + roff0 + static_cast<int64_t>(k) * HW + skip,
-                     4u * (len + Dpad - skip), &bar[i & 1]);
+            const int skip = skip_of(k);
+            if (skip < len + Dpad)
+                bulk_g2s(sR + k * rpitch + skip, tgt + roff0 + static_cast<int64_t>(k) * HW + skip,
+                         4u * (len + Dpad - skip), &bar[i & 1]);
         }
     };
 
@@ -191,14 +198,22 @@ gwc_volume_kchunk_kernel(const float *__restrict__ ref, const float *__restrict_
         const int k0 = (st % nkc) * KC;
         const int len = min(SPAN, HW - p0);
         const int64_t roff0 = plane0 + static_cast<int64_t>(k0) * HW + p0 - Dpad;
-        const int skip0 = roff0 < 0 ? static_cast<int>(-roff0) : 0;  // only the very first plane of the tensor
-        mbar_expect_tx(&full_bar[slot], static_cast<uint32_t>(KC) * (2u * len + Dpad) * 4u - 4u * skip0);
+        // clip every channel's window to the tensor (first planes of (b=0, g=0); several planes when HW < Dpad)
+        auto skip_of = [&](int k) -> int {
+            const int64_t o = roff0 + static_cast<int64_t>(k) * HW;
+            return o < 0 ? static_cast<int>(o < -(len + Dpad) ? len + Dpad : -o) : 0;
+        };
+        int skipped = 0;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) skipped += skip_of(k);
+        mbar_expect_tx(&full_bar[slot], static_cast<uint32_t>(KC) * (2u * len + Dpad) * 4u - 4u * skipped);
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             bulk_g2s(sL + k * SPAN, ref + plane0 + static_cast<int64_t>(k0 + k) * HW + p0, 4u * len, &full_bar[slot]);
-            const int skip = k == 0 ? skip0 : 0;
-            bulk_g2s(sR + k * rpitch + skip, tgt + roff0 + static_cast<int64_t>(k) * HW + skip, 4u * (len + Dpad - skip),
-                     &full_bar[slot]);
+            const int skip = skip_of(k);
+            if (skip < len + Dpad)
+                bulk_g2s(sR + k * rpitch + skip, tgt + roff0 + static_cast<int64_t>(k) * HW + skip, 4u * (len + Dpad - skip),
+                         &full_bar[slot]);
         }
     };
     if (threadIdx.x == 0)
@@ -370,8 +385,8 @@ static int launch_gwc_kchunk(const float *ref, const float *tgt, float *out, int
     constexpr int SPAN = SQ * 4;
     const int Dpad = ((D + DC - 1) / DC) * DC;
     const int nspans = (HW + SPAN - 1) / SPAN;
-    int tpc = tune_variant("DV_GWC_TPC", 8);
-    while (tpc > 1 && static_cast<int64_t>((nspans + tpc - 1) / tpc) * G * B < 4LL * kNumSMs * MINB) tpc /= 2;
+    int tpc = DV_TUNE("DV_GWC_TPC", 8);
+    while (tpc > 1 && static_cast<int64_t>((nspans + tpc - 1) / tpc) * G * B < 4LL * num_sms() * MINB) tpc /= 2;
     constexpr int STAGES = 3;
     const size_t smem = sizeof(float) * STAGES * (static_cast<size_t>(KC) * SPAN + static_cast<size_t>(KC) * (SPAN + Dpad));
     auto kern = gwc_volume_kchunk_kernel<KC, DC, SQ, NCH, MINB, STAGES>;
@@ -390,7 +405,7 @@ static int dispatch_gwc_kchunk(const float *ref, const float *tgt, float *out, i
     // ones, the third of which would hold a single plane — the kernel is shared-memory-bandwidth bound (5 LDS.128 per 48 FMA
     // per thread and chunk), and the wide tile needs 9 LDS.128 per 112 FMA: 0.190 -> 0.137 ms at B = 4, 384x1248.
     // (The same widening does nothing for the cpg = 8, D = 48 volume, which is not LDS-bound: measured 0.463 vs 0.456 ms.)
-    const int wide = tune_variant("DV_KCHUNK_WIDE", 28);
+    const int wide = DV_TUNE("DV_KCHUNK_WIDE", 28);
     if (D > 24 && D <= 28 && wide == 28) return launch_gwc_kchunk<KC, 28, SQ, 1, 4>(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
     if (D > 24 && D <= 32 && wide != 0) return launch_gwc_kchunk<KC, 16, SQ, 2, 3>(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
     const int nch = (D + DC - 1) / DC;
@@ -410,8 +425,8 @@ static int launch_gwc(const float *ref, const float *tgt, OutT *out, int B, int 
     const int Dpad = ((D + DC - 1) / DC) * DC;
     const int nspans = (HW + SPAN - 1) / SPAN;
     // spans per CTA (2-stage pipeline inside the CTA); keep >= ~4 CTAs per SM slot for balance
-    int tpc = tune_variant("DV_GWC_TPC", 8);
-    while (tpc > 1 && static_cast<int64_t>((nspans + tpc - 1) / tpc) * G * B < 4LL * kNumSMs * MINB) tpc /= 2;
+    int tpc = DV_TUNE("DV_GWC_TPC", 8);
+    while (tpc > 1 && static_cast<int64_t>((nspans + tpc - 1) / tpc) * G * B < 4LL * num_sms() * MINB) tpc /= 2;
     const int stages = tpc > 1 ? 2 : 1;
     const size_t smem = sizeof(float) * stages * (static_cast<size_t>(CPG) * SPAN + static_cast<size_t>(CPG) * (SPAN + Dpad));
     if (smem > 200 * 1024) return DV_ERR_UNSUPPORTED;
@@ -431,7 +446,7 @@ static int dispatch_gwc(const float *ref, const float *tgt, OutT *out, int B, in
     constexpr int DC = 12, SQ = 64;
     const int nch = (D + DC - 1) / DC;
     if (nch >= 4) {
-        if (tune_variant("DV_GWC_MINB", 2) == 2)
+        if (DV_TUNE("DV_GWC_MINB", 2) == 2)
             return launch_gwc<CPG, DC, SQ, 4, 2, OutT>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
         return launch_gwc<CPG, DC, SQ, 4, 3, OutT>(ref, tgt, out, B, C, HW, W, D, G, Dtot, dofs, st);
     }
@@ -450,7 +465,7 @@ static int gwc_volume_impl(const float *ref, const float *tgt, float *out, int64
                       W >= 4;
     if (fast) {
         int rc = DV_ERR_UNSUPPORTED;
-        if (cpg > 8 && cpg % 8 == 0 && D <= 48 && tune_variant("DV_GWC_KCHUNK", 1))
+        if (cpg > 8 && cpg % 8 == 0 && D <= 48 && DV_TUNE("DV_GWC_KCHUNK", 1))
             rc = dispatch_gwc_kchunk(ref, tgt, out, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
         if (rc != DV_ERR_UNSUPPORTED) return rc;
         switch (cpg) {
@@ -466,7 +481,7 @@ static int gwc_volume_impl(const float *ref, const float *tgt, float *out, int64
     const int64_t total = B * G * D * HW;
     const int threads = 256;
     const int64_t blocks = (total + threads - 1) / threads;
-    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
     gwc_volume_generic_kernel<<<grid, threads, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(HW),
                                                         static_cast<int>(W), static_cast<int>(D), static_cast<int>(G), cpg,
                                                         static_cast<int>(Dtot), static_cast<int>(dofs), total);
@@ -533,7 +548,7 @@ extern "C" int dv_corr_volume_2sided_f32(const float *ref, const float *tgt, flo
         return finish_launch(2);
     }
     const int64_t blocks = (total + 255) / 256;
-    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
     corr_negative_kernel<<<grid, 256, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(HW),
                                                static_cast<int>(W), static_cast<int>(maxdisp), static_cast<int>(G),
                                                static_cast<int>(C / G), total);

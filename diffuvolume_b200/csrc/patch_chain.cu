@@ -321,7 +321,7 @@ extern "C" int dv_depthwise3x3_chain_f32(const float *in, const float *w1, const
     if (B > 65535 || (c1 - c0) * D > 65535 || H * W > INT32_MAX) return DV_ERR_BAD_SHAPE;
     if (in == out) return DV_ERR_UNSUPPORTED;  // tiles read their neighbours' inputs
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (W % 4 == 0 && aligned16(in) && aligned16(out) && tune_variant("DV_PATCH_ROWS", 1)) {
+    if (W % 4 == 0 && aligned16(in) && aligned16(out) && DV_TUNE("DV_PATCH_ROWS", 1)) {
         // compile-time dilations (everything ACVNet uses): the row-blocked kernel
         const int Bi = static_cast<int>(B), Ci = static_cast<int>(C), Di = static_cast<int>(D), Hi = static_cast<int>(H),
                   Wi = static_cast<int>(W), a = static_cast<int>(c0), z = static_cast<int>(c1);
@@ -332,7 +332,7 @@ extern "C" int dv_depthwise3x3_chain_f32(const float *in, const float *w1, const
         if (!w2 && dil1 == 2) return launch_rows<false, 2, 1>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
         if (!w2 && dil1 == 3) return launch_rows<false, 3, 1>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
     }
-    if (W % 4 == 0 && aligned16(in) && aligned16(out) && dil1 <= 4 && (!w2 || dil2 <= 4) && tune_variant("DV_PATCH_QUAD", 1)) {
+    if (W % 4 == 0 && aligned16(in) && aligned16(out) && dil1 <= 4 && (!w2 || dil2 <= 4) && DV_TUNE("DV_PATCH_QUAD", 1)) {
         // tiles: up to 32 rows x 128 columns, balanced to the plane, widths in quads
         const int tiles_y = static_cast<int>((H + 31) / 32), tiles_x = static_cast<int>((W + 127) / 128);
         const int th = static_cast<int>((H + tiles_y - 1) / tiles_y);

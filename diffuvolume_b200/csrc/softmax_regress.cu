@@ -230,13 +230,14 @@ softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__r
 // Cross-slice reductions: one shuffle + (NDS/2)-way shared memory combine behind a named barrier of the consumer
 // warps (the producer warp never joins it).
 constexpr int kSrSlots = 256;
-static __device__ int g_sr_next[kSrSlots];
-static __device__ int g_sr_done[kSrSlots];
+// {next, done} tile counters: caller-owned through the C-ABI's `tile_counters` argument, else a pair of this pool (see
+// concat_stream.cu for the contract)
+static __device__ int g_sr_ctr[kSrSlots][2];
 static std::atomic<unsigned> g_sr_slot{0};
 
 template <int NJ, int NDS, int STAGES, int SPAN, int MINB, bool DYN, bool FULLD>
 __global__ void __launch_bounds__(SPAN / 4 * NDS + 32, MINB)
-softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int HW, int spans_per_b, int ntiles, int slot,
+softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int HW, int spans_per_b, int ntiles, int *ctr_arg, int slot,
                            float *__restrict__ disp_out, float *__restrict__ prob_out, const float *__restrict__ used,
                            float *__restrict__ unc_out, float *__restrict__ vote_out, float thr_dif, float thr_unc,
                            float *__restrict__ ens_acc, float ens_coef, int ens_init) {
@@ -247,6 +248,7 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
     __shared__ int tile_id[STAGES];
     const int stage_floats = D * SPAN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *const ctr = ctr_arg ? ctr_arg : g_sr_ctr[slot];
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -267,13 +269,13 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
         for (int it = 0;; ++it) {
             const int s = it % STAGES, k = it / STAGES;
             if (k > 0) mbar_wait(&empty_bar[s], (k & 1) ^ 1);
-            const int t = DYN ? atomicAdd(&g_sr_next[slot], 1) : static_cast<int>(blockIdx.x + it * gridDim.x);
+            const int t = DYN ? atomicAdd(&ctr[0], 1) : static_cast<int>(blockIdx.x + it * gridDim.x);
             if (t >= ntiles) {
                 tile_id[s] = -1;
                 mbar_arrive(&full_bar[s]);
-                if (DYN && atomicAdd(&g_sr_done[slot], 1) == static_cast<int>(gridDim.x) - 1) {
-                    g_sr_next[slot] = 0;   // last CTA out re-arms the counter pair
-                    g_sr_done[slot] = 0;
+                if (DYN && atomicAdd(&ctr[1], 1) == static_cast<int>(gridDim.x) - 1) {
+                    ctr[0] = 0;   // last CTA out re-arms the counter pair
+                    ctr[1] = 0;
                     __threadfence();
                 }
                 return;
@@ -431,11 +433,11 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
 template <int NJ, int NDS, int STAGES, int SPAN, int MINB>
 static int launch_sr_tma(const float *cost, int B, int D, int HW, float *disp_out, float *prob_out, const float *used,
                          float *unc_out, float *vote_out, float thr_dif, float thr_unc, float *ens_acc,
-                         float ens_coef, int ens_init, cudaStream_t st) {
+                         float ens_coef, int ens_init, int *ctr, cudaStream_t st) {
     const size_t smem = sizeof(float) * STAGES * static_cast<size_t>(D) * SPAN;
     const int spans = (HW + SPAN - 1) / SPAN;
     const int64_t ntiles = static_cast<int64_t>(spans) * B;
-    const int grid = static_cast<int>(ntiles < 1LL * MINB * kNumSMs ? ntiles : 1LL * MINB * kNumSMs);
+    const int grid = static_cast<int>(ntiles < 1LL * MINB * num_sms() ? ntiles : 1LL * MINB * num_sms());
     CUtensorMap tmap;
     const uint64_t dims[3] = {static_cast<uint64_t>(HW), static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
     const uint32_t box[3] = {static_cast<uint32_t>(SPAN), static_cast<uint32_t>(D), 1u};
@@ -447,7 +449,7 @@ static int launch_sr_tma(const float *cost, int B, int D, int HW, float *disp_ou
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=         \
             cudaSuccess)                                                                                               \
             return DV_ERR_LAUNCH;                                                                                      \
-        kern<<<grid, SPAN / 4 * NDS + 32, smem, st>>>(tmap, D, HW, spans, static_cast<int>(ntiles), slot, disp_out,    \
+        kern<<<grid, SPAN / 4 * NDS + 32, smem, st>>>(tmap, D, HW, spans, static_cast<int>(ntiles), ctr, slot, disp_out,    \
                                                       prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc,    \
                                                       ens_coef, ens_init);                                             \
     }
@@ -568,7 +570,7 @@ static void launch_sr(const float *cost, int B, int D, int HW, float *disp_out, 
 extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, int64_t H, int64_t W, float *disp_out,
                                       float *prob_out, const float *used, float *unc_out, float *vote_out,
                                       float thr_dif, float thr_unc, float *ens_acc, float ens_coef, int ens_init,
-                                      void *stream) {
+                                      void *tile_counters, void *stream) {
     using namespace dv;
     if (!cost) return DV_ERR_NULL;
     if (vote_out && !used) return DV_ERR_NULL;
@@ -583,14 +585,14 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
     const bool vec4 = (HW % 4 == 0) && all_aligned(15);
     const bool vec2 = (HW % 2 == 0) && all_aligned(7);
     // D <= 8*DPT.  Tuning switch DV_SR_VARIANT (scripts/tune_kernels.py) selects the D = 192 layout.
-    const int variant = tune_variant("DV_SR_VARIANT", 4);
-    if (vec4 && D <= 192 && tune_variant("DV_SR_TMA", 1) && static_cast<int64_t>((HW + 63) / 64) * B <= INT32_MAX) {
+    const int variant = DV_TUNE("DV_SR_VARIANT", 4);
+    if (vec4 && D <= 192 && DV_TUNE("DV_SR_TMA", 1) && static_cast<int64_t>((HW + 63) / 64) * B <= INT32_MAX) {
         int rc;
-#define DV_SR_TMA_ARGS cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, st
+#define DV_SR_TMA_ARGS cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, static_cast<int *>(tile_counters), st
         // thread = (quad of 16, slice of 8): 4 consumer warps per CTA, 2 CTAs per SM.  Measured at D = 192, B = 8
         // (gpurun_out/bench_sr3.log): 8 slices x 24 d per thread 0.496 ms (6.59 TB/s) vs 16 slices x 12 d 0.586 ms — half as
         // many partials to merge per pixel and half the per-tile overhead per element; 3 CTAs x 1 stage spills.
-        const int shape = tune_variant("DV_SR_SHAPE", 2);
+        const int shape = DV_TUNE("DV_SR_SHAPE", 2);
         if (D <= 48) rc = launch_sr_tma<6, 8, 4, 64, 2>(DV_SR_TMA_ARGS);
         else if (D <= 96) rc = launch_sr_tma<12, 8, 4, 64, 2>(DV_SR_TMA_ARGS);
         else if (shape == 0) rc = launch_sr_tma<12, 16, 2, 64, 2>(DV_SR_TMA_ARGS);
@@ -619,7 +621,7 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
     } else {
         const int64_t total = B * HW;
         const int64_t blocks = (total + 255) / 256;
-        const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+        const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
         softmax_regress_generic_kernel<<<grid, 256, 0, st>>>(cost, static_cast<int>(D), static_cast<int>(HW), disp_out,
                                                              prob_out, used, unc_out, vote_out, thr_dif, thr_unc,
                                                              ens_acc, ens_coef, ens_init, total);

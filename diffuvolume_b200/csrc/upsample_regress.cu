@@ -205,7 +205,7 @@ extern "C" int dv_upsample_softmax_regress_f32(const float *cost_q, int64_t B, i
     a.align_corners = align_corners ? 1 : 0;
     a.disp_out = disp_out; a.used = used; a.unc_out = unc_out; a.vote_out = vote_out;
     a.thr_dif = thr_dif; a.thr_unc = thr_unc; a.ens_acc = ens_acc; a.ens_coef = ens_coef; a.ens_init = ens_init;
-    if (Dq == 48 && D == 4 * Dq && !align_corners && tune_variant("DV_UPS_FAST", 1)) {
+    if (Dq == 48 && D == 4 * Dq && !align_corners && DV_TUNE("DV_UPS_FAST", 1)) {
         dim3 grid(static_cast<unsigned>((W + 31) / 32), static_cast<unsigned>((H + 7) / 8), static_cast<unsigned>(B));
         upsample_regress_fast_kernel<48><<<grid, dim3(32, 8), 0, st>>>(a);
     } else {

@@ -114,26 +114,37 @@ gwc_bwd_quad_kernel(const float *__restrict__ go, const float *__restrict__ ref,
     __syncthreads();
     if (threadIdx.x < 32) {
         const int rlen = min(len + Dpad, HW - p0);        // ref: do not run past the plane (masked terms only)
-        const int64_t toff = fb + p0 - Dpad;              // tgt window start; negative only for the very first plane
-        const int skip0 = toff < 0 ? static_cast<int>(-toff) : 0;
-        if (threadIdx.x == 0) mbar_expect_tx(&bar, 4u * (CK * (rlen + len + Dpad) - skip0));
+        // tgt window start of channel k is toff + k*HW; it lies before the tensor for the first channels of (b=0, g=0) whenever
+        // k*HW + p0 < Dpad (tiny planes: several channels) — clip each copy to the tensor
+        const int64_t toff = fb + p0 - Dpad;
+        auto skip_of = [&](int k) -> int {
+            const int64_t o = toff + static_cast<int64_t>(k) * HW;
+            return o < 0 ? static_cast<int>(o < -(len + Dpad) ? len + Dpad : -o) : 0;
+        };
+        if (threadIdx.x == 0) {
+            int skipped = 0;
+            for (int k = 0; k < CK; ++k) skipped += skip_of(k);
+            mbar_expect_tx(&bar, 4u * (CK * (rlen + len + Dpad) - skipped));
+        }
         __syncwarp();
         for (int k = threadIdx.x; k < CK; k += 32) {
             bulk_g2s(sR + k * pitch, ref + fb + static_cast<int64_t>(k) * HW + p0, 4u * rlen, &bar);
-            const int skip = k == 0 ? skip0 : 0;
-            bulk_g2s(sT + k * pitch + skip, tgt + toff + static_cast<int64_t>(k) * HW + skip, 4u * (len + Dpad - skip), &bar);
+            const int skip = skip_of(k);
+            if (skip < len + Dpad)
+                bulk_g2s(sT + k * pitch + skip, tgt + toff + static_cast<int64_t>(k) * HW + skip, 4u * (len + Dpad - skip), &bar);
         }
     }
     {   // the parts of the windows no copy lands in (plane tail of ref, tensor head of tgt) are only ever multiplied by a
         // masked (zero) gradient: clear them so that stale shared memory cannot inject NaNs
         const int rlen = min(len + Dpad, HW - p0);
         const int64_t toff = fb + p0 - Dpad;
-        const int skip0 = toff < 0 ? static_cast<int>(-toff) : 0;
         for (int k = 0; k < CK; ++k) {
             for (int e = rlen + threadIdx.x; e < pitch; e += 2 * SQ) sR[k * pitch + e] = 0.0f;
             for (int e = len + Dpad + threadIdx.x; e < pitch; e += 2 * SQ) sT[k * pitch + e] = 0.0f;
+            const int64_t o = toff + static_cast<int64_t>(k) * HW;
+            const int skip = o < 0 ? static_cast<int>(o < -(len + Dpad) ? len + Dpad : -o) : 0;
+            for (int e = threadIdx.x; e < skip; e += 2 * SQ) sT[k * pitch + e] = 0.0f;
         }
-        for (int e = threadIdx.x; e < skip0; e += 2 * SQ) sT[e] = 0.0f;
     }
     __syncthreads();
     mbar_wait(&bar, 0);
@@ -311,7 +322,7 @@ static int gwc_bwd_impl(const float *go, const float *ref, const float *tgt, flo
     const bool two_sided_ok = mneg > 0 && dofs == mneg && Dtot == 2 * mneg + 1 && W >= 2 * mneg;
     if ((mneg == 0 ? (dofs == 0 && Dtot == D) : two_sided_ok) && HW % 4 == 0 && W >= 4 && D <= 256 && aligned16(go) &&
         aligned16(ref) && aligned16(tgt) && (!gref || aligned16(gref)) && (!gtgt || aligned16(gtgt)) &&
-        G * static_cast<int64_t>(cpg) <= 65535 && tune_variant("DV_GWC_BWD_QUAD", 1)) {
+        G * static_cast<int64_t>(cpg) <= 65535 && DV_TUNE("DV_GWC_BWD_QUAD", 1)) {
         const int Bi = static_cast<int>(B), Ci = static_cast<int>(C), HWi = static_cast<int>(HW), Wi = static_cast<int>(W),
                   Di = static_cast<int>(D), Gi = static_cast<int>(G), Dt = static_cast<int>(Dtot), Do = static_cast<int>(dofs);
         int rc = DV_ERR_UNSUPPORTED;
@@ -342,7 +353,7 @@ static int gwc_bwd_impl(const float *go, const float *ref, const float *tgt, flo
         default: {
             const int64_t total = B * C * HW;
             const int64_t blocks = (total + 255) / 256;
-            const int gsz = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+            const int gsz = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
             gwc_bwd_generic_kernel<<<gsz, 256, 0, st>>>(go, ref, tgt, gref, gtgt, static_cast<int>(C), static_cast<int>(HW),
                                                         static_cast<int>(W), static_cast<int>(D), static_cast<int>(G), cpg,
                                                         static_cast<int>(Dtot), static_cast<int>(dofs),
@@ -442,7 +453,7 @@ extern "C" int dv_groupwise_correlation_bwd_f32(const float *grad_out, const flo
     const int64_t HW = H * W, total = B * C * HW;
     if (HW > INT32_MAX) return DV_ERR_BAD_SHAPE;
     const int64_t blocks = (total + 255) / 256;
-    const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+    const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
     groupwise_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, fea1, fea2, grad1, grad2,
                                                                             static_cast<int>(C), static_cast<int>(HW),
                                                                             static_cast<int>(G), static_cast<int>(C / G), total);

@@ -90,7 +90,7 @@ static int launch_filter(const float *vol, float *out, int64_t B, int64_t C, int
     } else {
         const int64_t total = B * D * HW;
         const int64_t blocks = (total + 255) / 256;
-        const int grid = static_cast<int>(blocks < static_cast<int64_t>(kNumSMs) * 32 ? blocks : static_cast<int64_t>(kNumSMs) * 32);
+        const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
         volume_filter_generic_kernel<XT><<<grid, 256, 0, st>>>(vol, out, static_cast<int>(C), static_cast<int>(D),
                                                                static_cast<int>(HW), xt, shift, scale, n_out, total);
     }

@@ -46,6 +46,27 @@ def _need_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
     return dev
 
 
+_tile_counter_cache: dict = {}
+
+
+def _tile_counters(dev: torch.device, family: int) -> int:
+    """Device address of the {next, done} tile-counter pair a persistent kernel of `family` (0 = streaming volume
+    producer, 1 = softmax-regression) draws from (include/dv_b200.h, `tile_counters`).  One zeroed pair per (device,
+    stream, family): launches on one stream are ordered, so they can share a pair; other streams get their own.  While a
+    CUDA graph is being captured every call gets a FRESH zeroed pair from the graph's private pool (a memset node in the
+    graph), so replays of different graphs never share counters with each other or with eager launches."""
+    if torch.cuda.is_current_stream_capturing():
+        t = torch.zeros(2, dtype=torch.int32, device=dev)
+        _tile_counter_cache.setdefault(("graph", dev.index), []).append(t)    # owned by the graph pool; keep the handle
+        return t.data_ptr()
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    t = _tile_counter_cache.get(key)
+    if t is None:
+        t = torch.zeros(16, dtype=torch.int32, device=dev)
+        _tile_counter_cache[key] = t
+    return t.data_ptr() + 32 * family
+
+
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise DvLibraryError(f"{name}: expected float32, got {t.dtype}")
@@ -229,12 +250,14 @@ def concat_volume_weighted(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, *
         # fp32 operands and products, one round-to-nearest-even at the store (half the write traffic of the filter pass)
         with torch.cuda.device(ref.device):
             check(_lib.lib().dv_concat_volume_weighted_bf16(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp,
-                                                            int(mask_left), _ptr(att_weights), _ptr(n), _stream(ref)),
+                                                            int(mask_left), _ptr(att_weights), _ptr(n),
+                                                            _tile_counters(ref.device, 0), _stream(ref)),
                   "dv_concat_volume_weighted_bf16")
         return out
     with torch.cuda.device(ref.device):
         check(_lib.lib().dv_concat_volume_weighted_f32(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp,
-                                                       int(mask_left), _ptr(att_weights), _ptr(n), _stream(ref)),
+                                                       int(mask_left), _ptr(att_weights), _ptr(n),
+                                                       _tile_counters(ref.device, 0), _stream(ref)),
               "dv_concat_volume_weighted_f32")
     return out
 
@@ -310,7 +333,7 @@ def softmax_regress(cost: torch.Tensor, *, return_prob: bool = False, used: Opti
         check(_lib.lib().dv_softmax_regress_f32(_ptr(cost), B, D, H, W, _ptr(res["disp"]), _ptr(res.get("prob")),
                                                 _ptr(used), _ptr(res.get("unc")), _ptr(res.get("vote")), thr_dif,
                                                 thr_unc, _ptr(ens_acc), float(ens_coef), int(ens_init),
-                                                _stream(cost)), "dv_softmax_regress_f32")
+                                                _tile_counters(dev, 1), _stream(cost)), "dv_softmax_regress_f32")
     return res
 
 

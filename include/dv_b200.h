@@ -4,10 +4,22 @@
  * Every entry point is `extern "C" int f(...)`: raw device pointers, int64 sizes, a
  * `cudaStream_t` passed as `void*`; it returns a dv_status (0 = ok) and never throws,
  * allocates, frees or retains memory.  The caller owns every buffer.  All launches go to
- * the stream given (0 = legacy default stream).  The library is re-entrant: no globals
- * except a relaxed launch counter (dv_launch_count), so it can be called from one host
+ * the stream given (0 = legacy default stream).  The library can be called from one host
  * thread per device concurrently (the reference runs under nn.DataParallel,
- * SceneFlow/main.py:67).
+ * SceneFlow/main.py:67).  Process-wide state, all of it: a relaxed launch counter
+ * (dv_launch_count), the per-device SM count (queried once), tuning environment variables
+ * (DV_*, read once per process, unset in production), and — only when the caller passes
+ * tile_counters == NULL to the three persistent kernels below — a library-owned pool of
+ * 256 device-side tile-counter pairs per kernel family handed out round-robin.
+ *
+ * `tile_counters` (dv_concat_volume_weighted_f32/_bf16, dv_softmax_regress_f32): the
+ * persistent kernels draw their tiles from a {next, done} pair of int32 in device memory.
+ * Pass 8 bytes (4-byte aligned) that were zero when first used; the kernel returns them
+ * to zero before it exits, so one pair can be reused by consecutive launches on ONE
+ * stream.  Launches that may overlap (other streams, other captured graphs) need their
+ * own pair.  NULL selects the internal pool: at most 256 overlapping launches per kernel
+ * family and device, a captured CUDA graph keeps its pair for life, and a kernel that is
+ * aborted mid-run leaves its pair dirty.
  *
  * The reference (iSEE-Laboratory/DiffuVolume) has no FFI of its own: the hot path is a set
  * of module-level Python functions.  Each function below names the
@@ -94,7 +106,7 @@ int dv_filter_factor(const void *xt, int xt_is_f64, const float *shift, double s
                      void *n_out_native, int64_t B, int64_t D, int64_t H, int64_t W, void *stream);
 int dv_concat_volume_weighted_f32(const float *ref, const float *tgt, float *out,
                                   int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int mask_left,
-                                  const float *att_weights, const float *n, void *stream);
+                                  const float *att_weights, const float *n, void *tile_counters, void *stream);
 
 /* ---- a9 at the op boundary: the DDIM filter multiply on an existing volume
  *          (SceneFlow/models/acv_ddim.py:254-260; KITTI12/models/pwcnet_ddim.py:466-472)
@@ -130,7 +142,7 @@ int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, int64_t H, i
                            const float *used, float *unc_out, float *vote_out,
                            float thr_dif, float thr_unc,
                            float *ens_acc, float ens_coef, int ens_init,
-                           void *stream);
+                           void *tile_counters, void *stream);
 
 /* ---- f2: F.upsample(..., mode='trilinear') fused into a6 (+a11 +a13)
  *          (SceneFlow/models/acv_ddim.py:267-270 align_corners=False; KITTI12/models/pwcnet_ddim.py:480-484 True)
@@ -315,7 +327,7 @@ int dv_gwc_volume_bf16(const float *ref, const float *tgt, void *out,
                        int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int64_t G, void *stream);
 int dv_concat_volume_weighted_bf16(const float *ref, const float *tgt, void *out,
                                    int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int mask_left,
-                                   const float *att_weights, const float *n, void *stream);
+                                   const float *att_weights, const float *n, void *tile_counters, void *stream);
 
 /* ---- f1: backward passes of the volume ops — the reference's training scripts differentiate through them
  *          (SceneFlow/main.py:154 -> models/acv_ddim.py:424-482; KITTI12/main.py; KITTI15/train_stereo.py).

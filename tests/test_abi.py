@@ -69,7 +69,7 @@ def test_argument_validation_without_a_gpu(lib):
     p = ctypes.cast(buf, ctypes.c_void_p)
     assert lib.dv_gwc_volume_f32(p, p, p, 1, 7, 4, 8, 4, 2, None) == 1                   # C % G != 0
     assert lib.dv_gwc_volume_f32(p, p, p, 0, 8, 4, 8, 4, 2, None) == 1
-    assert lib.dv_softmax_regress_f32(None, 1, 4, 2, 2, None, None, None, None, None, 0, 0, None, 0, 0, None) == 5
+    assert lib.dv_softmax_regress_f32(None, 1, 4, 2, 2, None, None, None, None, None, 0, 0, None, 0, 0, None, None) == 5
     assert lib.dv_volume_filter_f32(p, p, 1, 1, 1, 1, 1, p, 7, None, 1.0, None, None) == 2  # bad dtype flag
     assert lib.dv_ddim_step(None, None) == 5
     assert lib.dv_geo_lookup_f32(p, p, None, p, p, p, 1, 8, 48, 2, 2, 8, 9, 4, None) == 6   # too many levels

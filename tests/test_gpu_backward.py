@@ -47,7 +47,10 @@ def _corr_port(r, t_, m, G):
 
 
 @pytest.mark.parametrize("shape,D,G", [((2, 64, 9, 40), 48, 8), ((1, 24, 5, 20), 12, 2), ((2, 8, 3, 7), 9, 4),
-                                       ((1, 15, 4, 11), 6, 3), ((1, 320, 6, 24), 12, 40)])
+                                       ((1, 15, 4, 11), 6, 3), ((1, 320, 6, 24), 12, 40),
+                                       # H*W < D (+ padding): the tgt windows of SEVERAL channels of (b=0, g=0) start before
+                                       # the tensor — every bulk copy must be clipped per channel
+                                       ((2, 16, 4, 8), 48, 2), ((1, 24, 2, 8), 48, 2)])
 def test_gwc_volume_backward(shape, D, G):
     from diffuvolume_b200 import functional as Fn
     _check(Fn.build_gwc_volume, lambda r, t_, D_, G_: P.gwc_volume(r, t_, D_, G_), shape, (D, G), 201)

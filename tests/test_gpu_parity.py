@@ -56,6 +56,8 @@ def test_gwc_volume_golden(ops, golden, case):
     (1, 16, 4, 48, 9, 60),        # 4 channels per group, H*W % 256 != 0 tail span
     (1, 10, 2, 7, 5, 13),         # cpg = 5, H*W % 4 != 0: shape-agnostic kernel
     (1, 8, 1, 100, 8, 64),        # D > 48: chunk loop, D > W
+    (2, 16, 2, 48, 4, 8),         # H*W < D: several channel windows of (b=0, g=0) start before the tensor (clipped copies)
+    (1, 64, 2, 48, 2, 8),         # same on the K-chunked kernel (32 channels per group)
 ])
 def test_gwc_volume_vs_oracle(ops, shape):
     B, C, G, D, H, W = shape
