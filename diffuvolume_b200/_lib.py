@@ -109,6 +109,8 @@ SIGNATURES = {
     "dv_groupwise_correlation_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_concat_volume_bwd_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P]),
     "dv_disparity_regression_bwd_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _P]),
+    "dv_softmax_regress_bwd_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "dv_acv_volume_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P]),
     "dv_warp_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "dv_ensemble_f32": (_I, [_P, _P, _I, _P, _I64, _P]),
 }

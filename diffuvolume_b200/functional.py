@@ -185,3 +185,89 @@ def context_upsample(disp_low, up_weights):
     out = _ContextUpsample.apply(disp_low, up_weights)
     rt = torch.result_type(disp_low, up_weights)
     return out if rt == torch.float32 else out.to(rt)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Fused ops with fused backward passes — used by the forward-level (tier-3) drop-ins (diffuvolume_b200/sampler.py)
+# in place of the unnamed ops the reference runs BETWEEN its named functions.
+# ------------------------------------------------------------------------------------------------------------------
+class _AcvVolume(torch.autograd.Function):
+    """(concat(cl, cr) * softmax(att_logits, dim=2)) * n — SceneFlow/models/acv_ddim.py:388-390 and, with n, the training
+    branch's filter multiply :446-451 in ONE producer pass; backward: csrc/fused_backward.cu."""
+
+    @staticmethod
+    def forward(ctx, cl, cr, att_logits, maxdisp, n):
+        att_w = ops.att_softmax(_as_f32(att_logits))
+        ctx.save_for_backward(cl, cr, att_w, n)
+        ctx.att_shape = att_logits.shape
+        out = ops.concat_volume_weighted(_as_f32(cl), _as_f32(cr), maxdisp, mask_left=False, att_weights=att_w, n=n)
+        return out.to(cl.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        cl, cr, att_w, n = ctx.saved_tensors
+        gcl, gcr, gatt = ops.acv_volume_bwd(g.float().contiguous(), cl.float(), cr.float(), att_w, n,
+                                            need_cl=ctx.needs_input_grad[0], need_cr=ctx.needs_input_grad[1],
+                                            need_att=ctx.needs_input_grad[2])
+        return (None if gcl is None else gcl.to(cl.dtype), None if gcr is None else gcr.to(cr.dtype),
+                None if gatt is None else gatt.reshape(ctx.att_shape), None, None)
+
+
+def acv_attention_volume(concat_left, concat_right, att_logits, maxdisp, n=None):
+    """`F.softmax(att_weights, dim=2) * build_concat_volume(cl, cr, maxdisp)` (acv_ddim.py:388-390, acv.py:201-203),
+    optionally times the DDIM filter factor n [B,D,h,w] fp32 (acv_ddim.py:446-451) — differentiable w.r.t. the concat
+    features and the attention logits.  H*W % 4 != 0 (no reference shape) takes the unfused kernels."""
+    B, C, H, W = concat_left.shape
+    if (H * W) % 4 != 0 or W < 4:
+        vol = build_concat_volume_m(concat_left, concat_right, maxdisp)
+        vol = torch.softmax(att_logits, dim=2) * vol
+        return vol if n is None else vol * n.unsqueeze(1)
+    if n is not None:
+        n = n.detach().float().contiguous()
+    return _AcvVolume.apply(concat_left, concat_right, att_logits, maxdisp, n)
+
+
+class _SoftmaxRegress(torch.autograd.Function):
+    """disparity_regression(F.softmax(cost, 1), maxdisp) without materialising the probability volume, forward
+    (csrc/softmax_regress.cu) and backward (csrc/fused_backward.cu)."""
+
+    @staticmethod
+    def forward(ctx, cost, keepdim):
+        ctx.save_for_backward(cost)
+        ctx.keepdim = keepdim
+        disp = ops.softmax_regress(_as_f32(cost))["disp"]
+        return (disp.unsqueeze(1) if keepdim else disp).to(cost.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (cost,) = ctx.saved_tensors
+        return ops.softmax_regress_bwd(cost.float(), g.float().contiguous()).to(cost.dtype), None
+
+
+def softmax_disparity_regression(cost, maxdisp, keepdim=False):
+    """`disparity_regression(F.softmax(cost, dim=1), maxdisp)` (acv_ddim.py:460-480, acv.py:213-236) fused."""
+    assert len(cost.shape) == 4
+    if cost.shape[1] != maxdisp:
+        raise RuntimeError(
+            f"The size of tensor a ({cost.shape[1]}) must match the size of tensor b ({maxdisp}) at non-singleton dimension 1")
+    return _SoftmaxRegress.apply(cost, keepdim)
+
+
+class _VolumeFilter(torch.autograd.Function):
+    """volume * ((clamp(noise + shift, -s, s)/s + 1)/2).unsqueeze(1).float() (acv_ddim.py:254-260, pwcnet_ddim.py:466-472);
+    gradient w.r.t. the volume only (the factor is detached in the reference's training branches)."""
+
+    @staticmethod
+    def forward(ctx, volume, xt, shift, scale):
+        ctx.save_for_backward(xt, shift)
+        ctx.scale = scale
+        return ops.volume_filter(_as_f32(volume), xt, shift, scale).to(volume.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        xt, shift = ctx.saved_tensors
+        return ops.volume_filter(g.float().contiguous(), xt, shift, ctx.scale).to(g.dtype), None, None, None
+
+
+def volume_filter(volume, xt, shift=None, scale=1.0):
+    return _VolumeFilter.apply(volume, xt.detach(), None if shift is None else shift.detach(), scale)

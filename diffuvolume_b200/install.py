@@ -41,6 +41,7 @@ _TIER2 = {
     "kitti12": [("models.pwcnet_ddim", "PWCNet_ddim", {
         "q_sample": sampler.q_sample,
         "predict_noise_from_start": sampler.predict_noise_from_start,
+        "model_predictions": sampler.pcw_model_predictions,
         "ddim_sample": sampler.pcw_ddim_sample,
     })],
     "kitti15": [("core.igev_stereo_ddim", "IGEVStereo_ddim", {
@@ -49,6 +50,15 @@ _TIER2 = {
         "model_predictions": sampler.igev_model_predictions,
         "ddim_sample": sampler.igev_ddim_sample,
     })],
+}
+
+# tier 3: the models' `forward` (only there can the unnamed ops between the named functions be fused and the concat
+# features be handed to the sampler — see sampler.py)
+_TIER3 = {
+    "sceneflow": [("models.acv_ddim", "ACVNet_DDIM", {"forward": sampler.acv_ddim_forward}),
+                  ("models.acv", "ACVNet", {"forward": sampler.acvnet_forward})],
+    "kitti12": [],
+    "kitti15": [],
 }
 
 _undo: List[Tuple[object, str, object, bool]] = []   # (owner, name, original, existed)
@@ -60,9 +70,10 @@ def _bind(owner, name, value):
     setattr(owner, name, value)
 
 
-def install(project: str, tier2: bool = True, modules: Dict[str, object] = None) -> List[str]:
+def install(project: str, tier2: bool = True, modules: Dict[str, object] = None, tier3: bool = True) -> List[str]:
     """Rebind the hot-path names of `project` ('sceneflow' | 'kitti12' | 'kitti15').  `modules` overrides
-    sys.modules (used by the tests with stand-in modules).  Returns the list of 'module.name' rebound."""
+    sys.modules (used by the tests with stand-in modules).  tier2: the sampler methods; tier3 (needs tier2): the models'
+    `forward`.  Returns the list of 'module.name' rebound."""
     if project not in _TIER1:
         raise ValueError(f"unknown project {project!r}; expected one of {sorted(_TIER1)}")
     mods = sys.modules if modules is None else modules
@@ -86,6 +97,15 @@ def install(project: str, tier2: bool = True, modules: Dict[str, object] = None)
                 if hasattr(cls, name):
                     _bind(cls, name, fn)
                     done.append(f"{mname}.{cname}.{name}")
+    if tier2 and tier3:
+        for mname, cname, methods in _TIER3[project]:
+            mod = mods.get(mname)
+            cls = getattr(mod, cname, None) if mod is not None else None
+            if cls is None:
+                continue
+            for name, fn in methods.items():
+                _bind(cls, name, fn)
+                done.append(f"{mname}.{cname}.{name}")
     return done
 
 

@@ -22,15 +22,45 @@ def disparity_regression(x, maxdisp):
     return _dr(x, maxdisp, keepdim=True)
 
 
+def _wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _sample_rows(rows: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Linear interpolation of rows [N,C,L] at positions x [N,T] with zero padding (what bilinear_sampler /
+    grid_sample(align_corners=True) computes on an [N,C,1,L] image, core/utils/utils.py:59-77) as a differentiable
+    gather: the gradient reaches `rows` only (the lookup positions are detached in the reference, igev_stereo_ddim.py:236)."""
+    N, C, L = rows.shape
+    T = x.shape[1]
+    i0 = torch.floor(x)
+    f = x - i0
+    i0 = i0.long()
+    w0 = (1.0 - f) * ((i0 >= 0) & (i0 < L))
+    w1 = f * ((i0 + 1 >= 0) & (i0 + 1 < L))
+    g0 = torch.gather(rows, 2, i0.clamp(0, L - 1).unsqueeze(1).expand(N, C, T))
+    g1 = torch.gather(rows, 2, (i0 + 1).clamp(0, L - 1).unsqueeze(1).expand(N, C, T))
+    return (g0 * w0.unsqueeze(1) + g1 * w1.unsqueeze(1)).reshape(N, C * T)
+
+
 class Combined_Geo_Encoding_Volume:
     """Same constructor, attributes (`geo_volume_pyramid`, `init_corr_pyramid`, `num_levels`, `radius`,
     `channel`) and call convention as the reference class; `noisy` is optional so that one class serves
-    both geometry.py (2 arguments) and geometry_ddim.py (3 arguments)."""
+    both geometry.py (2 arguments) and geometry_ddim.py (3 arguments).
+
+    Autograd: the training forward differentiates through the lookup into the geometry volume and the two feature maps
+    (igev_stereo_ddim.py:402,443; train_stereo.py:122).  When gradients are enabled and any of the three construction
+    inputs requires one, the instance is built and sampled with differentiable torch ops (`_build_autograd`,
+    `_lookup_autograd`: matmul, avg_pool1d, gather) instead of the forward-only kernels — same values to fp32 roundoff,
+    gradients exact.  Without gradients (evaluation, `ddim_sample`) the fused kernels run."""
 
     def __init__(self, init_fmap1, init_fmap2, geo_volume, num_levels=2, radius=4):
         self.num_levels = num_levels
         self.radius = radius
         self.init_corr_pyramid = []
+        self._autograd = _wants_grad(init_fmap1, init_fmap2, geo_volume)
+        if self._autograd:
+            self._build_autograd(init_fmap1, init_fmap2, geo_volume)
+            return
         if num_levels >= 2 and init_fmap2.shape[-1] >= 2:
             # level 1 of the correlation pyramid comes out of the same launch (pooled from the accumulators)
             init_corr, pooled = ops.corr1d_allpairs(init_fmap1.float(), init_fmap2.float(), return_pooled=True)
@@ -49,6 +79,46 @@ class Combined_Geo_Encoding_Volume:
         for lvl in range(1, self.num_levels):
             init_corr = pooled.reshape(b * h * w, 1, 1, w2 // 2) if (lvl == 1 and pooled is not None) else ops.avgpool_w2(init_corr)
             self.init_corr_pyramid.append(init_corr)
+
+    def _build_autograd(self, init_fmap1, init_fmap2, geo_volume):
+        """geometry_ddim.py:7-30 with differentiable ops: all-pairs correlation as a batched matmul over (b, y), the
+        permuted geometry rows, and both pyramids by pairwise averaging."""
+        import torch.nn.functional as F
+        f1, f2 = init_fmap1.float(), init_fmap2.float()
+        b, c, d, h, w = geo_volume.shape
+        w2 = f2.shape[-1]
+        self.channel = c
+        corr = torch.matmul(f1.permute(0, 2, 3, 1), f2.permute(0, 2, 1, 3))        # [B,H,W1,W2]
+        corr_rows = corr.reshape(b * h * w, 1, w2)
+        geo_rows = geo_volume.float().permute(0, 3, 4, 1, 2).reshape(b * h * w, c, d)
+        self._geo_rows, self._corr_rows = [geo_rows], [corr_rows]
+        for _ in range(self.num_levels - 1):
+            geo_rows = F.avg_pool1d(geo_rows, 2, 2)
+            corr_rows = F.avg_pool1d(corr_rows, 2, 2)
+            self._geo_rows.append(geo_rows)
+            self._corr_rows.append(corr_rows)
+        self.init_corr_pyramid = [r.unsqueeze(2) for r in self._corr_rows]          # [N,1,1,W2 >> l], the reference's shape
+        self._geo_reference_layout = [r.unsqueeze(2) for r in self._geo_rows]       # [N,C,1,D >> l]
+
+    def _lookup_autograd(self, disp, coords, noisy):
+        """geometry_ddim.py:33-69 / geometry.py:34-58 on the differentiable rows."""
+        import torch.nn.functional as F
+        r = self.radius
+        b, _, h, w = disp.shape
+        N = b * h * w
+        dx = torch.arange(-r, r + 1, device=disp.device, dtype=torch.float32).view(1, 2 * r + 1)
+        d0 = disp.detach().reshape(N, 1).float()
+        c0 = coords.detach().reshape(N, 1).float()
+        noise = None if noisy is None else noisy.detach().float().reshape(N, 1, -1)   # raw reshape, as the reference (:37)
+        outs = []
+        for i in range(self.num_levels):
+            geo = self._geo_rows[i]
+            if noise is not None:
+                geo = geo * noise
+                noise = F.avg_pool1d(noise, 2, 2)
+            outs.append(_sample_rows(geo, dx + d0 / 2 ** i))
+            outs.append(_sample_rows(self._corr_rows[i], c0 / 2 ** i - d0 / 2 ** i + dx))
+        return torch.cat(outs, dim=-1).view(b, h, w, -1).permute(0, 3, 1, 2).contiguous().float()
 
     @property
     def geo_volume_pyramid(self):
@@ -77,6 +147,8 @@ class Combined_Geo_Encoding_Volume:
         return self._geo_filtered
 
     def __call__(self, disp, coords, noisy=None):
+        if self._autograd:
+            return self._lookup_autograd(disp, coords, noisy)
         pyr = self._geo_packed if noisy is None else self._filtered_pyramid(noisy)
         return ops.geo_lookup_packed(pyr, self.init_corr_pyramid, disp.float(), coords.float(), None, self.radius)
 

@@ -668,6 +668,46 @@ def disparity_regression_bwd(grad_out: torch.Tensor, maxdisp: int) -> torch.Tens
     return gx
 
 
+def softmax_regress_bwd(cost: torch.Tensor, grad_disp: torch.Tensor) -> torch.Tensor:
+    """Gradient of disparity_regression(F.softmax(cost, 1)) w.r.t. cost [B,D,H,W]; grad_disp is [B,H,W] (or [B,1,H,W])."""
+    B, D, H, W = cost.shape
+    _need_cuda(cost, grad_disp)
+    cost, grad_disp = _f32c(cost, "cost"), _f32c(grad_disp, "grad_disp")
+    assert grad_disp.numel() == B * H * W
+    gx = torch.empty_like(cost)
+    if gx.numel():
+        with torch.cuda.device(gx.device):
+            check(_lib.lib().dv_softmax_regress_bwd_f32(_ptr(cost), _ptr(grad_disp), _ptr(gx), B, D, H, W, _stream(gx)),
+                  "dv_softmax_regress_bwd_f32")
+    return gx
+
+
+def acv_volume_bwd(grad_out: torch.Tensor, cl: torch.Tensor, cr: torch.Tensor, att_weights: Optional[torch.Tensor],
+                   n: Optional[torch.Tensor], *, mask_left: bool = False, need_cl: bool = True, need_cr: bool = True,
+                   need_att: bool = True):
+    """Gradients of out = (concat(cl, cr) * att_weights) * n (`concat_volume_weighted`) w.r.t. cl, cr and the attention
+    LOGITS (att_weights = softmax over D of them).  Returns (grad_cl, grad_cr, grad_att [B,D,H,W]); entries not needed
+    are None."""
+    B, C2, D, H, W = grad_out.shape
+    Cc = C2 // 2
+    _need_cuda(grad_out, cl, cr, att_weights, n)
+    grad_out, cl, cr = _f32c(grad_out, "grad_out"), _f32c(cl, "cl"), _f32c(cr, "cr")
+    assert tuple(cl.shape) == (B, Cc, H, W) and tuple(cr.shape) == (B, Cc, H, W)
+    for name, t in (("att_weights", att_weights), ("n", n)):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != B * D * H * W):
+            raise RuntimeError(f"{name} must be a contiguous float32 [B,{D},{H},{W}] map")
+    need_att = need_att and att_weights is not None
+    gcl = torch.empty_like(cl) if need_cl else None
+    gcr = torch.empty_like(cr) if need_cr else None
+    gatt = torch.empty((B, D, H, W), dtype=torch.float32, device=grad_out.device) if need_att else None
+    if grad_out.numel() and (need_cl or need_cr or need_att):
+        with torch.cuda.device(grad_out.device):
+            check(_lib.lib().dv_acv_volume_bwd_f32(_ptr(grad_out), _ptr(cl), _ptr(cr), _ptr(att_weights), _ptr(n), _ptr(gcl),
+                                                   _ptr(gcr), _ptr(gatt), B, Cc, H, W, D, int(mask_left), _stream(grad_out)),
+                  "dv_acv_volume_bwd_f32")
+    return gcl, gcr, gatt
+
+
 # --------------------------------------------------------------------------------------------
 # IGEV geometry
 # --------------------------------------------------------------------------------------------

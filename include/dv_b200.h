@@ -349,6 +349,20 @@ int dv_concat_volume_bwd_f32(const float *grad_out, float *grad_ref, float *grad
                              int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int mask_left, void *stream);
 int dv_disparity_regression_bwd_f32(const float *grad_out, float *grad_x, int64_t B, int64_t D, int64_t H, int64_t W,
                                     void *stream);
+/* Backward of the FUSED forward ops — what the training branch of ACVNet_DDIM.forward / ACVNet.forward differentiates
+ * between its convolutions (SceneFlow/models/acv_ddim.py:388-390,446-480; acv.py:203,213-236; SceneFlow/main.py:154).
+ *   dv_softmax_regress_bwd_f32 : d_cost[b,d,p] = softmax_d(cost)[b,d,p] * (d - disp[b,p]) * grad_disp[b,p]  for
+ *        disp = disparity_regression(F.softmax(cost, 1)); the softmax is recomputed, never stored.
+ *   dv_acv_volume_bwd_f32 : out = (concat(cl, cr) * att_weights) * n (dv_concat_volume_weighted_f32; either factor may
+ *        be NULL = 1).  grad_cl / grad_cr [B,C,H,W] and grad_att_logits [B,D,H,W] (gradient of the LOGITS whose softmax
+ *        over D is att_weights; needs cl, cr, att_weights); any output may be NULL.  n carries no gradient in the
+ *        reference (torch.tensor(noisy), acv_ddim.py:449).
+ * The gradient of the filter multiply vol * n with respect to vol is dv_volume_filter_f32 applied to grad_out.        */
+int dv_softmax_regress_bwd_f32(const float *cost, const float *grad_disp, float *grad_cost,
+                               int64_t B, int64_t D, int64_t H, int64_t W, void *stream);
+int dv_acv_volume_bwd_f32(const float *grad_out, const float *cl, const float *cr, const float *att_weights,
+                          const float *n, float *grad_cl, float *grad_cr, float *grad_att_logits,
+                          int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int mask_left, void *stream);
 
 /* ---- f3: warp  (KITTI12/models/submodule.py:137-176; SceneFlow/submodule.py:188-227)
  * out[b,c,y,x] = mask * bilinear(x_in[b,c], ix, iy), zero padding, ix = (x - disp[b,0,y,x]) * W/(W-1) - 0.5,

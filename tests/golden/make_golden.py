@@ -491,10 +491,65 @@ def gen_f4():
     print("f4:", len(out), "arrays")
 
 
+def gen_tier3():
+    """Forward-level fixtures: the reference's UNMODIFIED ACVNet_DDIM.forward (eval branch with its own ddim_sample /
+    model_predictions, and training branch with autograd) and ACVNet.forward, run on the real classes whose out-of-scope
+    sub-networks were swapped for the light stand-ins of tests/acv_standin.py (same seeded weights on the GPU box)."""
+    import warnings
+
+    import torch
+    sys.path.insert(0, str(REF / "SceneFlow"))
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    warnings.simplefilter("ignore")
+    import models.acv as acv
+    import models.acv_ddim as acv_ddim
+    from acv_standin import SeededNoise, graft, t3_inputs
+    out = {}
+    left, right, used, disp_q, mask_gt = (_t(a) for a in t3_inputs())
+
+    def draws(rng):
+        return np.array(["|".join(map(str, d)) for d in rng.log])
+
+    net = graft(acv_ddim.ACVNet_DDIM(192, False, False)).eval()
+    with SeededNoise() as rng, torch.no_grad():
+        out["t3.eval.pred"] = net(left, right, used, disp_q, None)[0].numpy()
+    out["t3.eval.draws"] = draws(rng)
+    with SeededNoise() as rng, torch.no_grad():
+        out["t3.eval_mask.pred"] = net(left, right, used, disp_q, mask_gt)[0].numpy()
+
+    def train_pass(model, args, tag):
+        model.train()
+        model.zero_grad()
+        with SeededNoise() as rng:
+            preds = model(*args)
+        loss = 0
+        for i, p in enumerate(preds):
+            out[f"t3.{tag}.pred{i}"] = p.detach().numpy()
+            loss = loss + (p * _t(synth.normal(tuple(p.shape), 9700 + i))).sum() / p.numel()
+        loss.backward()
+        out[f"t3.{tag}.draws"] = draws(rng)
+        for name, p in model.named_parameters():
+            if p.grad is not None:
+                out[f"t3.{tag}.grad.{name}"] = p.grad.numpy().copy()
+        out[f"t3.{tag}.n_preds"] = np.array(len(preds))
+
+    train_pass(net, (left, right, None, disp_q, None), "train")
+    train_pass(net, (left, right, None, disp_q, mask_gt), "train_mask")
+    # ACVNet (acv.py:167-247): eval, training, frozen-attention training, attention-only training
+    for tag, (attn_only, freeze) in {"acv": (False, False), "acv_freeze": (False, True), "acv_attn": (True, False)}.items():
+        net2 = graft(acv.ACVNet(192, attn_only, freeze)).eval()
+        with torch.no_grad():
+            out[f"t3.{tag}.eval.pred"] = net2(left, right)[0].numpy()
+        train_pass(net2, (left, right), f"{tag}.train")
+    np.savez_compressed(HERE / "tier3.npz", **out)
+    print("tier3:", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sceneflow", "kitti12", "kitti15", "f4"]
+    which = sys.argv[1:] or ["sceneflow", "kitti12", "kitti15", "f4", "tier3"]
     if len(which) == 1 and os.environ.get("DV_GOLDEN_CHILD") == "1":
-        {"sceneflow": gen_sceneflow, "kitti12": gen_kitti12, "kitti15": gen_kitti15, "f4": gen_f4}[which[0]]()
+        {"sceneflow": gen_sceneflow, "kitti12": gen_kitti12, "kitti15": gen_kitti15, "f4": gen_f4,
+         "tier3": gen_tier3}[which[0]]()
     else:
         for name in which:
             env = dict(os.environ, DV_GOLDEN_CHILD="1")

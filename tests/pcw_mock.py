@@ -2,16 +2,15 @@
 
 tests/golden/make_golden.py binds the REFERENCE's unmodified `q_sample`, `predict_noise_from_start`, `model_predictions`
 and `ddim_sample` (pwcnet_ddim.py:453-602) onto this class on the CPU to mint the golden trace (the reference's own warp /
-build_corrleation_volume / disparity_regression run underneath); tests/test_gpu_sampler_pcw.py binds
-diffuvolume_b200.sampler's drop-ins and `drop_in_model_predictions` below (the same step on the CUDA ops) onto the same
-class.  The 3-D hourglasses, `dispupsample` and `refinenet3` are replaced by cheap deterministic modules — they are out of
+build_corrleation_volume / disparity_regression run underneath); tests/test_gpu_sampler_pcw.py lets
+diffuvolume_b200.install bind the product's tier-2 drop-ins (q_sample, predict_noise_from_start, model_predictions,
+ddim_sample) onto the same class.  The 3-D hourglasses, `dispupsample` and `refinenet3` are replaced by cheap deterministic modules — they are out of
 scope and only have to make the trace sensitive to the filter, the regression, the warp and the +-24
 correlation volume.
 """
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 import synth
 
@@ -76,27 +75,3 @@ def pcw_trace_inputs(device="cpu"):
     fr = {"finetune_feature": t(synth.normal((B, Cf, h, w), 506))}
     shifts = {tt: t(synth.normal((B, D), 510 + i) * np.float32(0.1)) for i, tt in enumerate(c["times"])}
     return dict(volume=t(volume), used=t(used), gt_q=t(gt_q), fl=fl, fr=fr, shifts=shifts)
-
-
-def drop_in_model_predictions(self, volume, noise, t, features_left, features_right):
-    """PWCNet_ddim.model_predictions (pwcnet_ddim.py:466-528) as it runs once the tier-1 names are rebound: the same
-    sequence on the CUDA ops (filter :468-472, softmax + regression :480-484 with align_corners=True, warp + +-24
-    correlation :493-494, x_start :504-524, pred_noise :526).  Returns (pred_noise, x_start, disp_finetune, pred3_volume)."""
-    from diffuvolume_b200 import kitti12, ops
-    b, c, d, h, w = volume.shape
-    shift = self.time_embedding(torch.zeros(b, d, 1, 1, device=volume.device), t).reshape(b, d)
-    vol_f, n = ops.volume_filter(volume, noise, shift, self.scale, return_n=True)
-    cost3 = self.classif3(self.dres4(self.dres3(self.dres2(vol_f))))
-    cost3 = F.interpolate(cost3, [self.maxdisp, h * 4, w * 4], mode="trilinear", align_corners=True).squeeze(1)
-    r = ops.softmax_regress(cost3, return_prob=True)
-    pred3 = r["disp"].unsqueeze(1)
-    fl = F.interpolate(features_left["finetune_feature"], [h * 4, w * 4], mode="bilinear", align_corners=True)
-    fr = F.interpolate(features_right["finetune_feature"], [h * 4, w * 4], mode="bilinear", align_corners=True)
-    fr_warp = kitti12.warp(fr, pred3)
-    costvolume = kitti12.build_corrleation_volume(fl, fr_warp, 24, 1).squeeze(1)
-    combine = torch.cat((fl - fr_warp, fl, self.dispupsample(pred3), pred3, costvolume), dim=1)
-    disp = self.refinenet3(combine, pred3).squeeze(1)
-    H, W = disp.shape[-2:]
-    disp_q = ops.downsample_bilinear(disp.contiguous(), (H // 4, W // 4), clamp=(0, self.maxdisp - 1), post_scale=0.25)
-    x_start = ops.xstart_from_disp(disp_q, d, self.scale)
-    return self.predict_noise_from_start(n, t, x_start), x_start, disp, r["prob"]

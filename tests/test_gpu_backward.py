@@ -111,3 +111,73 @@ def test_training_style_graph_matches_cpu_autograd():
     for a, b in zip(leaves_gpu, leaves_cpu):
         want = b.grad.numpy()
         assert np.abs(a.grad.cpu().numpy() - want).max() / np.abs(want).max() < 1e-4
+
+
+# ---- backward of the FUSED forward ops (csrc/fused_backward.cu) ----------------------------------------------------------
+@pytest.mark.parametrize("shape,D,with_n", [((2, 32, 9, 40), 48, True), ((1, 8, 5, 12), 8, False), ((1, 4, 6, 20), 20, True),
+                                            ((1, 32, 27, 60), 48, True), ((2, 3, 4, 8), 100, False)])
+def test_acv_attention_volume_backward(shape, D, with_n):
+    """(concat(cl, cr) * softmax(att, 2)) * n: gradients w.r.t. the concat features AND the attention logits
+    (acv_ddim.py:388-390, :446-451) against float64 autograd of the reference's op sequence."""
+    from diffuvolume_b200 import functional as Fn
+    B, C, H, W = shape
+    cl, cr = synth.normal(shape, 401), synth.normal(shape, 402)
+    att = synth.normal((B, 1, D, H, W), 403) * np.float32(2)
+    n = synth.uniform((B, D, H, W), 404, dtype=np.float32) if with_n else None
+    g = synth.normal((B, 2 * C, D, H, W), 405)
+    l_gpu = [_leaf(a, "cuda", torch.float32) for a in (cl, cr, att)]
+    l_cpu = [_leaf(a, "cpu", torch.float64) for a in (cl, cr, att)]
+    out = Fn.acv_attention_volume(*l_gpu, D, n=None if n is None else torch.from_numpy(n).cuda())
+    ref = torch.softmax(l_cpu[2], dim=2) * P.concat_volume(l_cpu[0], l_cpu[1], D, False)
+    if n is not None:
+        ref = ref * torch.from_numpy(n).double().unsqueeze(1)
+    assert np.abs(out.detach().cpu().numpy() - ref.detach().numpy()).max() < 1e-5 * max(1.0, float(ref.abs().max()))
+    out.backward(torch.from_numpy(g).cuda())
+    ref.backward(torch.from_numpy(g).double())
+    for a, b in zip(l_gpu, l_cpu):
+        want = b.grad.numpy()
+        err = np.abs(a.grad.cpu().numpy().astype(np.float64) - want).max() / max(np.abs(want).max(), 1e-30)
+        assert a.grad.shape == b.grad.shape and err < 5e-5, err
+
+
+def test_acv_attention_volume_backward_skips_what_is_not_needed():
+    from diffuvolume_b200 import functional as Fn
+    B, C, D, H, W = 1, 4, 12, 4, 16
+    cl = torch.from_numpy(synth.normal((B, C, H, W), 411)).cuda().requires_grad_(True)
+    cr = torch.from_numpy(synth.normal((B, C, H, W), 412)).cuda()
+    att = torch.from_numpy(synth.normal((B, 1, D, H, W), 413)).cuda()          # frozen attention (acv.py:169-184)
+    Fn.acv_attention_volume(cl, cr, att, D).sum().backward()
+    assert cl.grad is not None and cr.grad is None and att.grad is None
+
+
+@pytest.mark.parametrize("shape", [(2, 192, 8, 20), (1, 48, 6, 20), (1, 96, 5, 12), (1, 7, 3, 5), (1, 200, 4, 8), (1, 192, 5, 13)])
+def test_softmax_disparity_regression_backward(shape):
+    """disparity_regression(F.softmax(cost, 1)) fused, forward and backward (acv_ddim.py:460-480, SceneFlow/main.py:154)."""
+    from diffuvolume_b200 import functional as Fn
+    B, D, H, W = shape
+    x = synth.normal(shape, 421) * np.float32(3)
+    g = synth.normal((B, H, W), 422)
+    x1, x2 = _leaf(x, "cuda", torch.float32), _leaf(x, "cpu", torch.float64)
+    o1 = Fn.softmax_disparity_regression(x1, D)
+    o2 = torch.sum(torch.softmax(x2, 1) * torch.arange(D, dtype=torch.float64).view(1, D, 1, 1), 1)
+    assert np.abs(o1.detach().cpu().numpy() - o2.detach().numpy()).max() < 1e-3
+    o1.backward(torch.from_numpy(g).cuda())
+    o2.backward(torch.from_numpy(g).double())
+    want = x2.grad.numpy()
+    assert np.abs(x1.grad.cpu().numpy() - want).max() / np.abs(want).max() < 2e-5
+
+
+def test_volume_filter_backward():
+    """vol * n (acv_ddim.py:260): the gradient w.r.t. the volume is the same kernel applied to grad_out."""
+    from diffuvolume_b200 import functional as Fn
+    B, C, D, H, W = 2, 6, 12, 5, 16
+    vol = synth.normal((B, C, D, H, W), 431)
+    xt = synth.normal((B, D, H, W), 432, dtype=np.float64)
+    shift = synth.normal((B, D), 433) * np.float32(0.1)
+    g = synth.normal((B, C, D, H, W), 434)
+    v1 = _leaf(vol, "cuda", torch.float32)
+    out = Fn.volume_filter(v1, torch.from_numpy(xt).cuda(), torch.from_numpy(shift).cuda(), 1.0)
+    out.backward(torch.from_numpy(g).cuda())
+    n = ((np.clip(xt + shift.astype(np.float64)[:, :, None, None], -1, 1) + 1) / 2).astype(np.float32)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), vol * n[:, None], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(v1.grad.cpu().numpy(), g * n[:, None], rtol=1e-6, atol=1e-7)

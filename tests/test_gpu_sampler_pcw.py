@@ -1,4 +1,5 @@
-"""PCWNet tier-2 drop-ins (diffuvolume_b200.sampler.pcw_ddim_sample, q_sample, predict_noise_from_start) bound onto
+"""PCWNet tier-2 drop-ins (diffuvolume_b200.sampler: q_sample, predict_noise_from_start, pcw_model_predictions,
+pcw_ddim_sample), bound by diffuvolume_b200.install — the same table it applies to the reference's PWCNet_ddim — onto
 tests/pcw_mock.py:MockPCW and replayed against the trace that the REFERENCE's own PWCNet_ddim.model_predictions /
 ddim_sample (KITTI12/models/pwcnet_ddim.py:466-602) produced on the same mock (tests/golden/make_golden.py:
 _pcw_sampler_trace): same stand-in conv modules, same injected noise; filter, softmax-regression, warp, +-24 correlation
@@ -9,7 +10,7 @@ import torch
 
 import synth
 from oracle import dv_oracle as O
-from pcw_mock import PCW_TRACE, MockPCW, drop_in_model_predictions, pcw_trace_inputs
+from pcw_mock import PCW_TRACE, MockPCW, pcw_trace_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -31,13 +32,15 @@ def golden():
 
 @pytest.fixture()
 def bound(golden):
-    from diffuvolume_b200 import sampler
+    import types
+
+    from diffuvolume_b200 import install as dvi
     inp = pcw_trace_inputs("cuda")
     net = MockPCW(O.Schedule(), inp["shifts"]).cuda()
-    for name, fn in (("q_sample", sampler.q_sample), ("predict_noise_from_start", sampler.predict_noise_from_start),
-                     ("model_predictions", drop_in_model_predictions), ("ddim_sample", sampler.pcw_ddim_sample)):
-        setattr(MockPCW, name, fn)
-    return net, inp, cu(golden["pcw.asd"])
+    done = dvi.install("kitti12", modules={"models.pwcnet_ddim": types.SimpleNamespace(PWCNet_ddim=MockPCW)})
+    assert "models.pwcnet_ddim.PWCNet_ddim.model_predictions" in done and "models.pwcnet_ddim.PWCNet_ddim.ddim_sample" in done
+    yield net, inp, cu(golden["pcw.asd"])
+    dvi.uninstall()
 
 
 def test_pcw_model_predictions_replays_reference_steps(bound, golden):
