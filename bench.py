@@ -246,6 +246,35 @@ def run_ours(args):
         checksum = float(cs[0].item())
     ms_per_step = ms_total / args.steps
     value = (B * world) / (ms_per_step / 1e3)
+    # ---- the one collective of the path: the end-of-sweep metric vector — per-batch EPE / D1 / Thres sums
+    # of this rank's shard against a synthetic ground truth — reduced with ONE all_reduce(SUM) over NCCL
+    from diffuvolume_b200.distributed import MetricSums
+    msums = MetricSums()
+    gt = inp["used"] + 0.75
+    msums.update(out["pred"], gt, (gt < MAXDISP) & (gt > 0))
+    metrics = msums.reduce(device=dev)
+    metrics["note"] = ("EPE/D1/Thres of the ensemble prediction vs a synthetic ground truth, MetricSums.reduce(): one "
+                       + ("NCCL all_reduce(SUM) of 8 float64" if world > 1 else "local sum (world size 1)"))
+    # ---- sustained leg: the same step back to back for >= 2 s with its own clock record (the headline's timed region
+    # is a burst of `steps` x ~7 ms)
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(args.sustained_seconds / (ms_per_step / 1e3)) + 1)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(gpu_index) as clk2:
+            barrier()
+            s0.record()
+            for _ in range(n_sus):
+                step()
+            s1.record()
+            barrier()
+        sms = s0.elapsed_time(s1)
+        if dist is not None:
+            tt = torch.tensor([sms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sms = float(tt.item())
+        sustained = {"value": round(B * world * n_sus / (sms / 1e3), 2), "unit": "pairs/s", "steps": n_sus,
+                     "seconds": round(sms / 1e3, 3), "ms_per_step": round(sms / n_sus, 4), "clocks": clk2.summary()}
 
     result = None
     if rank == 0:
@@ -289,6 +318,8 @@ def run_ours(args):
                          "whole_step_frac": round(step_bytes / 1e9 / (ms_per_step / 1e3) / peak, 4)},
             "kernels": kernels,
             "checksum": checksum,
+            "metrics": metrics,
+            "sustained": sustained,
         }
     # ---- the same step replayed from a CUDA graph (no per-kernel events possible inside a graph, hence a separate
     # leg): at B = 8 the step is bandwidth-bound and the two agree; at B = 1 — the reference's own evaluation batch —
@@ -356,8 +387,15 @@ def run_ours(args):
                  "ms_per_step": round(fms / args.steps, 4), "e2e": fe2e,
                  "note": "same step with the trilinear x4 upsample fused into softmax/regression (SURVEY.md 8f row f2): "
                          "per-step input [B,1,48,135,240] instead of [B,192,540,960]"}
+    legs = None
+    if not args.no_legs:
+        inp = path = out = finp = fpath = gt = None      # release the headline leg's buffers (rebinding also clears `step`'s cells)
+        torch.cuda.empty_cache()
+        legs = extra_legs(args, dev, rank, world, barrier, dist)
     if rank == 0:
         result["e2e"] = e2e
+        if legs:
+            result.update(legs)
         if graph_leg is not None:
             result["cuda_graph"] = graph_leg
         if fused is not None:
@@ -366,9 +404,227 @@ def run_ours(args):
             cb, cpu_in, cpu_pred0, cpu_out = cpu_reference(steps=args.cpu_steps, warmup=1, regress=args.regress, keep_io=True)
             result["cpu_baseline"] = cb
             result["parity"] = parity_against_cpu_leg(cpu_in, cpu_pred0, cpu_out, args.filter, args.regress, dev)
+            result["gpu_aten_baseline"] = gpu_aten_baseline(cpu_in, args.regress, dev)
         emit(result)
     if dist is not None:
         dist.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------------
+# Extra legs of the default run: the ACV step at the north_star's second resolution and the hot-path kernel
+# sequences of configs[2] (PCWNet) and configs[3] (IGEV), each with its own roofline, a parity gate against the
+# reference's op sequence (oracle/torch_port.py) run on CUDA tensors on the same inputs at B = 1, and that run's time
+# as the `gpu_aten_baseline` (what a user of the reference gets on this very GPU today).
+# ------------------------------------------------------------------------------------------------
+def _timed(fn, steps, warmup, barrier, dist, dev):
+    for _ in range(warmup):
+        fn(None)
+    barrier()
+    timer = KernelTimer()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn(timer)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return ms / steps, timer.resolve()
+
+
+def _leg_result(name, B, world, ms_per_step, kt, steps, ab, extra_cfg):
+    peak, peak_src = measured_peak_gbs()
+    kernels = {}
+    for k, times in kt.items():
+        avg = sum(times) / len(times)
+        per_launch = ab.get(k, 0) / max(1, len(times) // steps)
+        kernels[k] = {"launches_per_step": len(times) // steps, "avg_ms": round(avg, 4),
+                      "ms_per_step": round(sum(times) / steps, 4), "algorithmic_GB_per_step": round(ab.get(k, 0) / 1e9, 4),
+                      "achieved_GBs": round(per_launch / 1e9 / (avg / 1e3), 1),
+                      "frac_of_peak": round(per_launch / 1e9 / (avg / 1e3) / peak, 4)}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    step_bytes = sum(ab.get(k, 0) for k in kernels)
+    return {"value": round(B * world / (ms_per_step / 1e3), 2), "unit": "pairs/s", "ms_per_step": round(ms_per_step, 4),
+            "config": dict(extra_cfg, pairs_per_gpu=B),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBs"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom]["frac_of_peak"], "peak_source": peak_src,
+                         "whole_step_achieved": round(step_bytes / 1e9 / (ms_per_step / 1e3), 1),
+                         "whole_step_frac": round(step_bytes / 1e9 / (ms_per_step / 1e3) / peak, 4)},
+            "kernels": kernels}
+
+
+def _aten_time(fn, steps=3):
+    """CUDA-event time of the reference op sequence (torch_port on CUDA tensors), B = 1."""
+    out = fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def _relerr(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def pcw_inputs(B, dev, seed, Hp=384, Wp=1248):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    rn = lambda *s, dt=torch.float32: torch.randn(*s, generator=g, device=dev, dtype=dt)
+    ru = lambda *s: torch.rand(*s, generator=g, device=dev)
+    D, h, w = 48, Hp // 4, Wp // 4
+    from diffuvolume_b200 import ops
+    return dict(
+        scales=[(rn(B, 320, Hp // s, Wp // s), rn(B, 320, Hp // s, Wp // s), rn(B, 12, Hp // s, Wp // s),
+                 rn(B, 12, Hp // s, Wp // s), D * 4 // s) for s in (4, 8, 16, 32)],
+        combine=rn(B, 32, D, h, w), costs=[rn(B, 192, Hp, Wp) * 4.0], used=ru(B, Hp, Wp) * 191.0,
+        feat_l_full=rn(B, 32, Hp, Wp), feat_r_full=rn(B, 32, Hp, Wp), start=rn(B, D, h, w),
+        asd=ops.xstart_from_disp(ru(B, h, w) * 47.75, D, 1.0), shifts=[rn(B, D) * 0.1 for _ in range(3)],
+        step_noises=[rn(B, D, h, w, dt=torch.float32 if i == 0 else torch.float64) for i in range(2)],
+        q_noises=[rn(B, D, h, w) for _ in range(2)])
+
+
+def pcw_bytes(B, Hp=384, Wp=1248):
+    F4, D, HW, hw = 4, 48, Hp * Wp, (Hp // 4) * (Wp // 4)
+    sc = [((Hp // s) * (Wp // s), D * 4 // s) for s in (4, 8, 16, 32)]
+    T = 3
+    per_pair = {
+        "gwc_volume": sum((2 * 320 + 40 * Ds) * p for p, Ds in sc) * F4,
+        "concat_volume": sum((2 * 12 + 24 * Ds) * p for p, Ds in sc) * F4,
+        "filter": T * (2 * 32 * D * hw * F4 + 2 * D * hw * 8),                       # volume in/out, x_t in, n out
+        "softmax_regress": T * (2 * 192 * HW + HW) * F4,                              # logits in, probabilities + disparity out
+        "warp": T * (2 * 32 + 1) * HW * F4,
+        "corr_volume_2sided": T * (2 * 32 + 49) * HW * F4,
+        "uncertainty_vote": (T - 1) * (192 + 3) * HW * F4,
+        "ddim_step": T * (2 * HW * F4 + D * hw * (8 + 8 + 4 + 4 + 8 + 8 + 4)),
+        "ensemble": (T + 2) * HW * F4,
+    }
+    return {k: v * B for k, v in per_pair.items()}
+
+
+def igev_inputs(B, dev, seed, Hp=384, Wp=1248):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    rn = lambda *s, dt=torch.float32: torch.randn(*s, generator=g, device=dev, dtype=dt)
+    ru = lambda *s: torch.rand(*s, generator=g, device=dev)
+    D, h, w = 48, Hp // 4, Wp // 4
+    from diffuvolume_b200 import ops
+    return dict(
+        fmap_l=rn(B, 96, h, w), fmap_r=rn(B, 96, h, w), geo=rn(B, 8, D, h, w), cost48=rn(B, D, h, w) * 4.0,
+        up_weights=torch.softmax(rn(B, 9, Hp, Wp), 1),
+        coords=torch.arange(w, device=dev, dtype=torch.float32).view(1, 1, 1, w).expand(B, 1, h, w).contiguous(),
+        used=ru(B, Hp, Wp) * 47.0, start=rn(B, D, h, w), asd=ops.xstart_from_disp(ru(B, h, w) * 47.0, D, 1.0),
+        shifts=[rn(B, D) * 0.1 for _ in range(2)], step_noises=[rn(B, D, h, w)], q_noises=[rn(B, D, h, w)])
+
+
+def igev_bytes(B, iters=32, Hp=384, Wp=1248):
+    F4, D, HW, h, w = 4, 48, Hp * Wp, Hp // 4, Wp // 4
+    hw, T = h * w, 2
+    look = (2 * (10 * 8 + 10) + 162 + 2) * hw * F4          # per call: two levels x 10 hypotheses x (8 geo + 1 corr), out, disp/coords
+    per_pair = {
+        "gwc_volume": (2 * 96 + 8 * D) * hw * F4,
+        "softmax_regress": (D + 1) * hw * F4,
+        "geo_init": (2 * 96 * hw + 1.5 * hw * w + 2.5 * 8 * D * hw) * F4,           # all-pairs corr (+ pooled level), geo pack
+        "filter_factor": T * D * hw * (8 + 4),
+        "geo_filter": T * (3 * 1.5 * 8 * D * hw * F4 + look),                        # pyramid in/out + noise, then the lookup
+        "geo_lookup": T * (iters - 1) * look,
+        "context_upsample": T * (10 * HW + hw) * F4,
+        "fallback": T * 3 * HW * F4,
+        "ddim_step": T * (3 * HW * F4 + D * hw * (8 + 8 + 4 + 4 + 8 + 8)),
+        "ensemble": (T + 2) * HW * F4,
+    }
+    return {k: v * B for k, v in per_pair.items()}
+
+
+def extra_legs(args, dev, rank, world, barrier, dist):
+    """size_384x1248 / pcwnet / igev legs (rank 0 returns the dict)."""
+    from diffuvolume_b200.pipeline import AcvHotPath, IgevHotPath, PcwHotPath
+    B, steps, warmup = args.batch, max(3, args.steps // 2), args.warmup
+    legs = {}
+    do_parity = rank == 0 and not args.no_cpu_baseline
+    if do_parity:
+        from oracle import dv_oracle as O
+        from oracle import torch_port as P
+
+    # ---- the ACV step at 384x1248 (376x1248 padded): north_star's second resolution
+    global H, W
+    H0, W0 = H, W
+    if (H0, W0) == (540, 960):
+        H, W = 384, 1248
+        inp = make_inputs(B, dev, seed=2234 + rank, regress="logits")
+        path = AcvHotPath(filter_mode=args.filter, regress_mode="logits")
+        ms, kt = _timed(lambda t: path(**inp, timer=t), steps, warmup, barrier, dist, dev)
+        per_launch = algorithmic_bytes(B, args.filter, "logits")
+        ab = {k: v * (T_STEPS if k in ("filter", "softmax_regress", "ddim_step") else 1) for k, v in per_launch.items()}
+        legs["size_384x1248"] = _leg_result("size_384x1248", B, world, ms, kt, steps, ab,
+                                            {"workload": "the headline ACV step at 384x1248 (KITTI, 376 rows padded), D=192",
+                                             "filter_mode": args.filter})
+        del inp, path
+        torch.cuda.empty_cache()
+        H, W = H0, W0
+
+    # ---- configs[2]: PCWNet + DiffuVolume, 384x1248
+    pin = pcw_inputs(B, dev, 3234 + rank)
+    ppath = PcwHotPath()
+    ms, kt = _timed(lambda t: ppath(**pin, timer=t), steps, warmup, barrier, dist, dev)
+    leg = _leg_result("pcwnet", B, world, ms, kt, steps, pcw_bytes(B),
+                      {"workload": "configs[2]: PCWNet+DiffuVolume KITTI12 384x1248: 4-scale gwc + concat(T); T=3 x {filter, "
+                                   "softmax/regression (+prob), warp, +-24 corr volume, uncertainty vote, DDIM step}; ensemble"})
+    if do_parity:
+        one = pcw_inputs(1, dev, 777)
+        got = ppath(**one, keep=True)
+        sched = O.Schedule(sampling_timesteps=3)
+        ams, (pred, (x_last, mask, prob, corr, vols)) = _aten_time(lambda: P.pcw_hot_path_pair(**one, sched=sched))
+        err = (got["pred"] - pred).abs()
+        leg["parity"] = {"epe_px": float(err.mean()), "max_err_px": float(err.max()),
+                         "corr_volume_max_rel_err": _relerr(got["corr"].squeeze(1), corr),
+                         "gwc_volume_max_rel_err": max(_relerr(gv, v[:, :40]) for (gv, _), v in zip(got["volumes"], vols)),
+                         "concat_volume_bit_exact": all(bool(torch.equal(cv, v[:, 40:])) for (_, cv), v in zip(got["volumes"], vols)),
+                         "prob_max_abs_err": float((got["prob"] - prob).abs().max()),
+                         "state_rel_err": _relerr(got["x_last"].double(), x_last.double()),
+                         "renewal_mask_agreement": float((got["mask"] == mask).float().mean()),
+                         "gates": {"epe_px": 0.01, "volume_max_rel_err": 1e-4},
+                         "checker": "oracle/torch_port.py:pcw_hot_path_pair on CUDA tensors, same inputs, B=1"}
+        leg["gpu_aten_baseline"] = {"value": round(1e3 / ams, 2), "unit": "pairs/s", "ms_per_pair": round(ams, 3),
+                                    "what": "the reference's op sequence (ATen kernels) for this leg on this GPU, B=1"}
+        del one, got, pred, x_last, mask, prob, corr, vols
+    legs["pcwnet"] = leg
+    del pin
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: IGEV + DiffuVolume, 384x1248
+    iin = igev_inputs(B, dev, 4234 + rank)
+    ipath = IgevHotPath()
+    ms, kt = _timed(lambda t: ipath(**iin, timer=t), steps, warmup, barrier, dist, dev)
+    leg = _leg_result("igev", B, world, ms, kt, steps, igev_bytes(B, ipath.iters),
+                      {"workload": "configs[3]: IGEV+DiffuVolume KITTI15 384x1248: gwc + regression(D=48) + all-pairs corr + geo "
+                                   "pyramid; T=2 x {filter factor, geo filter, 32 x pyramid lookup, context_upsample, DDIM step}; ensemble",
+                       "gru_iters": ipath.iters})
+    if do_parity:
+        one = igev_inputs(1, dev, 778)
+        got = ipath(**one, keep=True)
+        sched = O.Schedule(sampling_timesteps=2)
+        ams, (pred, (x_last, mask, look, gwc)) = _aten_time(lambda: P.igev_hot_path_pair(**one, sched=sched, iters=ipath.iters), steps=2)
+        err = (got["pred"] - pred).abs()
+        leg["parity"] = {"epe_px": float(err.mean()), "max_err_px": float(err.max()),
+                         "lookup_max_rel_err": _relerr(got["lookup"], look), "gwc_volume_max_rel_err": _relerr(got["gwc"], gwc),
+                         "state_rel_err": _relerr(got["x_last"].double(), x_last.double()),
+                         "renewal_mask_agreement": float((got["mask"] == mask).float().mean()),
+                         "gates": {"epe_px": 0.01, "volume_max_rel_err": 1e-4},
+                         "checker": "oracle/torch_port.py:igev_hot_path_pair on CUDA tensors, same inputs, B=1"}
+        leg["gpu_aten_baseline"] = {"value": round(1e3 / ams, 2), "unit": "pairs/s", "ms_per_pair": round(ams, 3),
+                                    "what": "the reference's op sequence (ATen kernels) for this leg on this GPU, B=1"}
+    legs["igev"] = leg
+    del iin
+    torch.cuda.empty_cache()
+    return legs
 
 
 def run_e2e(args, path, inp, dev, barrier, dist, world):
@@ -522,6 +778,23 @@ def parity_against_cpu_leg(a, pred0, cpu_out, filter_mode, regress, dev):
             "checker": "the cpu_baseline leg's own outputs (oracle/torch_port.py on the host), same inputs, B=1"}
 
 
+def gpu_aten_baseline(a, regress, dev):
+    """The reference's op sequence for one pair (oracle/torch_port.py:hot_path_pair — what the reference's PyTorch code
+    launches between its convolutions) on CUDA tensors on THIS GPU: the baseline a user of the reference has today.
+    Stated baseline only; nothing in the product path touches it."""
+    from oracle import dv_oracle as O
+    from oracle import torch_port as P
+    to = lambda v: [t.to(dev) for t in v] if isinstance(v, (list, tuple)) else (v.to(dev) if torch.is_tensor(v) else v)
+    d = {k: to(v) for k, v in a.items()}
+    up = None if regress == "logits" else (MAXDISP, H, W)
+    sched = O.Schedule()
+    with torch.no_grad():
+        ms, _ = _aten_time(lambda: P.hot_path_pair(**d, sched=sched, upsample_to=up), steps=3)
+    return {"value": round(1e3 / ms, 2), "unit": "pairs/s", "ms_per_pair": round(ms, 3), "batch": 1,
+            "what": "oracle/torch_port.py:hot_path_pair (the reference's ATen op sequence) on CUDA tensors, same GPU, B=1, "
+                    "CUDA-event timed"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -559,6 +832,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-legs", action="store_true", help="skip the size_384x1248 / pcwnet / igev legs")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained leg")
+    ap.add_argument("--sustained-seconds", type=float, default=2.2)
     args = ap.parse_args()
     protect_stdout()
     global H, W, METRIC

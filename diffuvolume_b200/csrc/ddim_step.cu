@@ -386,6 +386,25 @@ extern "C" int dv_downsample_bilinear_f32(const float *in, float *out, int64_t B
     return finish_launch();
 }
 
+namespace dv {
+__global__ void select_close_kernel(const float *__restrict__ a, const float *__restrict__ b, float thr, float *__restrict__ out,
+                                    int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float x = a[i], y = b[i];
+        out[i] = fabsf(x - y) < thr ? x : y;
+    }
+}
+}  // namespace dv
+
+extern "C" int dv_select_close_f32(const float *a, const float *b, float thr, float *out, int64_t n, void *stream) {
+    using namespace dv;
+    if (!a || !b || !out) return DV_ERR_NULL;
+    if (n <= 0) return DV_ERR_BAD_SHAPE;
+    select_close_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, thr, out, n);
+    return finish_launch();
+}
+
 extern "C" int dv_ensemble_f32(const float *const *maps, const float *cof, int n_maps, float *out, int64_t n,
                                void *stream) {
     using namespace dv;

@@ -46,39 +46,54 @@ def per_image_metrics(d_est: torch.Tensor, d_gt: torch.Tensor, mask: torch.Tenso
 
 @dataclass
 class MetricSums:
-    """Per-rank running sums over the images of its shard; `reduce()` makes them global."""
+    """Per-rank running sums over the batches of its shard; `reduce()` makes them global.
+
+    Averaging follows the reference exactly: `compute_metric_for_each_image` (SceneFlow/utils/metrics.py:21-41) returns
+    the mean over the NON-SKIPPED images of a batch — and 0 for a batch whose images were all skipped — and
+    `AverageMeterDict.mean` (utils/experiment.py:126-151) averages those per-batch values over the batches.  So the sums
+    kept here are sums of per-batch means and the divisor is the number of batches (an all-skipped batch still counts).
+    With batch size 1 (the reference's evaluation setting) this is the per-image mean; sharding the sweep over ranks changes
+    the numbers only through which images share a batch."""
     sums: Dict[str, float] = field(default_factory=lambda: {k: 0.0 for k in METRIC_KEYS})
+    n_batches: int = 0
     n_images: int = 0
     n_skipped: int = 0
 
     def update(self, d_est: torch.Tensor, d_gt: torch.Tensor, mask: torch.Tensor) -> None:
-        """d_est, d_gt, mask: [B,H,W]."""
+        """One batch: d_est, d_gt, mask are [B,H,W]."""
         assert d_est.dim() == 3 and d_est.shape == d_gt.shape == mask.shape
+        per_image = []
         for i in range(d_est.shape[0]):
             m = per_image_metrics(d_est[i], d_gt[i], mask[i])
             if m is None:
                 self.n_skipped += 1
                 continue
-            for k in METRIC_KEYS:
-                self.sums[k] += m[k]
+            per_image.append(m)
             self.n_images += 1
+        self.n_batches += 1
+        if per_image:                      # else: the reference adds 0 for this batch
+            for k in METRIC_KEYS:
+                self.sums[k] += sum(m[k] for m in per_image) / len(per_image)
 
     def as_tensor(self, device) -> torch.Tensor:
-        return torch.tensor([self.sums[k] for k in METRIC_KEYS] + [float(self.n_images), float(self.n_skipped)],
+        return torch.tensor([self.sums[k] for k in METRIC_KEYS] + [float(self.n_batches), float(self.n_images),
+                                                                    float(self.n_skipped)],
                             dtype=torch.float64, device=device)
 
     def reduce(self, device=None, group=None) -> Dict[str, float]:
-        """Global means.  With an initialised process group: one all_reduce(SUM) of 7 float64 values
+        """Global means.  With an initialised process group: one all_reduce(SUM) of 8 float64 values
         (NCCL over NVLink on GPUs, gloo in the CPU tests); otherwise the local values."""
         dev = device if device is not None else torch.device("cpu")
         v = self.as_tensor(dev)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
         v = v.cpu()
-        n = max(float(v[len(METRIC_KEYS)]), 1.0)
+        nk = len(METRIC_KEYS)
+        n = max(float(v[nk]), 1.0)
         out = {k: float(v[i]) / n for i, k in enumerate(METRIC_KEYS)}
-        out["n_images"] = int(v[len(METRIC_KEYS)])
-        out["n_skipped"] = int(v[len(METRIC_KEYS) + 1])
+        out["n_batches"] = int(v[nk])
+        out["n_images"] = int(v[nk + 1])
+        out["n_skipped"] = int(v[nk + 2])
         return out
 
 

@@ -94,9 +94,8 @@ def install(project: str, tier2: bool = True, modules: Dict[str, object] = None,
             if cls is None:
                 continue
             for name, fn in methods.items():
-                if hasattr(cls, name):
-                    _bind(cls, name, fn)
-                    done.append(f"{mname}.{cname}.{name}")
+                _bind(cls, name, fn)
+                done.append(f"{mname}.{cname}.{name}")
     if tier2 and tier3:
         for mname, cname, methods in _TIER3[project]:
             mod = mods.get(mname)

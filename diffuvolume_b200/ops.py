@@ -483,6 +483,19 @@ def ensemble(maps: Sequence[torch.Tensor], cof: Sequence[float]) -> torch.Tensor
     return out
 
 
+def select_close(a: torch.Tensor, b: torch.Tensor, thr: float) -> torch.Tensor:
+    """torch.where(torch.abs(a - b) < thr, a, b) — IGEV's fallback to the initial disparity (igev_stereo_ddim.py:323-325)."""
+    _need_cuda(a, b)
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    assert a.numel() == b.numel()
+    out = torch.empty_like(a)
+    if out.numel():
+        with torch.cuda.device(out.device):
+            check(_lib.lib().dv_select_close_f32(_ptr(a), _ptr(b), float(thr), _ptr(out), out.numel(), _stream(out)),
+                  "dv_select_close_f32")
+    return out
+
+
 def ddim_step(*, disp: torch.Tensor, xt: torch.Tensor, shift: Optional[torch.Tensor], scale: float,
               sqrt_recip: float, sqrt_recipm1: float, last_step: bool,
               disp_clamp_hi: float = 191.0, coords0: Optional[torch.Tensor] = None,

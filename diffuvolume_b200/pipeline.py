@@ -219,3 +219,149 @@ class AcvHotPath:
     def launches_per_call(self) -> int:
         T = self.sched.sampling_timesteps
         return (6 if self.filter_mode == "regenerate" else 4) + 3 * T
+
+
+PCW_ENSEMBLE = (0.9, 0.0, 0.0, 0.1)     # pwcnet_ddim.py:599
+IGEV_ENSEMBLE = (0.6, 0.1, 0.3)         # igev_stereo_ddim.py:356
+
+
+class PcwHotPath:
+    """BASELINE.json configs[2]: the kernel sequence PWCNet_ddim.forward (eval) + ddim_sample + model_predictions
+    (KITTI12/models/pwcnet_ddim.py:604-625, :530-602, :466-528) issue outside their 2-D / 3-D convolutions, for a batch of
+    pairs: 4-scale group-wise correlation volumes (D = 48/24/12/6) + concat volumes (variant T), then T = 3 x
+    {filter multiply on `combine` [B,32,48,h,w], softmax + regression over [B,192,H,W] with the probability volume kept
+    (model_predictions returns it), warp of the full-res right refinement features by the regressed disparity, the +-24
+    two-sided correlation volume, x_start / pred_noise, the uncertainty of the refined disparity against the kept
+    probabilities + renewal vote, fused DDIM step with cumulative re-noising}, ensemble.  The refinement network itself is a
+    convolution stack (out of scope): its output is stood in for by the regressed disparity."""
+
+    def __init__(self, schedule: Optional[DdimSchedule] = None, num_groups: int = 40, maxdisp: int = 192,
+                 ensemble: Sequence[float] = PCW_ENSEMBLE):
+        self.sched = schedule or DdimSchedule(sampling_timesteps=3)
+        self.G, self.maxdisp, self.D = num_groups, maxdisp, maxdisp // 4
+        self.cof = tuple(ensemble)
+        assert len(self.cof) == self.sched.sampling_timesteps + 1
+
+    def __call__(self, scales, combine, costs, used, feat_l_full, feat_r_full, start, asd, shifts, step_noises, q_noises,
+                 keep: bool = False, timer=None):
+        """scales: [(gw_l, gw_r, cat_l, cat_r, D_s)] x 4; combine [B,32,48,h,w]; costs[i] [B,maxdisp,H,W] logits of step i
+        (len T or 1); used [B,H,W]; feat_*_full [B,32,H,W]; start [B,48,h,w] fp32 (the randn start state, pwcnet_ddim.py:541);
+        asd [B,48,h,w] x_start of the initial disparity; shifts[i] [B,48]; step_noises[i] = randn_like(img) (fp32 for i = 0,
+        fp64 after), q_noises[i] = randn_like(asd) fp32.  Returns dict(pred, x_last, mask, ...)."""
+        tm = timer if timer is not None else (lambda name: contextlib.nullcontext())
+        sched, D = self.sched, self.D
+        B, _, _, h, w = combine.shape
+        dev = combine.device
+        vols = []
+        for gl, gr, cl, cr, Ds in scales:
+            with tm("gwc_volume"):
+                gv = ops.gwc_volume(gl, gr, Ds, self.G)
+            with tm("concat_volume"):
+                cv = ops.concat_volume(cl, cr, Ds, mask_left=True)
+            if keep:
+                vols.append((gv, cv))
+        img = start
+        disps = [used]
+        mask = torch.zeros((B, h, w), dtype=torch.float32, device=dev)
+        pairs = sched.time_pairs()
+        corr = prob = None
+        for i, (t, t_next) in enumerate(pairs):
+            with tm("filter"):
+                vol_f, n = ops.volume_filter(combine, img, shifts[i], sched.scale, return_n=True)
+            cost = costs[i if len(costs) > 1 else 0]
+            with tm("softmax_regress"):
+                r = ops.softmax_regress(cost, return_prob=True)
+            disp, prob = r["disp"], r["prob"]
+            with tm("warp"):
+                warped = ops.warp(feat_r_full, disp.unsqueeze(1))
+            with tm("corr_volume_2sided"):
+                corr = ops.corr_volume_2sided(feat_l_full, warped, 24, 1)
+            # (dispupsample / refinenet3 run here in the full network — out of scope; disp stands in for disp_finetune)
+            disps.append(disp)
+            last = t_next < 0
+            if last:
+                with tm("ddim_step"):
+                    st = ops.ddim_step(disp=disp, xt=img, shift=shifts[i], scale=sched.scale, sqrt_recip=sched.sqrt_recip(t),
+                                       sqrt_recipm1=sched.sqrt_recipm1(t), last_step=True,
+                                       disp_clamp_hi=float(self.maxdisp - 1), mask=mask)
+                img = st["x_next"]
+                continue
+            with tm("uncertainty_vote"):
+                vote = ops.uncertainty_vote(disp, prob, used, 1.0, 1.0)
+            san, c, sigma = sched.update_coefficients(t, t_next)
+            with tm("ddim_step"):
+                st = ops.ddim_step(disp=disp, xt=img, shift=shifts[i], scale=sched.scale, sqrt_recip=sched.sqrt_recip(t),
+                                   sqrt_recipm1=sched.sqrt_recipm1(t), last_step=False,
+                                   disp_clamp_hi=float(self.maxdisp - 1), vote=vote, mask=mask, sqrt_alpha_next=san, c=c,
+                                   sigma=sigma, step_noise=step_noises[i], asd=asd, q_noise=q_noises[i],
+                                   sqrt_ac=sched.sqrt_ac(t), sqrt_1m_ac=sched.sqrt_1m_ac(t), want_asd_out=True)
+            img, asd = st["x_next"], st["asd_out"]
+        with tm("ensemble"):
+            pred = ops.ensemble(disps, self.cof[: len(disps)])
+        out = {"pred": pred, "x_last": img, "mask": mask, "prob": prob}
+        if keep:
+            out.update(volumes=vols, corr=corr)
+        return out
+
+
+class IgevHotPath:
+    """BASELINE.json configs[3]: the kernel sequence IGEVStereo_ddim.forward (eval) + ddim_sample + model_predictions
+    (KITTI15/core/igev_stereo_ddim.py:361-427, :294-359, :226-292) issue outside their convolutions / GRU: gwc volume
+    (C = 96, G = 8, D = 48 at 1/4 res), softmax + regression of the initial D = 48 classifier, the all-pairs correlation +
+    geometry pyramid (Combined_Geo_Encoding_Volume.__init__), then T = 2 x {filter factor, geometry filter (once per
+    step), `iters` x pyramid lookup, convex upsampling of the last iteration, fused DDIM step with the renewal vote},
+    ensemble.  The GRU that would move the disparity between lookups is out of scope: every lookup of a step samples at
+    that step's initial disparity plus a fixed per-iteration offset."""
+
+    def __init__(self, schedule: Optional[DdimSchedule] = None, iters: int = 32, num_groups: int = 8, D: int = 48,
+                 ensemble: Sequence[float] = IGEV_ENSEMBLE):
+        self.sched = schedule or DdimSchedule(sampling_timesteps=2)
+        self.iters, self.G, self.D = iters, num_groups, D
+        self.cof = tuple(ensemble)
+
+    def __call__(self, fmap_l, fmap_r, geo, cost48, up_weights, coords, used, start, asd, shifts, step_noises, q_noises,
+                 keep: bool = False, timer=None):
+        from . import kitti15
+        tm = timer if timer is not None else (lambda name: contextlib.nullcontext())
+        sched, D = self.sched, self.D
+        B, _, h, w = fmap_l.shape
+        dev = fmap_l.device
+        with tm("gwc_volume"):
+            gwc = ops.gwc_volume(fmap_l, fmap_r, D, self.G)
+        with tm("softmax_regress"):
+            disp0 = ops.softmax_regress(cost48)["disp"].unsqueeze(1)            # init_disp (igev_stereo_ddim.py:384-385)
+        with tm("geo_init"):
+            fn = kitti15.Combined_Geo_Encoding_Volume(fmap_l, fmap_r, geo, num_levels=2, radius=4)
+        c0 = coords.reshape(B, h, w).contiguous()
+        used_map = used.reshape(B, used.shape[-2], used.shape[-1])
+        img = start
+        disps = [used_map]
+        mask = torch.zeros((B, h, w), dtype=torch.float32, device=dev)
+        look = None
+        for i, (t, t_next) in enumerate(sched.time_pairs()):
+            with tm("filter_factor"):
+                n32 = ops.filter_factor(img, shifts[i], sched.scale)
+            for it in range(self.iters):
+                with tm("geo_filter" if it == 0 else "geo_lookup"):              # the first lookup of a step builds the filtered pyramid
+                    look = fn(disp0 + 0.125 * it, coords, n32)
+            with tm("context_upsample"):
+                up = ops.context_upsample(disp0 * 4.0, up_weights)
+            with tm("fallback"):
+                disps.append(ops.select_close(up, used_map, 3.0))                         # igev_stereo_ddim.py:323-325
+            last = t_next < 0
+            kw = {}
+            if not last:
+                san, c, sigma = sched.update_coefficients(t, t_next)
+                kw = dict(sqrt_alpha_next=san, c=c, sigma=sigma, step_noise=step_noises[i], asd=asd, q_noise=q_noises[i],
+                          sqrt_ac=sched.sqrt_ac(t), sqrt_1m_ac=sched.sqrt_1m_ac(t))
+            with tm("ddim_step"):
+                st = ops.ddim_step(disp=up, xt=img, shift=shifts[i], scale=sched.scale, sqrt_recip=sched.sqrt_recip(t),
+                                   sqrt_recipm1=sched.sqrt_recipm1(t), last_step=last, disp_clamp_hi=float(D - 1), coords0=c0,
+                                   used=used_map, vote_thr_dif=5.0, mask=mask, **kw)
+            img = st["x_next"]
+        with tm("ensemble"):
+            pred = ops.ensemble(disps, self.cof[: len(disps)])
+        out = {"pred": pred, "x_last": img, "mask": mask, "lookup": look}
+        if keep:
+            out.update(gwc=gwc, geo=fn)
+        return out

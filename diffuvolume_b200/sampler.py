@@ -526,7 +526,7 @@ def igev_ddim_sample(self, coords0, coords1, flow_init, iters, net_list, inp_lis
         pred, coords1 = _igev_gru_loop(self, coords0, coords1, flow_init, iters, net_list, inp_list, corr_fn, n32, stem_2x)
         disp = pred.float().reshape(batch, H, W).contiguous()
         # fallback to the initial disparity where the sampled one strays (igev_stereo_ddim.py:323-325)
-        disps.append(torch.where(torch.abs(disp - used_map) < 3, disp, used_map))
+        disps.append(ops.select_close(disp, used_map, 3.0))
         last = time_next < 0
         kw = {}
         if not last:

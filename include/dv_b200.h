@@ -375,6 +375,10 @@ int dv_warp_f32(const float *x, const float *disp, float *out, int64_t B, int64_
 int dv_ensemble_f32(const float *const *maps, const float *cof, int n_maps, float *out,
                     int64_t n, void *stream);
 
+/* ---- IGEV fallback to the initial disparity (igev_stereo_ddim.py:323-325):
+ * out[p] = |a[p] - b[p]| < thr ? a[p] : b[p]   (torch.where(torch.abs(disp - used) < 3, disp, used))              */
+int dv_select_close_f32(const float *a, const float *b, float thr, float *out, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,9 +28,8 @@ def _worker(rank, world, port, q):
     est, gt, mask = _data()
     lo, hi = shard_range(est.shape[0], r, w)
     ms = MetricSums()
-    for i in range(lo, hi, 2):                      # batches of 2 inside the shard
-        j = min(i + 2, hi)
-        ms.update(est[i:j], gt[i:j], mask[i:j])
+    for i in range(lo, hi):                         # batch size 1: the reference's evaluation setting
+        ms.update(est[i:i + 1], gt[i:i + 1], mask[i:i + 1])
     out = ms.reduce()
     if r == 0:
         q.put(out)
@@ -42,9 +41,10 @@ def test_sharded_metric_reduction_matches_single_process():
     from diffuvolume_b200.distributed import MetricSums
     est, gt, mask = _data()
     single = MetricSums()
-    single.update(est, gt, mask)
+    for i in range(est.shape[0]):
+        single.update(est[i:i + 1], gt[i:i + 1], mask[i:i + 1])
     want = single.reduce()
-    assert want["n_images"] == 9 and want["n_skipped"] == 1
+    assert want["n_images"] == 9 and want["n_skipped"] == 1 and want["n_batches"] == 10
     # reference semantics for one image, spelled out
     e = (gt[0][mask[0]] - est[0][mask[0]]).abs()
     from diffuvolume_b200.distributed import per_image_metrics
@@ -66,3 +66,18 @@ def test_sharded_metric_reduction_matches_single_process():
         assert p.exitcode == 0
     for k, v in want.items():
         assert abs(got[k] - v) < 1e-9, (k, got[k], v)
+
+
+def test_metric_sums_follow_the_reference_batch_rule():
+    """compute_metric_for_each_image (SceneFlow/utils/metrics.py:21-41): mean over the non-skipped images of a batch, 0 for
+    an all-skipped batch; AverageMeterDict.mean (utils/experiment.py:126-151): mean of those per-batch values."""
+    from diffuvolume_b200.distributed import MetricSums, per_image_metrics
+    est, gt, mask = _data()
+    ms = MetricSums()
+    ms.update(est[2:4], gt[2:4], mask[2:4])          # image 3 is skipped -> the batch value is image 2's
+    ms.update(est[3:4], gt[3:4], mask[3:4])          # all skipped -> contributes 0, still counts as a batch
+    ms.update(est[4:7], gt[4:7], mask[4:7])
+    out = ms.reduce()
+    m = [per_image_metrics(est[i], gt[i], mask[i]) for i in range(10)]
+    want = (m[2]["EPE"] + 0.0 + (m[4]["EPE"] + m[5]["EPE"] + m[6]["EPE"]) / 3) / 3
+    assert abs(out["EPE"] - want) < 1e-12 and out["n_batches"] == 3 and out["n_images"] == 4 and out["n_skipped"] == 2
