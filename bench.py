@@ -584,7 +584,12 @@ def extra_legs(args, dev, rank, world, barrier, dist):
         ams, (pred, (x_last, mask, prob, corr, vols)) = _aten_time(lambda: P.pcw_hot_path_pair(**one, sched=sched))
         err = (got["pred"] - pred).abs()
         leg["parity"] = {"epe_px": float(err.mean()), "max_err_px": float(err.max()),
-                         "corr_volume_max_rel_err": _relerr(got["corr"].squeeze(1), corr),
+                         # warp + the +-24 volume on the SAME disparity map (ours): the chained value also carries the
+                         # 1e-5 px disparity difference through warp's 0.999 validity threshold (a handful of pixels flip)
+                         "corr_volume_max_rel_err": _relerr(got["corr"].squeeze(1), torch.squeeze(P.corr_volume_2sided(
+                             one["feat_l_full"], P.warp(one["feat_r_full"], got["disp_last"].unsqueeze(1)), 24, 1), 1)),
+                         "corr_volume_chained_frac_within_1e-4": float(((got["corr"].squeeze(1) - corr).abs()
+                                                                        <= 1e-4 * corr.abs().max()).float().mean()),
                          "gwc_volume_max_rel_err": max(_relerr(gv, v[:, :40]) for (gv, _), v in zip(got["volumes"], vols)),
                          "concat_volume_bit_exact": all(bool(torch.equal(cv, v[:, 40:])) for (_, cv), v in zip(got["volumes"], vols)),
                          "prob_max_abs_err": float((got["prob"] - prob).abs().max()),

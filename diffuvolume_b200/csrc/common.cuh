@@ -215,4 +215,8 @@ __device__ __forceinline__ double div_by_const(double x, double b, double inv) {
 int launch_concat_stream(const float *ref, const float *tgt, float *out, int B, int C, int HW, int W, int D, int mask_left,
                          const float *wts, const float *nf, int *tile_counters, cudaStream_t st);
 
+// allpairs_tcgen05.cu: a14 on tcgen05 / TMEM; DV_ERR_UNSUPPORTED when the shape does not fit its tiling
+int launch_allpairs_tcgen05(const float *f1, const float *f2, float *out, float *pooled, int64_t B, int64_t C, int64_t H,
+                            int64_t W1, int64_t W2, cudaStream_t st);
+
 }  // namespace dv

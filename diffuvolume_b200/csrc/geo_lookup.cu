@@ -714,6 +714,12 @@ static int corr1d_allpairs_impl(const float *fmap1, const float *fmap2, float *o
               static_cast<unsigned>(B * H));
     if (grid.y > 65535 || B * H > 65535 * 1LL) return DV_ERR_UNSUPPORTED;   // B*H = 96 per pair in every reference configuration
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (DV_TUNE("DV_ALLPAIRS_TCGEN05", 1)) {
+        // 5th-generation tensor cores (tcgen05.mma.kind::tf32, TMEM accumulators, TMA loads and stores); shapes outside
+        // its tiling rules fall through to the warp-level kernels
+        const int rc = launch_allpairs_tcgen05(fmap1, fmap2, out, pooled, B, C, H, W1, W2, st);
+        if (rc != DV_ERR_UNSUPPORTED) return rc;
+    }
     if (DV_TUNE("DV_ALLPAIRS_MMA", 1) || pooled) {
         corr1d_allpairs_mma_kernel<<<grid, 128, 0, st>>>(fmap1, fmap2, out, pooled, static_cast<int>(C), static_cast<int>(H),
                                                          static_cast<int>(W1), static_cast<int>(W2));

@@ -300,7 +300,7 @@ class PcwHotPath:
             pred = ops.ensemble(disps, self.cof[: len(disps)])
         out = {"pred": pred, "x_last": img, "mask": mask, "prob": prob}
         if keep:
-            out.update(volumes=vols, corr=corr)
+            out.update(volumes=vols, corr=corr, disp_last=disps[-1])
         return out
 
 

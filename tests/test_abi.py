@@ -50,16 +50,21 @@ def test_library_is_sm100a_and_uses_the_tma_engine(lib):
     assert "UBLKCP" in sass          # cp.async.bulk (TMA engine) in the gwc kernel
     assert "SYNCS" in sass           # mbarrier
     assert "UTMALDG" in sass         # tensor-map TMA loads (streaming producers)
-    # tensor cores appear in exactly one kernel: the compute-bound all-pairs correlation (a14, 3xTF32 mma.sync);
-    # every HBM-bound volume kernel stays on plain FFMA
+    # tensor cores appear in exactly one op: the compute-leaning all-pairs correlation (a14) — the tcgen05 kernel
+    # (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld from tensor memory, UTMASTG = TMA tensor store) and its warp-level
+    # 3xTF32 fallback (HMMA); every HBM-bound volume kernel stays on plain FFMA
     fn = None
-    owners = set()
+    owners, tc5 = set(), set()
     for line in sass.splitlines():
         if "Function :" in line:
             fn = line.split("Function :")[1].strip()
+        elif "UTCHMMA" in line:
+            tc5.add(fn)
         elif "HMMA" in line:
             owners.add(fn)
     assert owners and all("corr1d_allpairs_mma" in o for o in owners), owners
+    assert tc5 and all("corr1d_allpairs_tcgen05" in o for o in tc5), tc5
+    assert "LDTM" in sass and "UTMASTG" in sass
 
 
 def test_argument_validation_without_a_gpu(lib):

@@ -477,6 +477,25 @@ def test_corr1d_allpairs_pooled_epilogue(ops, shape):
     assert rel_max_err(host(out), O.corr1d_allpairs(f1, f2).reshape(out.shape)) < VOL_TOL
 
 
+@pytest.mark.parametrize("shape", [(1, 96, 4, 312), (2, 40, 3, 136), (1, 32, 2, 320), (1, 8, 1, 8), (1, 104, 2, 200),
+                                   (3, 96, 5, 312)])
+def test_corr1d_allpairs_tcgen05_vs_fp64(ops, shape):
+    """a14 on tcgen05 / TMEM (csrc/allpairs_tcgen05.cu): 3xTF32 against a float64 einsum — 1e-5 of the range (the
+    north_star bound is 1e-4; plain TF32 would sit at ~1e-3) — with partial 128-row / 160-column tiles, a partial
+    32-channel chunk, several persistent rounds per CTA, and the pooled level written from the same accumulators."""
+    B, C, H, W = shape
+    f1, f2 = synth.normal(shape, 441), synth.normal(shape, 442)
+    out, pooled = ops.corr1d_allpairs(cu(f1), cu(f2), return_pooled=True)
+    want = np.einsum("aijk,aijh->ajkh", f1.astype(np.float64), f2.astype(np.float64))
+    got = host(out).reshape(want.shape).astype(np.float64)
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+    wp = 0.5 * (want[..., 0::2] + want[..., 1::2])
+    gp = host(pooled).reshape(wp.shape).astype(np.float64)
+    assert np.abs(gp - wp).max() / np.abs(wp).max() < 1e-5
+    again = ops.corr1d_allpairs(cu(f1), cu(f2))
+    assert torch.equal(again, out)                       # deterministic, and independent of the pooled output
+
+
 def test_kitti15_geo_class_matches_oracle(ops):
     """The drop-in class (packed pyramid inside) against the oracle class, both call conventions; the reference-layout
     attribute is still available."""

@@ -89,7 +89,8 @@ def test_acvnet_ddim_eval_forward_launches_no_volume_sized_aten_kernel(bound):
     ours = [n for n in names if "dv::" in n]
     assert len(ours) >= 8 + 3 * 5
     # ATen elementwise / softmax / scatter / index kernels the reference's forward would have launched on volumes
-    banned = ("softmax", "scatter", "index_put", "upsample_trilinear", "upsample_bilinear", "where", "clamp")
+    # (no "clamp": nn.ReLU inside the stand-in conv stack launches ATen's clamp_min kernel — convolution-side, out of scope)
+    banned = ("softmax", "scatter", "index_put", "upsample_trilinear", "upsample_bilinear", "where", "gather", "cumsum")
     leaked = [n for n in names if "dv::" not in n and any(b in n.lower() for b in banned)]
     assert not leaked, leaked
 
