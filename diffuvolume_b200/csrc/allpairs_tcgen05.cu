@@ -16,8 +16,8 @@
 // at the same offsets of a second buffer: the split is a layout-agnostic LDS.128 / STS.128 pass.
 //
 // Roles (320 threads, one CTA per SM, static round-robin over items = (b*H + y, 128-row tile of x1, 160-column half of x2)):
-//   warp 0      TMA producer: per 32-channel chunk 4 + 5 boxes into a 2-stage ring            (mbarrier full_raw / empty)
-//   warps 2-5   splitters: raw -> hi (in place) + lo, fence.proxy.async, arrive                  (mbarrier conv_done)
+//   warp 0      TMA producer: per 16-channel chunk 4 + 5 boxes into a ring of R raw slots      (mbarrier full_raw / empty_raw)
+//   warps 2-5   splitters: raw -> lo into a ring of L lo slots, fence.proxy.async, arrive      (mbarrier conv_done / empty_lo)
 //   warp 1      MMA issuer (one thread): 4 K-steps x 3 tcgen05.mma (M=128, N=160, K=8) per chunk into one of 3 TMEM
 //               accumulators (160 columns each, 480 of 512 allocated columns); tcgen05.commit frees the stage / publishes
 //               the accumulator                                                                  (mbarrier tmem_full / tmem_empty)
@@ -30,26 +30,33 @@
 namespace dv {
 
 namespace ap5 {
-constexpr int BM = 128, BN = 160, KC = 32, STAGES = 2, ACC = 3;
-constexpr int A_ATOMS = BM / 32, B_ATOMS = BN / 32;           // 4 KB boxes [32 x | 32 channels]
-constexpr int ATOM_BYTES = 32 * KC * 4;                        // 4096
-constexpr int HI_BYTES = (A_ATOMS + B_ATOMS) * ATOM_BYTES;    // 36 KB: A boxes then B boxes
-constexpr int STAGE_BYTES = 2 * HI_BYTES;                      // hi region + lo region
+constexpr int BM = 128, BN = 160;
+constexpr int A_ATOMS = BM / 32, B_ATOMS = BN / 32;           // TMA boxes [32 x | KC channels]
 constexpr int EPI_FULL = 32 * 32 * 4, EPI_POOL = 32 * 16 * 4;  // staging tiles per warp and buffer
 constexpr int EPI_BUF = EPI_FULL + EPI_POOL;                   // 6 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * 2 * EPI_BUF + 1024;   // + alignment slack
 constexpr int THREADS = 320;
-constexpr uint32_t TMEM_COLS = 512;
 // instruction descriptor: D = F32, A = B = TF32, both MN-major, N = 160, M = 128 (cute::UMMA::InstrDescriptor bit layout)
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+// Pipeline shape: KC channels per chunk; R raw slots (TMA landing zone = the `hi` operand) and L lo slots — two rings, so
+// the loads run up to R chunks ahead of the tensor core while the split only has to stay L chunks ahead; ACC
+// tensor-memory accumulators of BN columns (TMEM columns allocated: the next power of two); EPIB staging buffers per
+// epilogue warp; MINB CTAs per SM.
+template <int KC_, int R_, int L_, int ACC_, int EPIB_, int MINB_>
+struct Cfg {
+    static constexpr int KC = KC_, R = R_, L = L_, ACC = ACC_, EPIB = EPIB_, MINB = MINB_;
+    static constexpr int ATOM_BYTES = 32 * KC * 4;
+    static constexpr int HI_BYTES = (A_ATOMS + B_ATOMS) * ATOM_BYTES;     // A boxes then B boxes
+    static constexpr int SMEM_BYTES = (R + L) * HI_BYTES + 4 * EPIB * EPI_BUF + 1024;   // + alignment slack
+    static constexpr uint32_t TMEM_COLS = ACC * BN <= 256 ? 256u : 512u;
+};
 }  // namespace ap5
 
-__device__ __forceinline__ uint64_t ap5_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t ap5_desc(uint32_t smem_addr, uint32_t atom_bytes) {
     // MN-major 32-bit operands have ONE legal swizzled layout: SWIZZLE_128B_BASE32B (layout type 1; 32-byte chunks of a
     // 128-byte row XORed with the row index mod 4 — TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; atom = 32 elements along
-    // M/N x 4 K rows = 512 B).  Start address, LBO = 4096 B (next 32-element block along M/N = next TMA box), SBO = 512 B
+    // M/N x 4 K rows = 512 B).  Start address, LBO = the box size (next 32-element block along M/N = next TMA box), SBO = 512 B
     // (next 4-row K atom: rows are contiguous inside a box), descriptor version 1 (Blackwell).
-    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>(4096u >> 4) << 16) |
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>(atom_bytes >> 4) << 16) |
            (static_cast<uint64_t>(512u >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 __device__ __forceinline__ void ap5_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t accumulate) {
@@ -98,24 +105,32 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
-__global__ void __launch_bounds__(ap5::THREADS, 1)
+template <class CFG>
+__global__ void __launch_bounds__(ap5::THREADS, CFG::MINB)
 corr1d_allpairs_tcgen05_kernel(const __grid_constant__ CUtensorMap map_f1, const __grid_constant__ CUtensorMap map_f2,
                                const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_pool,
                                int C, int H, int W1, int W2, int mtiles, int nhalves, int nitems, int has_pool) {
     using namespace ap5;
+    constexpr int KC = CFG::KC, R = CFG::R, L = CFG::L, ACC = CFG::ACC, EPIB = CFG::EPIB;
+    constexpr int ATOM_BYTES = CFG::ATOM_BYTES, HI_BYTES = CFG::HI_BYTES;
+    constexpr uint32_t TMEM_COLS = CFG::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_raw[STAGES], conv_done[STAGES], empty_bar[STAGES], tmem_full[ACC], tmem_empty[ACC];
+    __shared__ __align__(8) uint64_t full_raw[R], empty_raw[R], conv_done[L], empty_lo[L], tmem_full[ACC], tmem_empty[ACC];
     __shared__ uint32_t tmem_base_slot;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t *epi = smem + STAGES * STAGE_BYTES;
+    uint8_t *lo_base = smem + R * HI_BYTES;
+    uint8_t *epi = lo_base + L * HI_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = (C + KC - 1) / KC;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < R; ++s) {
             mbar_init(&full_raw[s], 1);
+            mbar_init(&empty_raw[s], 1);
+        }
+        for (int s = 0; s < L; ++s) {
             mbar_init(&conv_done[s], 4);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_lo[s], 1);
         }
         for (int a = 0; a < ACC; ++a) {
             mbar_init(&tmem_full[a], 1);
@@ -142,9 +157,9 @@ corr1d_allpairs_tcgen05_kernel(const __grid_constant__ CUtensorMap map_f1, const
                 const int nh = item % nhalves, mt = (item / nhalves) % mtiles, by = item / (nhalves * mtiles);
                 const int b = by / H, y = by % H;
                 for (int kc = 0; kc < kchunks; ++kc, ++n) {
-                    const int s = n % STAGES;
-                    mbar_wait(&empty_bar[s], ((n / STAGES) & 1) ^ 1);
-                    uint8_t *st = smem + s * STAGE_BYTES;
+                    const int s = n % R;
+                    mbar_wait(&empty_raw[s], ((n / R) & 1) ^ 1);
+                    uint8_t *st = smem + s * HI_BYTES;
                     int boxes = 0;
                     for (int a = 0; a < A_ATOMS; ++a) boxes += (mt * BM + 32 * a < W1) ? 1 : 0;
                     for (int a = 0; a < B_ATOMS; ++a) boxes += (nh * BN + 32 * a < W2) ? 1 : 0;
@@ -168,19 +183,20 @@ corr1d_allpairs_tcgen05_kernel(const __grid_constant__ CUtensorMap map_f1, const
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * BN;
                 for (int kc = 0; kc < kchunks; ++kc, ++n) {
-                    const int s = n % STAGES;
-                    mbar_wait(&conv_done[s], (n / STAGES) & 1);
+                    const int s = n % R, l = n % L;
+                    mbar_wait(&conv_done[l], (n / L) & 1);           // lo written (which implies the raw tile has landed)
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_ATOMS * ATOM_BYTES;
-                    const uint32_t a_lo = a_hi + HI_BYTES, b_lo = b_hi + HI_BYTES;
+                    const uint32_t a_hi = smem_u32(smem + s * HI_BYTES), b_hi = a_hi + A_ATOMS * ATOM_BYTES;
+                    const uint32_t a_lo = smem_u32(lo_base + l * HI_BYTES), b_lo = a_lo + A_ATOMS * ATOM_BYTES;
                     const int ksteps = min(KC, C - kc * KC) / 8;
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint32_t o = ks * 1024;    // one K atom = 8 channel rows of 128 B
-                        ap5_mma(d, ap5_desc(a_lo + o), ap5_desc(b_hi + o), (kc | ks) ? 1u : 0u);
-                        ap5_mma(d, ap5_desc(a_hi + o), ap5_desc(b_lo + o), 1u);
-                        ap5_mma(d, ap5_desc(a_hi + o), ap5_desc(b_hi + o), 1u);
+                        ap5_mma(d, ap5_desc(a_lo + o, ATOM_BYTES), ap5_desc(b_hi + o, ATOM_BYTES), (kc | ks) ? 1u : 0u);
+                        ap5_mma(d, ap5_desc(a_hi + o, ATOM_BYTES), ap5_desc(b_lo + o, ATOM_BYTES), 1u);
+                        ap5_mma(d, ap5_desc(a_hi + o, ATOM_BYTES), ap5_desc(b_hi + o, ATOM_BYTES), 1u);
                     }
-                    ap5_commit(&empty_bar[s]);                       // stage free once these MMAs have read it
+                    ap5_commit(&empty_raw[s]);                       // both slots are free once these MMAs have read them
+                    ap5_commit(&empty_lo[l]);
                     if (kc == kchunks - 1) ap5_commit(&tmem_full[acc]);   // accumulator complete
                 }
             }
@@ -191,34 +207,32 @@ corr1d_allpairs_tcgen05_kernel(const __grid_constant__ CUtensorMap map_f1, const
         uint32_t n = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             for (int kc = 0; kc < kchunks; ++kc, ++n) {
-                const int s = n % STAGES;
-                mbar_wait(&full_raw[s], (n / STAGES) & 1);
-                float4 *hi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
-                float4 *lo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + HI_BYTES);
-#pragma unroll 6
+                const int s = n % R, l = n % L;
+                mbar_wait(&empty_lo[l], ((n / L) & 1) ^ 1);      // the MMAs that read this lo slot L chunks ago are done
+                mbar_wait(&full_raw[s], (n / R) & 1);
+                const float4 *hi = reinterpret_cast<const float4 *>(smem + s * HI_BYTES);
+                float4 *lo = reinterpret_cast<float4 *>(lo_base + l * HI_BYTES);
+                // hi is used as it landed: the tensor core ignores the low 13 mantissa bits of a TF32 operand (truncation),
+                // so lo = x - trunc(x) (exact in fp32), rounded to TF32
+#pragma unroll 3
                 for (int i = t; i < HI_BYTES / 16; i += 128) {
                     const float4 v = hi[i];
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    l.x = tf32_rna(v.x - h.x);
-                    l.y = tf32_rna(v.y - h.y);
-                    l.z = tf32_rna(v.z - h.z);
-                    l.w = tf32_rna(v.w - h.w);
-                    hi[i] = h;
-                    lo[i] = l;
+                    float4 o;
+                    o.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+                    o.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+                    o.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+                    o.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+                    lo[i] = o;
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&conv_done[s]);
+                if (lane == 0) mbar_arrive(&conv_done[l]);
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 6..9)
         const int q = warp & 3;                                 // TMEM lane quarter this warp may read
-        uint8_t *my = epi + (warp - 6) * 2 * EPI_BUF;
+        uint8_t *my = epi + (warp - 6) * EPIB * EPI_BUF;
         uint32_t it = 0, nstore = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
             const int nh = item % nhalves, mt = (item / nhalves) % mtiles, by = item / (nhalves * mtiles);
@@ -232,8 +246,8 @@ corr1d_allpairs_tcgen05_kernel(const __grid_constant__ CUtensorMap map_f1, const
                     if (col0 >= W2) break;
                     uint32_t v[32];
                     tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * BN + 32 * g, v);
-                    uint8_t *buf = my + (nstore & 1) * EPI_BUF;
-                    if (lane == 0) bulk_wait_read<1>();          // the stores that last read this buffer are done with it
+                    uint8_t *buf = my + (nstore % EPIB) * EPI_BUF;
+                    if (lane == 0) bulk_wait_read<EPIB - 1>();          // the stores that last read this buffer are done with it
                     __syncwarp();
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -308,15 +322,11 @@ int launch_allpairs_tcgen05(const float *f1, const float *f2, float *out, float 
     const int64_t nitems = B * H * mtiles * nhalves;
     if (nitems > INT32_MAX || B * H > INT32_MAX) return DV_ERR_UNSUPPORTED;
     CUtensorMap m1, m2, mo, mp;
+    const uint64_t d1[4] = {static_cast<uint64_t>(W1), static_cast<uint64_t>(H), static_cast<uint64_t>(C), static_cast<uint64_t>(B)};
+    const uint64_t s1[3] = {static_cast<uint64_t>(W1) * 4, static_cast<uint64_t>(H * W1) * 4, static_cast<uint64_t>(C * H * W1) * 4};
+    const uint64_t d2[4] = {static_cast<uint64_t>(W2), static_cast<uint64_t>(H), static_cast<uint64_t>(C), static_cast<uint64_t>(B)};
+    const uint64_t s2[3] = {static_cast<uint64_t>(W2) * 4, static_cast<uint64_t>(H * W2) * 4, static_cast<uint64_t>(C * H * W2) * 4};
     {
-        const uint64_t d1[4] = {static_cast<uint64_t>(W1), static_cast<uint64_t>(H), static_cast<uint64_t>(C), static_cast<uint64_t>(B)};
-        const uint64_t s1[3] = {static_cast<uint64_t>(W1) * 4, static_cast<uint64_t>(H * W1) * 4, static_cast<uint64_t>(C * H * W1) * 4};
-        const uint64_t d2[4] = {static_cast<uint64_t>(W2), static_cast<uint64_t>(H), static_cast<uint64_t>(C), static_cast<uint64_t>(B)};
-        const uint64_t s2[3] = {static_cast<uint64_t>(W2) * 4, static_cast<uint64_t>(H * W2) * 4, static_cast<uint64_t>(C * H * W2) * 4};
-        const uint32_t box[4] = {32u, 1u, static_cast<uint32_t>(KC), 1u};
-        if (!make_map(&m1, f1, 4, d1, s1, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
-            !make_map(&m2, f2, 4, d2, s2, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-            return DV_ERR_UNSUPPORTED;
         const uint64_t dout[3] = {static_cast<uint64_t>(W2), static_cast<uint64_t>(W1), static_cast<uint64_t>(B * H)};
         const uint64_t sout[2] = {static_cast<uint64_t>(W2) * 4, static_cast<uint64_t>(W1 * W2) * 4};
         const uint32_t bout[3] = {32u, 32u, 1u};
@@ -329,12 +339,36 @@ int launch_allpairs_tcgen05(const float *f1, const float *f2, float *out, float 
             if (!make_map(&mp, pooled, 3, dp, sp, bp, CU_TENSOR_MAP_SWIZZLE_64B)) return DV_ERR_UNSUPPORTED;
         }
     }
-    auto kern = corr1d_allpairs_tcgen05_kernel;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return DV_ERR_LAUNCH;
-    const int grid = static_cast<int>(nitems < num_sms() ? nitems : num_sms());
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(m1, m2, mo, mp, static_cast<int>(C), static_cast<int>(H), static_cast<int>(W1),
-                                            static_cast<int>(W2), static_cast<int>(mtiles), static_cast<int>(nhalves),
-                                            static_cast<int>(nitems), pooled ? 1 : 0);
+    const int variant = DV_TUNE("DV_AP5_VARIANT", 0);
+#define DV_AP5_LAUNCH(CFG)                                                                                               \
+    {                                                                                                                    \
+        const uint32_t boxc[4] = {32u, 1u, static_cast<uint32_t>(CFG::KC), 1u};                                          \
+        if (!make_map(&m1, f1, 4, d1, s1, boxc, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||                                   \
+            !make_map(&m2, f2, 4, d2, s2, boxc, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))                                     \
+            return DV_ERR_UNSUPPORTED;                                                                                   \
+        auto kern = corr1d_allpairs_tcgen05_kernel<CFG>;                                                                 \
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM_BYTES) != cudaSuccess)     \
+            return DV_ERR_LAUNCH;                                                                                        \
+        const int64_t slots = static_cast<int64_t>(num_sms()) * CFG::MINB;                                               \
+        const int grid = static_cast<int>(nitems < slots ? nitems : slots);                                              \
+        kern<<<grid, THREADS, CFG::SMEM_BYTES, st>>>(m1, m2, mo, mp, static_cast<int>(C), static_cast<int>(H),           \
+                                                     static_cast<int>(W1), static_cast<int>(W2), static_cast<int>(mtiles), \
+                                                     static_cast<int>(nhalves), static_cast<int>(nitems), pooled ? 1 : 0); \
+    }
+    // Measured at B = 8, C = 96, 96 x 312 (gpurun_out r02: scripts/bench_allpairs.py): <32,3,2,3,1,1> 0.155 ms,
+    // <16,8,3,3,1,1> 0.158, <16,6,3,3,2,1> 0.166, <16,3,1,1,1,2> (two CTAs per SM) 0.171, <16,4,2,3,2,1> 0.188;
+    // one coupled 2-stage ring (first version) 0.186.
+    using CfgA = Cfg<32, 3, 2, 3, 1, 1>;    // 3 raw slots (1.5 items ahead), 2 lo slots, 3 accumulators, one CTA per SM
+    using CfgB = Cfg<16, 8, 3, 3, 1, 1>;
+    using CfgC = Cfg<16, 6, 3, 3, 2, 1>;
+    using CfgE = Cfg<16, 3, 1, 1, 1, 2>;    // two CTAs per SM (256 TMEM columns each)
+    switch (variant) {
+        case 1: DV_AP5_LAUNCH(CfgB) break;
+        case 2: DV_AP5_LAUNCH(CfgC) break;
+        case 4: DV_AP5_LAUNCH(CfgE) break;
+        default: DV_AP5_LAUNCH(CfgA) break;
+    }
+#undef DV_AP5_LAUNCH
     return finish_launch();
 }
 
