@@ -500,8 +500,9 @@ def pcw_bytes(B, Hp=384, Wp=1248):
         "concat_volume": sum((2 * 12 + 24 * Ds) * p for p, Ds in sc) * F4,
         "filter": T * (2 * 32 * D * hw * F4 + 2 * D * hw * 8),                       # volume in/out, x_t in, n out
         "softmax_regress": T * (2 * 192 * HW + HW) * F4,                              # logits in, probabilities + disparity out
-        "warp": T * (2 * 32 + 1) * HW * F4,
-        "corr_volume_2sided": T * (2 * 32 + 49) * HW * F4,
+        # warp (+ left - warped, + copy of left) and the +-24 volume, written into the refinement network's concat buffer:
+        # right, disparity, left in; warped, difference, copy out; then left + warped in, 49 planes out
+        "refine_input": T * ((32 + 1 + 32 + 3 * 32) + (2 * 32 + 49)) * HW * F4,
         "uncertainty_vote": (T - 1) * (192 + 3) * HW * F4,
         "ddim_step": T * (2 * HW * F4 + D * hw * (8 + 8 + 4 + 4 + 8 + 8 + 4)),
         "ensemble": (T + 2) * HW * F4,
@@ -576,7 +577,8 @@ def extra_legs(args, dev, rank, world, barrier, dist):
     ms, kt = _timed(lambda t: ppath(**pin, timer=t), steps, warmup, barrier, dist, dev)
     leg = _leg_result("pcwnet", B, world, ms, kt, steps, pcw_bytes(B),
                       {"workload": "configs[2]: PCWNet+DiffuVolume KITTI12 384x1248: 4-scale gwc + concat(T); T=3 x {filter, "
-                                   "softmax/regression (+prob), warp, +-24 corr volume, uncertainty vote, DDIM step}; ensemble"})
+                                   "softmax/regression (+prob), refinement input (warp, left - warped, +-24 corr volume, assembled in the concat buffer), "
+                                   "uncertainty vote, DDIM step}; ensemble"})
     if do_parity:
         one = pcw_inputs(1, dev, 777)
         got = ppath(**one, keep=True)
@@ -586,9 +588,9 @@ def extra_legs(args, dev, rank, world, barrier, dist):
         leg["parity"] = {"epe_px": float(err.mean()), "max_err_px": float(err.max()),
                          # warp + the +-24 volume on the SAME disparity map (ours): the chained value also carries the
                          # 1e-5 px disparity difference through warp's 0.999 validity threshold (a handful of pixels flip)
-                         "corr_volume_max_rel_err": _relerr(got["corr"].squeeze(1), torch.squeeze(P.corr_volume_2sided(
+                         "corr_volume_max_rel_err": _relerr(got["corr"], torch.squeeze(P.corr_volume_2sided(
                              one["feat_l_full"], P.warp(one["feat_r_full"], got["disp_last"].unsqueeze(1)), 24, 1), 1)),
-                         "corr_volume_chained_frac_within_1e-4": float(((got["corr"].squeeze(1) - corr).abs()
+                         "corr_volume_chained_frac_within_1e-4": float(((got["corr"] - corr).abs()
                                                                         <= 1e-4 * corr.abs().max()).float().mean()),
                          "gwc_volume_max_rel_err": max(_relerr(gv, v[:, :40]) for (gv, _), v in zip(got["volumes"], vols)),
                          "concat_volume_bit_exact": all(bool(torch.equal(cv, v[:, 40:])) for (_, cv), v in zip(got["volumes"], vols)),

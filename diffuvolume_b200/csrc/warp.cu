@@ -26,7 +26,8 @@ __device__ __forceinline__ float warp_div(float a, float b, float y, bool use_rc
 
 __global__ void __launch_bounds__(256)
 warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *__restrict__ out, int C, int H, int W,
-            int cgroups, float rcp_w, float rcp_h, int use_rcp) {
+            int cgroups, float rcp_w, float rcp_h, int use_rcp, const float *__restrict__ ref, float *__restrict__ diff_out,
+            int64_t diff_bstride, float *__restrict__ copy_out, int64_t copy_bstride) {
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z / cgroups, cbeg = (blockIdx.z % cgroups) * kWarpCg;
     const int cend = min(cbeg + kWarpCg, C);
@@ -50,9 +51,22 @@ warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *
     const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
     const int o00 = cy0 * W + cx0, o01 = cy0 * W + cx1, o10 = cy1 * W + cx0, o11 = cy1 * W + cx1;   // H*W < 2^31
     const float *xp = x + static_cast<int64_t>(b) * C * HW;
-    float *op = out + static_cast<int64_t>(b) * C * HW + static_cast<int64_t>(y) * W + px;
+    const int64_t pofs = static_cast<int64_t>(y) * W + px;
+    float *op = out + static_cast<int64_t>(b) * C * HW + pofs;
+    // refinement-input assembly (pwcnet_ddim.py:497-499): `ref - warp(x)` and the copy of `ref` go straight into channel
+    // slices of the caller's concat buffer
+    const float *rp = ref ? ref + static_cast<int64_t>(b) * C * HW + pofs : nullptr;
+    float *dp = diff_out ? diff_out + b * diff_bstride + pofs : nullptr;
+    float *cp = copy_out ? copy_out + b * copy_bstride + pofs : nullptr;
     if (m == 0.0f) {
-        for (int c = cbeg; c < cend; ++c) op[static_cast<int64_t>(c) * HW] = 0.0f;
+        for (int c = cbeg; c < cend; ++c) {
+            op[static_cast<int64_t>(c) * HW] = 0.0f;
+            if (rp) {
+                const float r = __ldg(rp + static_cast<int64_t>(c) * HW);
+                if (dp) dp[static_cast<int64_t>(c) * HW] = __fsub_rn(r, 0.0f);
+                if (cp) cp[static_cast<int64_t>(c) * HW] = r;
+            }
+        }
         return;
     }
     float t00[kWarpCg], t01[kWarpCg], t10[kWarpCg], t11[kWarpCg];
@@ -67,16 +81,24 @@ warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *
         v = __fadd_rn(v, __fmul_rn(t01[k], w01));
         v = __fadd_rn(v, __fmul_rn(t10[k], w10));
         v = __fadd_rn(v, __fmul_rn(t11[k], w11));
-        if (cbeg + k < cend) op[static_cast<int64_t>(cbeg + k) * HW] = v;
+        if (cbeg + k < cend) {
+            op[static_cast<int64_t>(cbeg + k) * HW] = v;
+            if (rp) {
+                const float r = __ldg(rp + static_cast<int64_t>(cbeg + k) * HW);
+                if (dp) dp[static_cast<int64_t>(cbeg + k) * HW] = __fsub_rn(r, v);
+                if (cp) cp[static_cast<int64_t>(cbeg + k) * HW] = r;
+            }
+        }
     }
 }
 
 }  // namespace dv
 
-extern "C" int dv_warp_f32(const float *x, const float *disp, float *out, int64_t B, int64_t C, int64_t H, int64_t W,
-                           void *stream) {
+static int warp_impl(const float *x, const float *disp, float *out, const float *ref, float *diff_out, int64_t diff_bstride,
+                     float *copy_out, int64_t copy_bstride, int64_t B, int64_t C, int64_t H, int64_t W, void *stream) {
     using namespace dv;
     if (!x || !disp || !out) return DV_ERR_NULL;
+    if ((diff_out || copy_out) && !ref) return DV_ERR_NULL;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
     const int64_t cgroups = (C + kWarpCg - 1) / kWarpCg;
     if (H * W > INT32_MAX || B * cgroups > 65535 || H > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
@@ -85,6 +107,17 @@ extern "C" int dv_warp_f32(const float *x, const float *disp, float *out, int64_
     const float rcp_w = 1.0f / static_cast<float>(W > 1 ? W - 1 : 1), rcp_h = 1.0f / static_cast<float>(H > 1 ? H - 1 : 1);
     warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, disp, out, static_cast<int>(C), static_cast<int>(H),
                                                                    static_cast<int>(W), static_cast<int>(cgroups), rcp_w, rcp_h,
-                                                                   use_rcp);
+                                                                   use_rcp, ref, diff_out, diff_bstride, copy_out, copy_bstride);
     return finish_launch();
+}
+
+extern "C" int dv_warp_f32(const float *x, const float *disp, float *out, int64_t B, int64_t C, int64_t H, int64_t W,
+                           void *stream) {
+    return warp_impl(x, disp, out, nullptr, nullptr, 0, nullptr, 0, B, C, H, W, stream);
+}
+
+extern "C" int dv_warp_assemble_f32(const float *x, const float *disp, const float *ref, float *warp_out, float *diff_out,
+                                    int64_t diff_batch_stride, float *copy_out, int64_t copy_batch_stride, int64_t B, int64_t C,
+                                    int64_t H, int64_t W, void *stream) {
+    return warp_impl(x, disp, warp_out, ref, diff_out, diff_batch_stride, copy_out, copy_batch_stride, B, C, H, W, stream);
 }

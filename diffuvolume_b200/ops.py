@@ -284,19 +284,33 @@ def volume_filter(vol: torch.Tensor, xt: torch.Tensor, shift: Optional[torch.Ten
     return (out, n_out) if return_n else out
 
 
-def corr_volume_2sided(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, num_groups: int) -> torch.Tensor:
-    """a5 — build_corrleation_volume, KITTI12/models/submodule.py:121-135 -> [B,G,2*maxdisp+1,H,W]."""
+def corr_volume_2sided(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, num_groups: int,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a5 — build_corrleation_volume, KITTI12/models/submodule.py:121-135 -> [B,G,2*maxdisp+1,H,W].
+    `out` (optional): a float32 [B, G*(2*maxdisp+1), H, W] block, contiguous per sample — e.g. a channel slice of a concat
+    buffer; a batch-strided `out` is filled one sample per call (the C-ABI writes contiguous volumes)."""
     B, Cc, H, W = ref.shape
     assert Cc % num_groups == 0
-    _need_cuda(ref, tgt)
+    _need_cuda(ref, tgt, out)
     ref, tgt = _f32c(ref, "refimg_fea"), _f32c(tgt, "targetimg_fea")
     if tgt.shape != ref.shape:
         raise RuntimeError(f"The size of tensor a {tuple(ref.shape)} must match the size of tensor b {tuple(tgt.shape)}")
-    out = torch.empty((B, num_groups, 2 * maxdisp + 1, H, W), dtype=torch.float32, device=ref.device)
+    S = num_groups * (2 * maxdisp + 1)
+    if out is None:
+        res = torch.empty((B, num_groups, 2 * maxdisp + 1, H, W), dtype=torch.float32, device=ref.device)
+        calls = [(ref, tgt, res.data_ptr(), B)]
+    else:
+        res = out
+        ptr, bstride = _slice_view(out, B, S, H, W, "out")
+        if B == 1 or bstride == S * H * W:
+            calls = [(ref, tgt, ptr, B)]
+        else:
+            calls = [(ref[b:b + 1], tgt[b:b + 1], ptr + 4 * b * bstride, 1) for b in range(B)]
     with torch.cuda.device(ref.device):
-        check(_lib.lib().dv_corr_volume_2sided_f32(_ptr(ref), _ptr(tgt), _ptr(out), B, Cc, H, W, maxdisp, num_groups,
-                                                   _stream(ref)), "dv_corr_volume_2sided_f32")
-    return out
+        for r_, t_, p_, b_ in calls:
+            check(_lib.lib().dv_corr_volume_2sided_f32(_ptr(r_), _ptr(t_), p_, b_, Cc, H, W, maxdisp, num_groups,
+                                                       _stream(ref)), "dv_corr_volume_2sided_f32")
+    return res
 
 
 # --------------------------------------------------------------------------------------------
@@ -610,6 +624,42 @@ def warp(x: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
         with torch.cuda.device(x.device):
             check(_lib.lib().dv_warp_f32(_ptr(x), _ptr(disp), _ptr(out), B, C, H, W, _stream(x)), "dv_warp_f32")
     return out
+
+
+def _slice_view(t: Optional[torch.Tensor], B: int, Cc: int, H: int, W: int, name: str):
+    """(pointer, batch stride in floats) of an output that is a [B,Cc,H,W] float32 block, contiguous per sample — a whole
+    tensor or a channel slice `buf[:, c0:c0+Cc]` of a contiguous concat buffer."""
+    if t is None:
+        return None, 0
+    if t.dtype != torch.float32 or tuple(t.shape) != (B, Cc, H, W):
+        raise RuntimeError(f"{name} must be float32 [{B},{Cc},{H},{W}], got {t.dtype} {tuple(t.shape)}")
+    st = t.stride()
+    if not (st[3] == 1 and st[2] == W and st[1] == H * W and (B == 1 or st[0] >= Cc * H * W)):
+        raise RuntimeError(f"{name} must be contiguous within each sample (a channel slice of a contiguous buffer is fine)")
+    return t.data_ptr(), (st[0] if B > 1 else Cc * H * W)
+
+
+def refine_input_assemble(ref: torch.Tensor, src: torch.Tensor, disp: torch.Tensor, maxdisp: int, num_groups: int = 1, *,
+                          corr_out: Optional[torch.Tensor] = None, diff_out: Optional[torch.Tensor] = None,
+                          copy_out: Optional[torch.Tensor] = None):
+    """PWCNet's refinement input without torch.cat (KITTI12/models/pwcnet_ddim.py:493-499): warp(src, disp), the +-maxdisp
+    correlation volume of (ref, warped), `ref - warped` and a copy of `ref`, the last three written directly into
+    caller-provided buffers that may be channel slices of one concat buffer.  Returns (warped, corr)."""
+    B, Cc, H, W = ref.shape
+    assert Cc % num_groups == 0
+    _need_cuda(ref, src, disp, corr_out, diff_out, copy_out)
+    ref, src, disp = _f32c(ref, "ref"), _f32c(src, "src"), _f32c(disp, "disp")
+    if src.shape != ref.shape or disp.numel() != B * H * W:
+        raise RuntimeError("refine_input_assemble: src must match ref and disp must be [B,1,H,W]")
+    dp, ds = _slice_view(diff_out, B, Cc, H, W, "diff_out")
+    yp, ys = _slice_view(copy_out, B, Cc, H, W, "copy_out")
+    warped = torch.empty_like(src)
+    if warped.numel():
+        with torch.cuda.device(ref.device):
+            check(_lib.lib().dv_warp_assemble_f32(_ptr(src), _ptr(disp), _ptr(ref), _ptr(warped), dp, ds, yp, ys, B, Cc, H, W,
+                                                  _stream(ref)), "dv_warp_assemble_f32")
+    corr = corr_volume_2sided(ref, warped, maxdisp, num_groups, out=corr_out)
+    return warped, corr
 
 
 # --------------------------------------------------------------------------------------------

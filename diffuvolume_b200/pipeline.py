@@ -240,7 +240,15 @@ class PcwHotPath:
         self.sched = schedule or DdimSchedule(sampling_timesteps=3)
         self.G, self.maxdisp, self.D = num_groups, maxdisp, maxdisp // 4
         self.cof = tuple(ensemble)
+        self._buf: Dict[str, torch.Tensor] = {}
         assert len(self.cof) == self.sched.sampling_timesteps + 1
+
+    def _out(self, name, shape, device):
+        t = self._buf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.device != device:
+            t = torch.empty(shape, dtype=torch.float32, device=device)
+            self._buf[name] = t
+        return t
 
     def __call__(self, scales, combine, costs, used, feat_l_full, feat_r_full, start, asd, shifts, step_noises, q_noises,
                  keep: bool = False, timer=None):
@@ -272,10 +280,14 @@ class PcwHotPath:
             with tm("softmax_regress"):
                 r = ops.softmax_regress(cost, return_prob=True)
             disp, prob = r["disp"], r["prob"]
-            with tm("warp"):
-                warped = ops.warp(feat_r_full, disp.unsqueeze(1))
-            with tm("corr_volume_2sided"):
-                corr = ops.corr_volume_2sided(feat_l_full, warped, 24, 1)
+            # the refinement network's input assembled as the product does (sampler.pcw_model_predictions): warp, left - warped,
+            # copy of left and the +-24 volume straight into the concat buffer — no subtraction / torch.cat passes
+            Cf = feat_l_full.shape[1]
+            combine_in = self._out("refine_in", (B, 2 * Cf + 32 + 1 + 49, feat_l_full.shape[2], feat_l_full.shape[3]), dev)
+            with tm("refine_input"):
+                _, corr = ops.refine_input_assemble(feat_l_full, feat_r_full, disp.unsqueeze(1), 24, 1,
+                                                    diff_out=combine_in[:, :Cf], copy_out=combine_in[:, Cf:2 * Cf],
+                                                    corr_out=combine_in[:, 2 * Cf + 33:])
             # (dispupsample / refinenet3 run here in the full network — out of scope; disp stands in for disp_finetune)
             disps.append(disp)
             last = t_next < 0

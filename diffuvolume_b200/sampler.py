@@ -356,7 +356,6 @@ def pcw_model_predictions(self, volume, noise, t, features_left, features_right)
     once by the same kernel), warp + the +-24 correlation volume :493-494, x_start scatter :504-524 and pred_noise :526
     are the CUDA ops; the 3-D hourglasses, `dispupsample`, `refinenet3` and the two F.upsample calls are the reference's
     own modules / ATen (out of scope)."""
-    from . import kitti12
     b, c, d, h, w = volume.shape
     ti = _time_index(t)
     hb = _host_buffers(self)
@@ -374,12 +373,18 @@ def pcw_model_predictions(self, volume, noise, t, features_left, features_right)
                                            align_corners=True)
     refinenet_feature_right = F.interpolate(features_right["finetune_feature"], [h * 4, w * 4], mode="bilinear",
                                             align_corners=True)
-    refinenet_feature_right_warp = kitti12.warp(refinenet_feature_right, pred3)
-    refinenet_costvolume = kitti12.build_corrleation_volume(refinenet_feature_left, refinenet_feature_right_warp, 24, 1)
-    refinenet_costvolume = torch.squeeze(refinenet_costvolume, 1)
+    # warp + (left - warped) + copy of left + the +-24 volume written straight into the refinement input: the reference's
+    # torch.cat((left - right_warp, left, dispupsample(pred3), pred3, cost), 1) (:497-499) without the subtraction and
+    # concatenation passes over 146 full-resolution channels
     pred3feature = self.dispupsample(pred3)
-    refinenet_combine = torch.cat((refinenet_feature_left - refinenet_feature_right_warp, refinenet_feature_left,
-                                   pred3feature, pred3, refinenet_costvolume), dim=1)
+    B_, Cf, Hf, Wf = refinenet_feature_left.shape
+    Cd, S = pred3feature.shape[1], 2 * 24 + 1
+    refinenet_combine = torch.empty((B_, 2 * Cf + Cd + 1 + S, Hf, Wf), dtype=torch.float32, device=volume.device)
+    ops.refine_input_assemble(refinenet_feature_left.float(), refinenet_feature_right.float(), pred3, 24, 1,
+                              diff_out=refinenet_combine[:, :Cf], copy_out=refinenet_combine[:, Cf:2 * Cf],
+                              corr_out=refinenet_combine[:, 2 * Cf + Cd + 1:])
+    refinenet_combine[:, 2 * Cf:2 * Cf + Cd] = pred3feature
+    refinenet_combine[:, 2 * Cf + Cd:2 * Cf + Cd + 1] = pred3
     disp_finetune = self.refinenet3(refinenet_combine, pred3)
     disp_finetune = torch.squeeze(disp_finetune, 1)
     H, W = disp_finetune.shape[-2:]

@@ -370,6 +370,18 @@ int dv_acv_volume_bwd_f32(const float *grad_out, const float *cl, const float *c
  * mask = 0 where the in-bounds tap weights sum to < 0.999, else 1.                                              */
 int dv_warp_f32(const float *x, const float *disp, float *out, int64_t B, int64_t C, int64_t H, int64_t W, void *stream);
 
+/* ---- f3 + refinement-input assembly  (KITTI12/models/pwcnet_ddim.py:493-499: right_warp = warp(right, pred3);
+ *          combine = torch.cat((left - right_warp, left, ..., cost), 1))
+ * dv_warp_f32 with two extra outputs written in the same pass, addressed as base + b * batch_stride (floats) + the
+ * contiguous [C,H,W] block of the sample — i.e. channel slices of ONE concat buffer, so neither the subtraction nor
+ * torch.cat run as separate volume-sized passes:
+ *   warp_out[b,c,y,x] = warp(x, disp)            (contiguous [B,C,H,W]; the correlation volume reads it)
+ *   diff_out[b,c,y,x] = ref - warp(x, disp)      (optional)
+ *   copy_out[b,c,y,x] = ref                      (optional)                                                          */
+int dv_warp_assemble_f32(const float *x, const float *disp, const float *ref, float *warp_out,
+                         float *diff_out, int64_t diff_batch_stride, float *copy_out, int64_t copy_batch_stride,
+                         int64_t B, int64_t C, int64_t H, int64_t W, void *stream);
+
 /* ---- a13: ensemble (acv_ddim.py:365-369): out[p] = sum_i cof[i] * maps[i][p], i < n_maps <= 8
  * `maps` is a HOST array of n_maps device pointers, `cof` a HOST array of n_maps floats.          */
 int dv_ensemble_f32(const float *const *maps, const float *cof, int n_maps, float *out,

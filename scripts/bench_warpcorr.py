@@ -1,0 +1,23 @@
+import sys, torch
+sys.path.insert(0, "/root/repo")
+from diffuvolume_b200 import ops
+B, C, H, W = 8, 32, 384, 1248
+g = torch.Generator(device="cuda").manual_seed(0)
+fl = torch.randn(B, C, H, W, device="cuda", generator=g); fr = torch.randn(B, C, H, W, device="cuda", generator=g)
+disp = torch.rand(B, 1, H, W, device="cuda", generator=g) * 190
+buf = torch.empty(B, 146, H, W, device="cuda")
+def t(fn, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+sep = t(lambda: ops.corr_volume_2sided(fl, ops.warp(fr, disp), 24, 1))
+full = t(lambda: ops.refine_input_assemble(fl, fr, disp, 24, 1, corr_out=buf[:, 97:], diff_out=buf[:, :32], copy_out=buf[:, 32:64]))
+def aten():
+    w = ops.warp(fr, disp); c = ops.corr_volume_2sided(fl, w, 24, 1).squeeze(1)
+    return torch.cat((fl - w, fl, buf[:, 64:96], disp, c), 1)
+at = t(aten)
+print(f"B={B}: warp+corr {sep:.4f} ms | warp + diff + copy + corr assembled in the concat buffer {full:.4f} ms | warp, corr, then sub + cat on ATen {at:.4f} ms")

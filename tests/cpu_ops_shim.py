@@ -181,3 +181,15 @@ def acv_patch_volume(*a, **k):
 
 def disparity_regression(x, maxdisp, keepdim=False):
     return _t(O.disparity_regression(_np(x), maxdisp, keepdim))
+
+
+def refine_input_assemble(ref, src, disp, maxdisp, num_groups=1, *, corr_out=None, diff_out=None, copy_out=None):
+    w = _t(O.warp(_np(src), _np(disp)))
+    c = _t(O.build_corrleation_volume(_np(ref), _np(w), maxdisp, num_groups)).reshape(ref.shape[0], -1, *ref.shape[-2:])
+    if corr_out is not None:
+        corr_out.copy_(c)
+    if diff_out is not None:
+        diff_out.copy_(ref - w)
+    if copy_out is not None:
+        copy_out.copy_(ref)
+    return w, (corr_out if corr_out is not None else c)

@@ -686,3 +686,26 @@ def test_concurrent_host_threads_and_streams(ops):
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+@pytest.mark.parametrize("shape,m,G", [((2, 32, 12, 64), 24, 1), ((1, 16, 7, 52), 24, 2), ((1, 8, 5, 20), 9, 1), ((3, 32, 40, 156), 24, 1),
+                                       ((1, 6, 3, 7), 3, 1)])
+def test_refine_input_assemble_fills_a_concat_buffer(ops, shape, m, G):
+    """PWCNet's refinement input without torch.cat (pwcnet_ddim.py:493-499): `left - warp(right)`, the copy of `left` and
+    the +-m volume land directly in channel slices of one concat buffer (batch-strided outputs), bit-identical to
+    warp -> subtraction -> build_corrleation_volume -> cat; untouched channels stay untouched."""
+    B, C, H, W = shape
+    fl, fr = synth.normal(shape, 451), synth.normal(shape, 452)
+    disp = (synth.uniform((B, 1, H, W), 453, dtype=np.float32) * np.float32(min(W, 40)) - np.float32(2)).astype(np.float32)
+    warped = ops.warp(cu(fr), cu(disp))
+    want_corr = ops.corr_volume_2sided(cu(fl), warped, m, G).reshape(B, G * (2 * m + 1), H, W)
+    S = G * (2 * m + 1)
+    buf = torch.full((B, 2 * C + 5 + S, H, W), float("nan"), device="cuda")
+    w2, corr = ops.refine_input_assemble(cu(fl), cu(fr), cu(disp), m, G, corr_out=buf[:, 2 * C + 5:], diff_out=buf[:, :C],
+                                         copy_out=buf[:, C:2 * C])
+    assert corr.data_ptr() == buf[:, 2 * C + 5:].data_ptr() and torch.equal(w2, warped)
+    want = torch.cat((cu(fl) - warped, cu(fl), buf[:, 2 * C:2 * C + 5], want_corr), 1)
+    assert torch.equal(torch.nan_to_num(buf, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+    assert torch.isnan(buf[:, 2 * C:2 * C + 5]).all()
+    ref = O.build_corrleation_volume(fl, O.warp(fr, disp), m, G).reshape(B, S, H, W)
+    assert rel_max_err(host(buf[:, 2 * C + 5:].contiguous()), ref) < 1e-4
