@@ -321,9 +321,8 @@ __global__ void gwc_volume_generic_kernel(const float *__restrict__ ref, const f
 // the FIRST k columns, pairing ref[x] with tgt[W-k+x]; everything else in the plane stays 0.
 __global__ void corr_negative_kernel(const float *__restrict__ ref, const float *__restrict__ tgt,
                                      float *__restrict__ out, int C, int HW, int W, int m, int G, int cpg,
-                                     int64_t total) {
+                                     int64_t total, int Dtot, int dofs0) {
     const float inv = 1.0f / static_cast<float>(cpg);
-    const int Dtot = 2 * m + 1;
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int p = static_cast<int>(idx % HW);
@@ -342,7 +341,7 @@ __global__ void corr_negative_kernel(const float *__restrict__ ref, const float 
             for (int c = 0; c < cpg; ++c) acc = fmaf(l[static_cast<int64_t>(c) * HW], r[static_cast<int64_t>(c) * HW], acc);
             v = acc * inv;
         }
-        out[((b * G + g) * Dtot + slot) * HW + p] = v;
+        out[((b * G + g) * Dtot + dofs0 + slot) * HW + p] = v;
     }
 }
 
@@ -360,7 +359,7 @@ zero_planes_kernel(float *__restrict__ out, int64_t plane_stride, int64_t quads_
 }
 __global__ void __launch_bounds__(128)
 corr_negative_live_kernel(const float *__restrict__ ref, const float *__restrict__ tgt, float *__restrict__ out, int C,
-                          int H, int W, int m, int G, int cpg) {
+                          int H, int W, int m, int G, int cpg, int Dtot, int dofs0) {
     // grid: x = row chunks, y = slot, z = b*G + g; thread = (row, column x < min(k, W))
     const int slot = blockIdx.y, k = m - slot;
     const int kw = min(k, W);
@@ -376,7 +375,7 @@ corr_negative_live_kernel(const float *__restrict__ ref, const float *__restrict
     float acc = 0.0f;
 #pragma unroll 8
     for (int c = 0; c < cpg; ++c) acc = fmaf(__ldg(l + c * HW), __ldg(r + c * HW), acc);
-    out[(static_cast<int64_t>(blockIdx.z) * (2 * m + 1) + slot) * HW + p] = acc * (1.0f / static_cast<float>(cpg));
+    out[(static_cast<int64_t>(blockIdx.z) * Dtot + dofs0 + slot) * HW + p] = acc * (1.0f / static_cast<float>(cpg));
 }
 
 template <int KC, int DC, int SQ, int NCH, int MINB>
@@ -526,31 +525,47 @@ extern "C" int dv_groupwise_correlation_f32(const float *fea1, const float *fea2
 }
 
 // a5: slots [m, 2m] are a gwc volume with D = m+1 written at plane offset m of a (2m+1)-plane
-// output; slots [0, m) are the reference's first-k-columns quirk.
-extern "C" int dv_corr_volume_2sided_f32(const float *ref, const float *tgt, float *out, int64_t B, int64_t C,
-                                         int64_t H, int64_t W, int64_t maxdisp, int64_t G, void *stream) {
+// output; slots [0, m) are the reference's first-k-columns quirk.  Dtot = planes between consecutive (b, g) blocks of
+// `out`, dofs0 = plane offset of slot 0 inside a block: (2m+1, 0) for a contiguous volume; for G == 1 any
+// (planes per sample, channel offset) addresses a channel slice of a larger [B, planes, H, W] buffer.
+static int corr2_impl(const float *ref, const float *tgt, float *out, int64_t B, int64_t C, int64_t H, int64_t W,
+                      int64_t maxdisp, int64_t G, int64_t Dtot, int64_t dofs0, cudaStream_t st) {
     using namespace dv;
     if (maxdisp < 0) return DV_ERR_BAD_SHAPE;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int rc = gwc_volume_impl(ref, tgt, out, B, C, H, W, maxdisp + 1, G, 2 * maxdisp + 1, maxdisp, st);
+    const int rc = gwc_volume_impl(ref, tgt, out, B, C, H, W, maxdisp + 1, G, Dtot, dofs0 + maxdisp, st);
     if (rc != DV_OK || maxdisp == 0) return rc;
     const int64_t HW = H * W;
     const int64_t total = B * G * maxdisp * HW;
     if (HW % 4 == 0 && aligned16(out) && maxdisp <= 128 && B * G <= 65535 && HW <= INT32_MAX) {
         const int64_t quads_per_bg = maxdisp * HW / 4;
         dim3 zgrid(static_cast<unsigned>((quads_per_bg + 1023) / 1024), static_cast<unsigned>(B * G));
-        zero_planes_kernel<<<zgrid, 256, 0, st>>>(out, (2 * maxdisp + 1) * HW, quads_per_bg);
+        zero_planes_kernel<<<zgrid, 256, 0, st>>>(out + dofs0 * HW, Dtot * HW, quads_per_bg);
         // rows per CTA for the widest slot (k = m) bound the grid; narrower slots use fewer of their CTAs' threads
         dim3 lgrid(static_cast<unsigned>(H), static_cast<unsigned>(maxdisp), static_cast<unsigned>(B * G));
         corr_negative_live_kernel<<<lgrid, 128, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(H),
                                                          static_cast<int>(W), static_cast<int>(maxdisp), static_cast<int>(G),
-                                                         static_cast<int>(C / G));
+                                                         static_cast<int>(C / G), static_cast<int>(Dtot), static_cast<int>(dofs0));
         return finish_launch(2);
     }
     const int64_t blocks = (total + 255) / 256;
     const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
     corr_negative_kernel<<<grid, 256, 0, st>>>(ref, tgt, out, static_cast<int>(C), static_cast<int>(HW),
                                                static_cast<int>(W), static_cast<int>(maxdisp), static_cast<int>(G),
-                                               static_cast<int>(C / G), total);
+                                               static_cast<int>(C / G), total, static_cast<int>(Dtot), static_cast<int>(dofs0));
     return finish_launch();
+}
+
+extern "C" int dv_corr_volume_2sided_f32(const float *ref, const float *tgt, float *out, int64_t B, int64_t C,
+                                         int64_t H, int64_t W, int64_t maxdisp, int64_t G, void *stream) {
+    return corr2_impl(ref, tgt, out, B, C, H, W, maxdisp, G, 2 * maxdisp + 1, 0, static_cast<cudaStream_t>(stream));
+}
+
+// The same volume written into planes [plane_offset, plane_offset + 2*maxdisp + 1) of every sample of a larger
+// [B, planes_per_sample, H, W] buffer (one group only: the refinement network's concat buffer, pwcnet_ddim.py:497-499).
+extern "C" int dv_corr_volume_2sided_into_f32(const float *ref, const float *tgt, float *buffer, int64_t planes_per_sample,
+                                              int64_t plane_offset, int64_t B, int64_t C, int64_t H, int64_t W,
+                                              int64_t maxdisp, void *stream) {
+    if (planes_per_sample <= 0 || plane_offset < 0 || plane_offset + 2 * maxdisp + 1 > planes_per_sample) return DV_ERR_BAD_SHAPE;
+    if (planes_per_sample > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    return corr2_impl(ref, tgt, buffer, B, C, H, W, maxdisp, 1, planes_per_sample, plane_offset, static_cast<cudaStream_t>(stream));
 }

@@ -304,6 +304,12 @@ def corr_volume_2sided(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, num_g
         ptr, bstride = _slice_view(out, B, S, H, W, "out")
         if B == 1 or bstride == S * H * W:
             calls = [(ref, tgt, ptr, B)]
+        elif num_groups == 1 and bstride % (H * W) == 0:
+            # a channel slice of a contiguous [B, planes, H, W] buffer: one launch set, batch stride = planes per sample
+            with torch.cuda.device(ref.device):
+                check(_lib.lib().dv_corr_volume_2sided_into_f32(_ptr(ref), _ptr(tgt), ptr, bstride // (H * W), 0, B, Cc, H, W,
+                                                                maxdisp, _stream(ref)), "dv_corr_volume_2sided_into_f32")
+            return res
         else:
             calls = [(ref[b:b + 1], tgt[b:b + 1], ptr + 4 * b * bstride, 1) for b in range(B)]
     with torch.cuda.device(ref.device):

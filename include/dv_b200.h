@@ -378,6 +378,11 @@ int dv_warp_f32(const float *x, const float *disp, float *out, int64_t B, int64_
  *   warp_out[b,c,y,x] = warp(x, disp)            (contiguous [B,C,H,W]; the correlation volume reads it)
  *   diff_out[b,c,y,x] = ref - warp(x, disp)      (optional)
  *   copy_out[b,c,y,x] = ref                      (optional)                                                          */
+/* dv_corr_volume_2sided_f32 (G = 1) written into planes [plane_offset, plane_offset + 2*maxdisp + 1) of every sample of
+ * a larger contiguous [B, planes_per_sample, H, W] buffer.                                                            */
+int dv_corr_volume_2sided_into_f32(const float *ref, const float *tgt, float *buffer, int64_t planes_per_sample,
+                                   int64_t plane_offset, int64_t B, int64_t C, int64_t H, int64_t W, int64_t maxdisp,
+                                   void *stream);
 int dv_warp_assemble_f32(const float *x, const float *disp, const float *ref, float *warp_out,
                          float *diff_out, int64_t diff_batch_stride, float *copy_out, int64_t copy_batch_stride,
                          int64_t B, int64_t C, int64_t H, int64_t W, void *stream);

@@ -21,3 +21,14 @@ def aten():
     return torch.cat((fl - w, fl, buf[:, 64:96], disp, c), 1)
 at = t(aten)
 print(f"B={B}: warp+corr {sep:.4f} ms | warp + diff + copy + corr assembled in the concat buffer {full:.4f} ms | warp, corr, then sub + cat on ATen {at:.4f} ms")
+from diffuvolume_b200 import _lib
+lib = _lib.lib(); st = torch.cuda.current_stream().cuda_stream
+warped = torch.empty_like(fr)
+HWs = H * W
+t_w = t(lambda: lib.dv_warp_f32(fr.data_ptr(), disp.data_ptr(), warped.data_ptr(), B, C, H, W, st))
+t_wa = t(lambda: lib.dv_warp_assemble_f32(fr.data_ptr(), disp.data_ptr(), fl.data_ptr(), warped.data_ptr(), buf[:, :32].data_ptr(), 146 * HWs, buf[:, 32:64].data_ptr(), 146 * HWs, B, C, H, W, st))
+t_wd = t(lambda: lib.dv_warp_assemble_f32(fr.data_ptr(), disp.data_ptr(), fl.data_ptr(), warped.data_ptr(), buf[:, :32].data_ptr(), 146 * HWs, None, 0, B, C, H, W, st))
+cc = torch.empty(B, 49, H, W, device="cuda")
+t_c = t(lambda: lib.dv_corr_volume_2sided_f32(fl.data_ptr(), warped.data_ptr(), cc.data_ptr(), B, C, H, W, 24, 1, st))
+t_cs = t(lambda: lib.dv_corr_volume_2sided_into_f32(fl.data_ptr(), warped.data_ptr(), buf[:, 97:].data_ptr(), 146, 0, B, C, H, W, 24, st))
+print(f"warp {t_w:.4f} | warp_assemble(diff+copy) {t_wa:.4f} | warp_assemble(diff) {t_wd:.4f} | corr {t_c:.4f} | corr into buffer {t_cs:.4f}")
