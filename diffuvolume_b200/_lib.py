@@ -112,6 +112,7 @@ SIGNATURES = {
     "dv_softmax_regress_bwd_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "dv_acv_volume_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P]),
     "dv_warp_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "dv_warp_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "dv_corr_volume_2sided_into_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_warp_assemble_f32": (_I, [_P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P]),
     "dv_select_close_f32": (_I, [_P, _P, _F, _P, _I64, _P]),

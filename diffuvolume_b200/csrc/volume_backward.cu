@@ -226,6 +226,184 @@ gwc_bwd_quad_kernel(const float *__restrict__ go, const float *__restrict__ ref,
             make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
 }
 
+// ---- ring kernel: the quad kernel with the gradient volume staged through a cp.async ring -------------------------------
+// ncu on the quad kernel: 26 % warps active, long-scoreboard stalls on the gradient LDG.128s, issue slots 52 % — a thread
+// waits for its own 4-8 loads before every block of 128 FMAs.  Here the gradient rows of (b, g) stream through an NST-deep
+// ring of [RS disparity rows][SPAN + Dpad] tiles filled by LDGSTS (cp.async.cg, 16 B, zero-fill past D / past the tensor):
+// loads run NST-1 stages ahead of the FMAs, d_ref and d_tgt warps read the SAME staged tile (the shifted d_tgt reads were a
+// second pass through L1), and the feature window slides in registers — a block of 4 disparities re-uses half of the
+// previous block's window, so it costs 1 LDS.128 per channel instead of 2 (the quad kernel was at 20-24 LSU wavefronts per
+// 128 FMAs).
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, bool valid) {
+    const int sz = valid ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int CK, int SQ, int RS, int NST>
+__global__ void __launch_bounds__(2 * SQ)
+gwc_bwd_ring_kernel(const float *__restrict__ go, const float *__restrict__ ref, const float *__restrict__ tgt,
+                    float *__restrict__ gref, float *__restrict__ gtgt, int C, int HW, int W, int D, int G, int cpg, int Dpad,
+                    int Dtot, int dofs, int64_t go_elems) {
+    static_assert(RS % 4 == 0, "a stage holds whole blocks of 4 disparities");
+    constexpr int SPAN = SQ * 4, NT = 2 * SQ;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int pitch = SPAN + Dpad;
+    float *sR = smem;                   // ref rows  [CK][pitch], element 0 = flat index p0
+    float *sT = smem + CK * pitch;      // tgt rows  [CK][pitch], element Dpad = flat index p0
+    float *sG = smem + 2 * CK * pitch;  // gradient ring [NST][RS][pitch], element 0 = flat index p0 of the row's plane
+    const int chunks = cpg / CK;
+    const int g = blockIdx.y / chunks, kc = blockIdx.y % chunks, b = blockIdx.z;
+    const int p0 = blockIdx.x * SPAN;
+    const int len = min(SPAN, HW - p0);
+    const int64_t fb = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * cpg + kc * CK) * HW;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    // gradient ring: stage s = disparity rows [s*RS, s*RS + RS) of plane block (b, g), columns [p0, p0 + pitch)
+    const int64_t gplane0 = ((static_cast<int64_t>(b) * G + g) * Dtot + dofs) * HW + p0;   // flat index of row 0, column p0
+    const int P4 = pitch / 4, per_stage = RS * P4;
+    const int nstage = (D + RS - 1) / RS;
+    auto issue_stage = [&](int s) {
+        float *dst = sG + (s % NST) * RS * pitch;
+        int r = 0, c = tid;
+        while (c >= P4) { c -= P4; ++r; }
+        for (int e = tid; e < per_stage; e += NT) {
+            const int d = s * RS + r;
+            const int64_t src = gplane0 + static_cast<int64_t>(d) * HW + 4 * c;
+            cp_async16(dst + r * pitch + 4 * c, go + (d < D && src + 3 < go_elems ? src : 0), d < D && src + 3 < go_elems);
+            c += NT;
+            while (c >= P4) { c -= P4; ++r; }
+        }
+    };
+    for (int s = 0; s < NST - 1; ++s) {
+        if (s < nstage) issue_stage(s);
+        cp_async_commit();
+    }
+    __syncthreads();   // barrier initialised
+    if (tid < 32) {    // feature rows: one bulk copy per channel row (see gwc_bwd_quad_kernel)
+        const int rlen = min(len + Dpad, HW - p0);
+        const int64_t toff = fb + p0 - Dpad;
+        auto skip_of = [&](int k) -> int {
+            const int64_t o = toff + static_cast<int64_t>(k) * HW;
+            return o < 0 ? static_cast<int>(o < -(len + Dpad) ? len + Dpad : -o) : 0;
+        };
+        if (tid == 0) {
+            int skipped = 0;
+            for (int k = 0; k < CK; ++k) skipped += skip_of(k);
+            mbar_expect_tx(&bar, 4u * (CK * (rlen + len + Dpad) - skipped));
+        }
+        __syncwarp();
+        for (int k = tid; k < CK; k += 32) {
+            bulk_g2s(sR + k * pitch, ref + fb + static_cast<int64_t>(k) * HW + p0, 4u * rlen, &bar);
+            const int skip = skip_of(k);
+            if (skip < len + Dpad)
+                bulk_g2s(sT + k * pitch + skip, tgt + toff + static_cast<int64_t>(k) * HW + skip, 4u * (len + Dpad - skip), &bar);
+        }
+    }
+    {   // window parts no copy lands in are only ever multiplied by a masked (zero) gradient: clear them (no stale NaNs)
+        const int rlen = min(len + Dpad, HW - p0);
+        const int64_t toff = fb + p0 - Dpad;
+        for (int k = 0; k < CK; ++k) {
+            for (int e = rlen + tid; e < pitch; e += NT) sR[k * pitch + e] = 0.0f;
+            for (int e = len + Dpad + tid; e < pitch; e += NT) sT[k * pitch + e] = 0.0f;
+            const int64_t o = toff + static_cast<int64_t>(k) * HW;
+            const int skip = o < 0 ? static_cast<int>(o < -(len + Dpad) ? len + Dpad : -o) : 0;
+            for (int e = tid; e < skip; e += NT) sT[k * pitch + e] = 0.0f;
+        }
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    const int q = tid % SQ;
+    const bool tgt_pass = tid >= SQ;
+    float *gdst = tgt_pass ? gtgt : gref;
+    const int p = p0 + 4 * q;
+    const bool active = p < HW && gdst != nullptr;
+    int xs[4];
+    xs[0] = p % W;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        xs[i] = xs[i - 1] + 1;
+        if (xs[i] >= W) xs[i] -= W;
+    }
+    float acc[CK][4];
+    float4 keep[CK];   // the half of the feature window the next block of 4 disparities re-uses
+#pragma unroll
+    for (int k = 0; k < CK; ++k) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[k][i] = 0.0f;
+        keep[k] = tgt_pass ? *reinterpret_cast<const float4 *>(sR + k * pitch + 4 * q)            // ref[p .. p+3]
+                           : *reinterpret_cast<const float4 *>(sT + k * pitch + Dpad + 4 * q);    // tgt[p .. p+3]
+    }
+    for (int s = 0; s < nstage; ++s) {
+        cp_async_wait<NST - 2>();
+        __syncthreads();   // stage s has landed for every thread; everyone is done with stage s-1's buffer
+        if (s + NST - 1 < nstage) issue_stage(s + NST - 1);
+        cp_async_commit();
+        if (!active) continue;
+        const float *gs = sG + (s % NST) * RS * pitch + 4 * q;
+#pragma unroll
+        for (int blk = 0; blk < RS / 4; ++blk) {
+            const int d0 = s * RS + 4 * blk;
+            if (d0 >= D) break;
+            float m[4][4];
+            if (!tgt_pass) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {   // d_ref needs x >= d (rows past D are zero-filled)
+                    const float4 gv = *reinterpret_cast<const float4 *>(gs + (4 * blk + j) * pitch);
+                    const float v[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) m[j][i] = xs[i] >= d0 + j ? v[i] : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < CK; ++k) {
+                    const float4 t0 = *reinterpret_cast<const float4 *>(sT + k * pitch + Dpad + 4 * q - d0 - 4), t1 = keep[k];
+                    const float tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(m[j][i], tw[4 + i - j], acc[k][i]);
+                    keep[k] = t0;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {   // d_tgt pairs g[d][p+i+d] with ref[p+i+d] and needs x + d < W
+                    const float *gr = gs + (4 * blk + j) * pitch + d0;
+                    const float4 ga = *reinterpret_cast<const float4 *>(gr), gb = *reinterpret_cast<const float4 *>(gr + 4);
+                    const float v[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) m[j][i] = xs[i] + d0 + j < W ? v[i + j] : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < CK; ++k) {
+                    const float4 r0 = keep[k], r1 = *reinterpret_cast<const float4 *>(sR + k * pitch + 4 * q + d0 + 4);
+                    const float rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(m[j][i], rw[i + j], acc[k][i]);
+                    keep[k] = r1;
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (!active) return;
+    const float inv = 1.0f / static_cast<float>(cpg);
+#pragma unroll
+    for (int k = 0; k < CK; ++k)
+        *reinterpret_cast<float4 *>(gdst + fb + static_cast<int64_t>(k) * HW + p) =
+            make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
+}
+
 // Negative shifts of the two-sided volume (slot s <-> k = m - s pairs ref[x] with tgt[x + W - k] for x < k, KITTI12/models/
 // submodule.py:128-131): only the first m columns of d_ref and the last m columns of d_tgt receive terms.  One thread per
 // (b, c, y, j < m) ADDS them to the gradients the quad kernel has written (same stream, one owner per element).
@@ -279,6 +457,36 @@ static int launch_gwc_bwd_quad(const float *go, const float *ref, const float *t
     return finish_launch();
 }
 
+template <int CK, int RS, int NST>
+static int launch_gwc_bwd_ring(const float *go, const float *ref, const float *tgt, float *gref, float *gtgt, int B, int C,
+                               int HW, int W, int D, int G, int cpg, int Dtot, int dofs, cudaStream_t st) {
+    constexpr int SQ = 64, SPAN = SQ * 4;
+    const int Dpad = (D + 3) / 4 * 4 + 4;
+    const size_t smem = sizeof(float) * (2 * CK + NST * RS) * (SPAN + Dpad);
+    if (smem > 200 * 1024) return DV_ERR_UNSUPPORTED;
+    auto kern = gwc_bwd_ring_kernel<CK, SQ, RS, NST>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return DV_ERR_LAUNCH;
+    dim3 grid((HW + SPAN - 1) / SPAN, G * (cpg / CK), B);
+    kern<<<grid, 2 * SQ, smem, st>>>(go, ref, tgt, gref, gtgt, C, HW, W, D, G, cpg, Dpad, Dtot, dofs,
+                                     static_cast<int64_t>(B) * G * Dtot * HW);
+    return finish_launch();
+}
+
+template <int CK>
+static int launch_gwc_bwd_best(const float *go, const float *ref, const float *tgt, float *gref, float *gtgt, int B, int C,
+                               int HW, int W, int D, int G, int cpg, int Dtot, int dofs, cudaStream_t st) {
+    switch (DV_TUNE("DV_GWC_BWD_RING", 1)) {
+        case 0: break;
+        case 2: return launch_gwc_bwd_ring<CK, 4, 4>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+        case 3: return launch_gwc_bwd_ring<CK, 8, 4>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+        case 4: return launch_gwc_bwd_ring<CK, 4, 3>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+        default: return launch_gwc_bwd_ring<CK, 8, 3>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+    }
+    return launch_gwc_bwd_quad<CK>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+}
+
 // any channels-per-group: thread = (b, channel, pixel)
 __global__ void gwc_bwd_generic_kernel(const float *__restrict__ go, const float *__restrict__ ref,
                                        const float *__restrict__ tgt, float *__restrict__ gref, float *__restrict__ gtgt,
@@ -326,9 +534,9 @@ static int gwc_bwd_impl(const float *go, const float *ref, const float *tgt, flo
         const int Bi = static_cast<int>(B), Ci = static_cast<int>(C), HWi = static_cast<int>(HW), Wi = static_cast<int>(W),
                   Di = static_cast<int>(D), Gi = static_cast<int>(G), Dt = static_cast<int>(Dtot), Do = static_cast<int>(dofs);
         int rc = DV_ERR_UNSUPPORTED;
-        if (cpg % 8 == 0) rc = launch_gwc_bwd_quad<8>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, Dt, Do, st);
-        else if (cpg % 6 == 0) rc = launch_gwc_bwd_quad<6>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, Dt, Do, st);
-        else if (cpg % 4 == 0) rc = launch_gwc_bwd_quad<4>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, Dt, Do, st);
+        if (cpg % 8 == 0) rc = launch_gwc_bwd_best<8>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, Dt, Do, st);
+        else if (cpg % 6 == 0) rc = launch_gwc_bwd_best<6>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, Dt, Do, st);
+        else if (cpg % 4 == 0) rc = launch_gwc_bwd_best<4>(go, ref, tgt, gref, gtgt, Bi, Ci, HWi, Wi, Di, Gi, cpg, Dt, Do, st);
         if (rc == DV_OK && mneg > 0) {
             const int64_t total = B * C * H * mneg;
             corr_negative_bwd_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, st>>>(

@@ -93,23 +93,10 @@ class _DisparityRegression(torch.autograd.Function):
         return ops.disparity_regression_bwd(g.float().contiguous(), maxdisp).to(dt), None, None
 
 
-def _warp_reference_ops(x, disp):
-    """The reference's own op sequence (KITTI12/models/submodule.py:145-176), used only to differentiate `warp`:
-    PCWNet's training back-propagates through grid_sample to both the features and the disparity."""
-    import torch.nn.functional as F
-    B, C, H, W = x.size()
-    xx = torch.arange(0, W, device=x.device).view(1, -1).repeat(H, 1).view(1, 1, H, W).repeat(B, 1, 1, 1).float()
-    yy = torch.arange(0, H, device=x.device).view(-1, 1).repeat(1, W).view(1, 1, H, W).repeat(B, 1, 1, 1).float()
-    vgrid = torch.cat((xx - disp, yy), 1)
-    vgrid = torch.stack((2.0 * vgrid[:, 0] / max(W - 1, 1) - 1.0, 2.0 * vgrid[:, 1] / max(H - 1, 1) - 1.0), dim=1)
-    vgrid = vgrid.permute(0, 2, 3, 1)
-    output = F.grid_sample(x, vgrid, align_corners=False)
-    mask = F.grid_sample(torch.ones_like(x), vgrid, align_corners=False)
-    mask = (mask >= 0.999).to(x.dtype)
-    return output * mask
-
-
 class _Warp(torch.autograd.Function):
+    """warp(x, disp) with kernel-backed gradients to both inputs (PCWNet's training differentiates through grid_sample
+    into the right features and the disparity, KITTI12/models/submodule.py:169-176)."""
+
     @staticmethod
     def forward(ctx, x, disp):
         ctx.save_for_backward(x, disp)
@@ -118,15 +105,9 @@ class _Warp(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, disp = ctx.saved_tensors
-        with torch.enable_grad():
-            xr = x.detach().requires_grad_(ctx.needs_input_grad[0])
-            dr = disp.detach().requires_grad_(ctx.needs_input_grad[1])
-            out = _warp_reference_ops(xr, dr)
-            grads = torch.autograd.grad(out, [t for t in (xr, dr) if t.requires_grad], g, allow_unused=True)
-        grads = list(grads)
-        gx = grads.pop(0) if ctx.needs_input_grad[0] else None
-        gd = grads.pop(0) if ctx.needs_input_grad[1] else None
-        return gx, gd
+        gx, gd = ops.warp_bwd(g.float().contiguous(), _as_f32(x), _as_f32(disp), ctx.needs_input_grad[0],
+                              ctx.needs_input_grad[1])
+        return (None if gx is None else gx.to(x.dtype)), (None if gd is None else gd.reshape(disp.shape).to(disp.dtype))
 
 
 def warp(x, disp):

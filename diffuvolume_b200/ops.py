@@ -632,6 +632,25 @@ def warp(x: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def warp_bwd(grad_out: torch.Tensor, x: torch.Tensor, disp: torch.Tensor, need_x: bool = True, need_disp: bool = True):
+    """f1 — gradients of warp(x, disp) w.r.t. the features and the disparity (the autograd of
+    KITTI12/models/submodule.py:169-176).  Returns (grad_x or None, grad_disp [B,1,H,W] or None)."""
+    B, C, H, W = x.shape
+    _need_cuda(grad_out, x, disp)
+    grad_out, x, disp = _f32c(grad_out, "grad_out"), _f32c(x, "x"), _f32c(disp, "disp")
+    if tuple(grad_out.shape) != (B, C, H, W) or disp.numel() != B * H * W:
+        raise RuntimeError(f"grad_out {tuple(grad_out.shape)} / disp {tuple(disp.shape)} do not match x {tuple(x.shape)}")
+    if not (need_x or need_disp):
+        return None, None
+    gx = torch.empty_like(x) if need_x else None
+    gd = torch.empty(B, 1, H, W, device=x.device, dtype=torch.float32) if need_disp else None
+    if x.numel():
+        with torch.cuda.device(x.device):
+            check(_lib.lib().dv_warp_bwd_f32(_ptr(grad_out), _ptr(x), _ptr(disp), _ptr(gx) if need_x else None,
+                                             _ptr(gd) if need_disp else None, B, C, H, W, _stream(x)), "dv_warp_bwd_f32")
+    return gx, gd
+
+
 def _slice_view(t: Optional[torch.Tensor], B: int, Cc: int, H: int, W: int, name: str):
     """(pointer, batch stride in floats) of an output that is a [B,Cc,H,W] float32 block, contiguous per sample — a whole
     tensor or a channel slice `buf[:, c0:c0+Cc]` of a contiguous concat buffer."""

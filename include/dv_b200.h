@@ -370,6 +370,14 @@ int dv_acv_volume_bwd_f32(const float *grad_out, const float *cl, const float *c
  * mask = 0 where the in-bounds tap weights sum to < 0.999, else 1.                                              */
 int dv_warp_f32(const float *x, const float *disp, float *out, int64_t B, int64_t C, int64_t H, int64_t W, void *stream);
 
+/* ---- f1: backward of warp — the autograd of KITTI12/models/submodule.py:169-176 (grid_sample's bilinear
+ * backward with zero padding, the reference's grid normalisation, the piecewise-constant validity mask):
+ *   grad_x[b,c,tap]   += w_tap * mask * grad_out[b,c,y,x]        (scatter-add, like ATen's grid_sampler_2d_backward)
+ *   grad_disp[b,0,y,x] = -(W/2) * 2/(W-1) * sum_c mask * grad_out[b,c,y,x] * d(bilinear)/d(ix)
+ * Either output may be NULL (not both); both are fully written (the call clears them first on `stream`).            */
+int dv_warp_bwd_f32(const float *grad_out, const float *x, const float *disp, float *grad_x, float *grad_disp,
+                    int64_t B, int64_t C, int64_t H, int64_t W, void *stream);
+
 /* ---- f3 + refinement-input assembly  (KITTI12/models/pwcnet_ddim.py:493-499: right_warp = warp(right, pred3);
  *          combine = torch.cat((left - right_warp, left, ..., cost), 1))
  * dv_warp_f32 with two extra outputs written in the same pass, addressed as base + b * batch_stride (floats) + the

@@ -197,6 +197,18 @@ def main():
                Bc * (2 * 32 + 49) * 384 * 1248 * F4, flops=2.0 * Bc * 32 * 49 * 384 * 1248)
         R.time("a2 gwc_volume C=32 G=1 D=25 (positive half of a5)", f"pcw B={Bc} 384x1248", lambda: ops.gwc_volume(fl, fr, 25, 1),
                Bc * (2 * 32 + 25) * 384 * 1248 * F4)
+        R.time("f3 refine_input_assemble (warp + left-warped + copy + +-24 volume into the concat buffer)", f"pcw B={Bc} 384x1248",
+               (lambda buf=torch.empty(Bc, 2 * 32 + 5 + 49, 384, 1248, device=dev): ops.refine_input_assemble(
+                   fl, fr, dsm, 24, 1, corr_out=buf[:, 69:], diff_out=buf[:, :32], copy_out=buf[:, 32:64])),
+               Bc * (2 * 32 + 1 + 2 * 32 + 32 + 32 + 49) * 384 * 1248 * F4,
+               note="bytes: ref, src, disp read; warped written + read back by the volume; diff, copy, volume written")
+        gw = rn(Bc, 32, 384, 1248)
+        R.time("f1 warp_bwd (grad_x scatter-add + grad_disp, smooth disparities)", f"pcw B={Bc} C=32 384x1248",
+               lambda: ops.warp_bwd(gw, fr, dsm), Bc * (3 * 32 + 2 + 32) * 384 * 1248 * F4,
+               note="bytes: grad_out + features read, grad_x cleared then accumulated (2 x), disp read, grad_disp written")
+        R.time("f1 warp_bwd (grad_x only)", f"pcw B={Bc} C=32 384x1248", lambda: ops.warp_bwd(gw, fr, dsm, True, False),
+               Bc * (3 * 32 + 1) * 384 * 1248 * F4)
+        del gw
         gv = rn(Bc, 1, 49, 384, 1248)
         R.time("f1 corr_volume_2sided_bwd", f"pcw B={Bc}", lambda: ops.gwc_volume_bwd(gv, fl, fr, 1, two_sided_maxdisp=24),
                Bc * (49 + 4 * 32) * 384 * 1248 * F4)

@@ -630,7 +630,7 @@ def test_warp_fullres_vs_oracle_and_autograd(ops):
     want = O.warp(x, disp)
     assert np.array_equal(got == 0, want == 0)
     assert np.abs(got - want).max() < 2e-4               # |x| ~ 4 sigma, ix up to 1248: fp32 coordinate rounding
-    # the autograd Function differentiates through the reference's own grid_sample sequence
+    # the autograd Function is kernel-backed (dv_warp_bwd_f32; parity in tests/test_gpu_backward.py)
     from diffuvolume_b200 import functional as Fn
     xs, ds = _warp_inputs((1, 4, 6, 20), 69, 10.0)
     xt, dt = cu(xs).requires_grad_(True), cu(ds).requires_grad_(True)
