@@ -226,14 +226,18 @@ gwc_bwd_quad_kernel(const float *__restrict__ go, const float *__restrict__ ref,
             make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
 }
 
-// ---- ring kernel: the quad kernel with the gradient volume staged through a cp.async ring -------------------------------
-// ncu on the quad kernel: 26 % warps active, long-scoreboard stalls on the gradient LDG.128s, issue slots 52 % — a thread
-// waits for its own 4-8 loads before every block of 128 FMAs.  Here the gradient rows of (b, g) stream through an NST-deep
-// ring of [RS disparity rows][SPAN + Dpad] tiles filled by LDGSTS (cp.async.cg, 16 B, zero-fill past D / past the tensor):
-// loads run NST-1 stages ahead of the FMAs, d_ref and d_tgt warps read the SAME staged tile (the shifted d_tgt reads were a
-// second pass through L1), and the feature window slides in registers — a block of 4 disparities re-uses half of the
-// previous block's window, so it costs 1 LDS.128 per channel instead of 2 (the quad kernel was at 20-24 LSU wavefronts per
-// 128 FMAs).
+// ---- ring kernel: gradient volume staged through a cp.async ring, mask-free inner loops ----------------------------------
+// ncu on the quad kernel (profiles/r02_gwc_bwd.md): 26 % warps active with long-scoreboard stalls on the gradient LDG.128s,
+// 332 instructions per block of 128 FMAs (64-bit row addressing, 32 mask instructions, run-time smem pitch), LSU wavefronts
+// at 70 % of peak (the d_tgt warps re-read the tile the d_ref warps read, through L1).  This kernel, for W % 4 == 0:
+//  * the gradient rows of (b, g) stream through an NST-deep ring of [RS rows][PITCH] tiles filled by LDGSTS (cp.async.cg 16 B,
+//    zero-fill past D / past the tensor); loads run NST-1 stages ahead of the FMAs and both roles read the SAME staged tile;
+//  * NO masks: a quad starts at a column x0 % 4 == 0, so for d_ref (needs x >= d) every block of 4 disparities d0 < x0 is
+//    fully live, the block d0 == x0 is the static triangle i >= j, and later blocks are dead — the loop just ends; d_tgt
+//    (needs x + d < W) is the mirror image with lim = W - x0 - 4 and the triangle i + j < 4;
+//  * the feature window slides in registers: a block re-uses half of the previous block's window (1 LDS.128 per channel
+//    instead of 2), ping-ponged between two register sets so that no moves are needed;
+//  * compile-time pitch (LDS with immediate offsets), features staged by the same cp.async group as the first tile.
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, bool valid) {
     const int sz = valid ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled, nothing is read
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(sz) : "memory");
@@ -244,159 +248,172 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int CK, int SQ, int RS, int NST>
-__global__ void __launch_bounds__(2 * SQ)
+constexpr int kRingSQ = 64, kRingSpan = 4 * kRingSQ, kRingDpad = 64, kRingPitch = kRingSpan + kRingDpad;
+
+template <int CK, bool TGT>
+struct RingBlock {
+    // one block of 4 disparities d0 .. d0+3 for one quad.  `gs` = staged gradient rows of the block at the quad's column,
+    // `fw` = this role's staged feature rows at the quad (sT + DPAD + 4q for d_ref, sR + 4q for d_tgt), `o` = the window
+    // half kept from the previous block, `n` = the half loaded here (kept for the next block).
+    static __device__ __forceinline__ void full(float (&acc)[CK][4], const float *gs, const float *fw, int d0, float4 (&o)[CK],
+                                                float4 (&n)[CK]) {
+        float m[4][4];
+        if constexpr (!TGT) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 gv = *reinterpret_cast<const float4 *>(gs + j * kRingPitch);
+                m[j][0] = gv.x; m[j][1] = gv.y; m[j][2] = gv.z; m[j][3] = gv.w;
+            }
+#pragma unroll
+            for (int k = 0; k < CK; ++k) {   // window tgt[p-d0-4 .. p-d0+3] = {n, o}
+                n[k] = *reinterpret_cast<const float4 *>(fw + k * kRingPitch - d0 - 4);
+                const float tw[8] = {n[k].x, n[k].y, n[k].z, n[k].w, o[k].x, o[k].y, o[k].z, o[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(m[j][i], tw[4 + i - j], acc[k][i]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {    // g[d0+j][p + d0 + j + i]
+                const float *gr = gs + j * kRingPitch + d0;
+                const float4 ga = *reinterpret_cast<const float4 *>(gr), gb = *reinterpret_cast<const float4 *>(gr + 4);
+                const float v[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m[j][i] = v[i + j];
+            }
+#pragma unroll
+            for (int k = 0; k < CK; ++k) {   // window ref[p+d0 .. p+d0+7] = {o, n}
+                n[k] = *reinterpret_cast<const float4 *>(fw + k * kRingPitch + d0 + 4);
+                const float rw[8] = {o[k].x, o[k].y, o[k].z, o[k].w, n[k].x, n[k].y, n[k].z, n[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(m[j][i], rw[i + j], acc[k][i]);
+            }
+        }
+    }
+};
+
+template <int CK, int RS, int NST>
+__global__ void __launch_bounds__(2 * kRingSQ)
 gwc_bwd_ring_kernel(const float *__restrict__ go, const float *__restrict__ ref, const float *__restrict__ tgt,
-                    float *__restrict__ gref, float *__restrict__ gtgt, int C, int HW, int W, int D, int G, int cpg, int Dpad,
-                    int Dtot, int dofs, int64_t go_elems) {
-    static_assert(RS % 4 == 0, "a stage holds whole blocks of 4 disparities");
-    constexpr int SPAN = SQ * 4, NT = 2 * SQ;
+                    float *__restrict__ gref, float *__restrict__ gtgt, int C, int HW, int W, int D, int G, int cpg, int chunks,
+                    int Dtot, int dofs) {
+    constexpr int SQ = kRingSQ, SPAN = kRingSpan, NT = 2 * SQ, PITCH = kRingPitch, DPAD = kRingDpad, P4 = PITCH / 4;
+    static_assert(RS == 8, "a stage holds two blocks of 4 disparities (the window ping-pong)");
+    static_assert(NT == 16 * RS && P4 % 16 == 0, "stage copy: 16 threads per gradient row");
     extern __shared__ __align__(16) float smem[];
-    __shared__ __align__(8) uint64_t bar;
-    const int pitch = SPAN + Dpad;
-    float *sR = smem;                   // ref rows  [CK][pitch], element 0 = flat index p0
-    float *sT = smem + CK * pitch;      // tgt rows  [CK][pitch], element Dpad = flat index p0
-    float *sG = smem + 2 * CK * pitch;  // gradient ring [NST][RS][pitch], element 0 = flat index p0 of the row's plane
-    const int chunks = cpg / CK;
-    const int g = blockIdx.y / chunks, kc = blockIdx.y % chunks, b = blockIdx.z;
-    const int p0 = blockIdx.x * SPAN;
-    const int len = min(SPAN, HW - p0);
+    float *sR = smem;                   // ref rows  [CK][PITCH], element 0 = flat index p0
+    float *sT = smem + CK * PITCH;      // tgt rows  [CK][PITCH], element DPAD = flat index p0
+    float *sG = smem + 2 * CK * PITCH;  // gradient ring [NST][RS][PITCH], element 0 = column p0 of the row's plane
+    const int kc = blockIdx.x % chunks, p0 = (blockIdx.x / chunks) * SPAN;   // chunk fastest: CTAs sharing a tile are neighbours
+    const int g = blockIdx.y, b = blockIdx.z;
     const int64_t fb = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * cpg + kc * CK) * HW;
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    // gradient ring: stage s = disparity rows [s*RS, s*RS + RS) of plane block (b, g), columns [p0, p0 + pitch)
-    const int64_t gplane0 = ((static_cast<int64_t>(b) * G + g) * Dtot + dofs) * HW + p0;   // flat index of row 0, column p0
-    const int P4 = pitch / 4, per_stage = RS * P4;
+    const float *gplane = go + ((static_cast<int64_t>(b) * G + g) * Dtot + dofs) * HW;   // row 0 of this (b, g)
     const int nstage = (D + RS - 1) / RS;
+    // stage copy: 16 threads per row, 5 chunks each (columns tid%16 + 16 i).  Columns past the plane read the next row (dead
+    // terms); only the last row of the last (b, g) would leave the tensor there, so that row is clipped to the plane.
+    const int srow = tid / 16, scol = 4 * (tid % 16);
+    const bool last_bg = b == static_cast<int>(gridDim.z) - 1 && g == G - 1 && dofs + D == Dtot;
     auto issue_stage = [&](int s) {
-        float *dst = sG + (s % NST) * RS * pitch;
-        int r = 0, c = tid;
-        while (c >= P4) { c -= P4; ++r; }
-        for (int e = tid; e < per_stage; e += NT) {
-            const int d = s * RS + r;
-            const int64_t src = gplane0 + static_cast<int64_t>(d) * HW + 4 * c;
-            cp_async16(dst + r * pitch + 4 * c, go + (d < D && src + 3 < go_elems ? src : 0), d < D && src + 3 < go_elems);
-            c += NT;
-            while (c >= P4) { c -= P4; ++r; }
+        const int d = s * RS + srow;
+        float *dst = sG + ((s % NST) * RS + srow) * PITCH + scol;
+        const float *src = gplane + static_cast<int64_t>(d) * HW + p0 + scol;
+        const int ncol = (last_bg && d == D - 1) ? HW - p0 - scol : PITCH;   // columns of this row that may be read
+#pragma unroll
+        for (int i = 0; i < P4 / 16; ++i) {
+            const bool ok = d < D && 64 * i + 3 < ncol;
+            cp_async16(dst + 64 * i, ok ? src + 64 * i : go, ok);
         }
     };
+    {   // features: ref columns [p0, p0 + PITCH), tgt columns [p0 - DPAD, p0 + SPAN); what lies outside the plane is only ever
+        // paired with dead gradient terms and is zero-filled.  NT / (2 CK) threads per row.
+        constexpr int TPR = NT / (2 * CK), CPT = (P4 + TPR - 1) / TPR;
+        const int row = tid / TPR, c0 = tid % TPR;       // rows [0, CK) = ref, [CK, 2 CK) = tgt
+        const bool is_t = row >= CK;
+        const int colbase = p0 - (is_t ? DPAD : 0);      // flat index of the row's element 0
+        const float *src = (is_t ? tgt : ref) + fb + static_cast<int64_t>(is_t ? row - CK : row) * HW + colbase;
+        float *dst = smem + row * PITCH;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int c = c0 + TPR * i;
+            if ((P4 % TPR != 0 && c >= P4) || (NT % (2 * CK) != 0 && row >= 2 * CK)) break;
+            const int col = colbase + 4 * c;
+            const bool ok = col >= 0 && col + 3 < HW;
+            cp_async16(dst + 4 * c, ok ? src + 4 * c : go, ok);
+        }
+    }
     for (int s = 0; s < NST - 1; ++s) {
         if (s < nstage) issue_stage(s);
         cp_async_commit();
     }
-    __syncthreads();   // barrier initialised
-    if (tid < 32) {    // feature rows: one bulk copy per channel row (see gwc_bwd_quad_kernel)
-        const int rlen = min(len + Dpad, HW - p0);
-        const int64_t toff = fb + p0 - Dpad;
-        auto skip_of = [&](int k) -> int {
-            const int64_t o = toff + static_cast<int64_t>(k) * HW;
-            return o < 0 ? static_cast<int>(o < -(len + Dpad) ? len + Dpad : -o) : 0;
-        };
-        if (tid == 0) {
-            int skipped = 0;
-            for (int k = 0; k < CK; ++k) skipped += skip_of(k);
-            mbar_expect_tx(&bar, 4u * (CK * (rlen + len + Dpad) - skipped));
-        }
-        __syncwarp();
-        for (int k = tid; k < CK; k += 32) {
-            bulk_g2s(sR + k * pitch, ref + fb + static_cast<int64_t>(k) * HW + p0, 4u * rlen, &bar);
-            const int skip = skip_of(k);
-            if (skip < len + Dpad)
-                bulk_g2s(sT + k * pitch + skip, tgt + toff + static_cast<int64_t>(k) * HW + skip, 4u * (len + Dpad - skip), &bar);
-        }
-    }
-    {   // window parts no copy lands in are only ever multiplied by a masked (zero) gradient: clear them (no stale NaNs)
-        const int rlen = min(len + Dpad, HW - p0);
-        const int64_t toff = fb + p0 - Dpad;
-        for (int k = 0; k < CK; ++k) {
-            for (int e = rlen + tid; e < pitch; e += NT) sR[k * pitch + e] = 0.0f;
-            for (int e = len + Dpad + tid; e < pitch; e += NT) sT[k * pitch + e] = 0.0f;
-            const int64_t o = toff + static_cast<int64_t>(k) * HW;
-            const int skip = o < 0 ? static_cast<int>(o < -(len + Dpad) ? len + Dpad : -o) : 0;
-            for (int e = tid; e < skip; e += NT) sT[k * pitch + e] = 0.0f;
-        }
-    }
-    __syncthreads();
-    mbar_wait(&bar, 0);
-
     const int q = tid % SQ;
     const bool tgt_pass = tid >= SQ;
     float *gdst = tgt_pass ? gtgt : gref;
     const int p = p0 + 4 * q;
     const bool active = p < HW && gdst != nullptr;
-    int xs[4];
-    xs[0] = p % W;
-#pragma unroll
-    for (int i = 1; i < 4; ++i) {
-        xs[i] = xs[i - 1] + 1;
-        if (xs[i] >= W) xs[i] -= W;
-    }
+    const int x0 = p % W;                                  // % 4 == 0
+    // blocks d0 < lim are fully live; d0 == lim_raw is the boundary triangle (done after the loop, all lanes at once: inside
+    // the loop it would run for one lane at a time); rows past D are zero-filled and their blocks skipped
+    const int lim_raw = tgt_pass ? W - x0 - 4 : x0, Dc = (D + 3) / 4 * 4;
+    const int lim = active ? min(lim_raw, Dc) : 0;
+    const float *fw = tgt_pass ? sR + 4 * q : sT + DPAD + 4 * q;
     float acc[CK][4];
-    float4 keep[CK];   // the half of the feature window the next block of 4 disparities re-uses
+    float4 wa[CK], wb[CK];
 #pragma unroll
-    for (int k = 0; k < CK; ++k) {
+    for (int k = 0; k < CK; ++k)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[k][i] = 0.0f;
-        keep[k] = tgt_pass ? *reinterpret_cast<const float4 *>(sR + k * pitch + 4 * q)            // ref[p .. p+3]
-                           : *reinterpret_cast<const float4 *>(sT + k * pitch + Dpad + 4 * q);    // tgt[p .. p+3]
-    }
     for (int s = 0; s < nstage; ++s) {
         cp_async_wait<NST - 2>();
-        __syncthreads();   // stage s has landed for every thread; everyone is done with stage s-1's buffer
+        __syncthreads();   // stage s (and, for s == 0, the features) landed for every thread; stage s-1's buffer is free
         if (s + NST - 1 < nstage) issue_stage(s + NST - 1);
         cp_async_commit();
-        if (!active) continue;
-        const float *gs = sG + (s % NST) * RS * pitch + 4 * q;
+        const int d0 = s * RS;
+        if (d0 >= lim) continue;
+        const float *gs = sG + (s % NST) * RS * PITCH + 4 * q;
+        if (s == 0) {
 #pragma unroll
-        for (int blk = 0; blk < RS / 4; ++blk) {
-            const int d0 = s * RS + 4 * blk;
-            if (d0 >= D) break;
-            float m[4][4];
-            if (!tgt_pass) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {   // d_ref needs x >= d (rows past D are zero-filled)
-                    const float4 gv = *reinterpret_cast<const float4 *>(gs + (4 * blk + j) * pitch);
-                    const float v[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) m[j][i] = xs[i] >= d0 + j ? v[i] : 0.0f;
-                }
-#pragma unroll
-                for (int k = 0; k < CK; ++k) {
-                    const float4 t0 = *reinterpret_cast<const float4 *>(sT + k * pitch + Dpad + 4 * q - d0 - 4), t1 = keep[k];
-                    const float tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(m[j][i], tw[4 + i - j], acc[k][i]);
-                    keep[k] = t0;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {   // d_tgt pairs g[d][p+i+d] with ref[p+i+d] and needs x + d < W
-                    const float *gr = gs + (4 * blk + j) * pitch + d0;
-                    const float4 ga = *reinterpret_cast<const float4 *>(gr), gb = *reinterpret_cast<const float4 *>(gr + 4);
-                    const float v[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) m[j][i] = xs[i] + d0 + j < W ? v[i + j] : 0.0f;
-                }
-#pragma unroll
-                for (int k = 0; k < CK; ++k) {
-                    const float4 r0 = keep[k], r1 = *reinterpret_cast<const float4 *>(sR + k * pitch + 4 * q + d0 + 4);
-                    const float rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(m[j][i], rw[i + j], acc[k][i]);
-                    keep[k] = r1;
-                }
-            }
+            for (int k = 0; k < CK; ++k) wa[k] = *reinterpret_cast<const float4 *>(fw + k * PITCH);   // window at d0 = 0
+        }
+        if (!tgt_pass) {
+            RingBlock<CK, false>::full(acc, gs, fw, d0, wa, wb);
+            if (d0 + 4 < lim) RingBlock<CK, false>::full(acc, gs + 4 * PITCH, fw, d0 + 4, wb, wa);
+        } else {
+            RingBlock<CK, true>::full(acc, gs, fw, d0, wa, wb);
+            if (d0 + 4 < lim) RingBlock<CK, true>::full(acc, gs + 4 * PITCH, fw, d0 + 4, wb, wa);
         }
     }
     cp_async_wait<0>();
     if (!active) return;
+    if (lim_raw < Dc) {   // boundary triangle: gradient rows lim_raw .. +3 straight from global (rows >= D count as zero)
+        const float *gq = gplane + static_cast<int64_t>(lim_raw) * HW + p + (tgt_pass ? lim_raw : 0);
+        float4 gv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            gv[j] = lim_raw + j < D ? __ldg(reinterpret_cast<const float4 *>(gq + static_cast<int64_t>(j) * HW))
+                                    : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const float *fo = fw + (tgt_pass ? lim_raw : -lim_raw);
+#pragma unroll
+        for (int k = 0; k < CK; ++k) {
+            const float4 o = *reinterpret_cast<const float4 *>(fo + k * PITCH);
+            const float w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float v[4] = {gv[j].x, gv[j].y, gv[j].z, gv[j].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (tgt_pass) {          // terms i + j < 4:  g[d][p + d + i] * ref[p + d + i]
+                        if (i + j < 4) acc[k][i] = fmaf(v[i + j], w[i + j], acc[k][i]);
+                    } else {                 // terms i >= j:     g[d][p + i] * tgt[p + i - d]
+                        if (i >= j) acc[k][i] = fmaf(v[i], w[i - j], acc[k][i]);
+                    }
+                }
+            }
+        }
+    }
     const float inv = 1.0f / static_cast<float>(cpg);
 #pragma unroll
     for (int k = 0; k < CK; ++k)
@@ -460,30 +477,31 @@ static int launch_gwc_bwd_quad(const float *go, const float *ref, const float *t
 template <int CK, int RS, int NST>
 static int launch_gwc_bwd_ring(const float *go, const float *ref, const float *tgt, float *gref, float *gtgt, int B, int C,
                                int HW, int W, int D, int G, int cpg, int Dtot, int dofs, cudaStream_t st) {
-    constexpr int SQ = 64, SPAN = SQ * 4;
-    const int Dpad = (D + 3) / 4 * 4 + 4;
-    const size_t smem = sizeof(float) * (2 * CK + NST * RS) * (SPAN + Dpad);
-    if (smem > 200 * 1024) return DV_ERR_UNSUPPORTED;
-    auto kern = gwc_bwd_ring_kernel<CK, SQ, RS, NST>;
+    // rows past D are zero-filled in the ring, so D is rounded up to whole blocks; the window reaches DPAD columns back
+    if (W % 4 != 0 || (D + 3) / 4 * 4 + 4 > kRingDpad || static_cast<int64_t>(Dtot) * HW > INT32_MAX) return DV_ERR_UNSUPPORTED;
+    const int chunks = cpg / CK, nspan = (HW + kRingSpan - 1) / kRingSpan;
+    if (static_cast<int64_t>(nspan) * chunks > INT32_MAX) return DV_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(float) * (2 * CK + NST * RS) * kRingPitch;
+    auto kern = gwc_bwd_ring_kernel<CK, RS, NST>;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
         return DV_ERR_LAUNCH;
-    dim3 grid((HW + SPAN - 1) / SPAN, G * (cpg / CK), B);
-    kern<<<grid, 2 * SQ, smem, st>>>(go, ref, tgt, gref, gtgt, C, HW, W, D, G, cpg, Dpad, Dtot, dofs,
-                                     static_cast<int64_t>(B) * G * Dtot * HW);
+    dim3 grid(nspan * chunks, G, B);
+    kern<<<grid, 2 * kRingSQ, smem, st>>>(go, ref, tgt, gref, gtgt, C, HW, W, D, G, cpg, chunks, Dtot, dofs);
     return finish_launch();
 }
 
 template <int CK>
 static int launch_gwc_bwd_best(const float *go, const float *ref, const float *tgt, float *gref, float *gtgt, int B, int C,
                                int HW, int W, int D, int G, int cpg, int Dtot, int dofs, cudaStream_t st) {
+    int rc = DV_ERR_UNSUPPORTED;
     switch (DV_TUNE("DV_GWC_BWD_RING", 1)) {
         case 0: break;
-        case 2: return launch_gwc_bwd_ring<CK, 4, 4>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
-        case 3: return launch_gwc_bwd_ring<CK, 8, 4>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
-        case 4: return launch_gwc_bwd_ring<CK, 4, 3>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
-        default: return launch_gwc_bwd_ring<CK, 8, 3>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
+        case 2: rc = launch_gwc_bwd_ring<CK, 8, 4>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st); break;
+        case 3: rc = launch_gwc_bwd_ring<CK, 8, 2>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st); break;
+        default: rc = launch_gwc_bwd_ring<CK, 8, 3>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st); break;
     }
+    if (rc != DV_ERR_UNSUPPORTED) return rc;
     return launch_gwc_bwd_quad<CK>(go, ref, tgt, gref, gtgt, B, C, HW, W, D, G, cpg, Dtot, dofs, st);
 }
 
