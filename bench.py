@@ -393,7 +393,16 @@ def run_ours(args):
         torch.cuda.empty_cache()
         legs = extra_legs(args, dev, rank, world, barrier, dist)
     if rank == 0:
-        result["e2e"] = e2e
+        # primary end-to-end number: the quarter-resolution boundary (the conv stack's real output; F.upsample fused into the
+        # regression kernel) — the full-resolution logits boundary the metric's `value` is defined on ships 10x the bytes
+        # over PCIe for tensors that only ever exist on the device, and stays in the line as the stated worst case
+        if fused is not None and fused.get("e2e") is not None:
+            result["e2e"] = dict(fused["e2e"], boundary="quarter-res cost [B,1,48,h,w] per step, trilinear x4 upsample fused "
+                                                        "(AcvHotPath(regress_mode='fused_upsample'))")
+            if e2e is not None:
+                result["e2e_logits_boundary"] = dict(e2e, boundary="full-res logits [B,192,H,W] per step (worst case)")
+        else:
+            result["e2e"] = e2e
         if legs:
             result.update(legs)
         if graph_leg is not None:
@@ -636,34 +645,46 @@ def extra_legs(args, dev, rank, world, barrier, dist):
 
 def run_e2e(args, path, inp, dev, barrier, dist, world):
     """Host-resident inputs (pinned) -> H2D copies -> hot path -> D2H of the prediction, every step inside the
-    timed region.  The per-step logits are part of the step's inputs, so they are copied too."""
+    timed region.  The per-step cost tensors are part of the step's inputs, so they are copied too.
+
+    The DDIM noise is NOT an input: the reference draws it on the device inside ddim_sample (acv_ddim.py:310,354-360), so
+    this leg draws it on the device too, inside the timed region, in the reference's order and dtypes (SURVEY.md §8a row a16,
+    including the draws whose values the reference never uses) — `--e2e-noise host` restores the round-1 behaviour of
+    shipping pre-drawn noise over PCIe.  Pinned buffers are allocated after the rank has been bound to the CPUs local to
+    its GPU (diffuvolume_b200.distributed.bind_to_gpu_numa_node), so the pages sit on the GPU's NUMA node."""
+    from diffuvolume_b200.distributed import bind_to_gpu_numa_node, gpu_numa_info
     B = args.batch
+    placement = dict(gpu_numa_info(dev.index), bound_cpus=None if args.no_numa_bind else bind_to_gpu_numa_node(dev.index))
+    device_noise = args.e2e_noise == "device"
     names = ["feat_l", "feat_r", "cfeat_l", "cfeat_r", "att_logits", "used", "disp_q"]
+    lists = ("shifts",) if device_noise else ("shifts", "step_noises", "renoises")
     host = {k: inp[k].cpu().pin_memory() for k in names}
     host["costs"] = [inp["costs"][0].cpu().pin_memory()]
-    for k in ("shifts", "step_noises", "renoises"):
+    for k in lists:
         host[k] = [t.cpu().pin_memory() for t in inp[k]]
     pred_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
     h2d = sum(host[k].numel() * host[k].element_size() for k in names)
     h2d += T_STEPS * host["costs"][0].numel() * 4      # the cost tensor of each of the T steps is a step input
-    h2d += sum(t.numel() * t.element_size() for k in ("shifts", "step_noises", "renoises") for t in host[k])
+    h2d += sum(t.numel() * t.element_size() for k in lists for t in host[k])
     d2h = pred_host.numel() * 4
-    # Two device-side input sets: the H2D copies of step i+1 run on a copy stream while step i computes (every step's
+    # Two device-side input sets: the H2D copies of step i+1 run on copy streams while step i computes (every step's
     # inputs are still copied inside the timed region; the first copy of the region is not overlapped with anything).
-    lists = ("shifts", "step_noises", "renoises")
     sets = []
     for _ in range(2):
         d = {k: torch.empty_like(inp[k]) for k in names}
         for k in lists:
             d[k] = [torch.empty_like(t) for t in inp[k]]
         sets.append(d)
-    cost_bufs = [torch.empty_like(inp["costs"][0]) for _ in range(2)]   # double buffer for the per-step logits
-    copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event() for _ in range(2)]
+    cost_bufs = [torch.empty_like(inp["costs"][0]) for _ in range(2)]   # double buffer for the per-step cost tensors
+    copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.e2e_copy_streams))]
+    ready = [[torch.cuda.Event() for _ in copy_streams] for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+    shape_q = tuple(inp["step_noises"][0].shape)
 
     def stage_logits(i):
-        # the logits of step i arrive from the host right before that step consumes them; two device buffers
+        # the cost tensor of step i arrives from the host right before that step consumes it; two device buffers
         # alternate (stream order guarantees step i-2 has consumed a buffer before it is overwritten)
         buf = cost_bufs[i % 2]
         buf.copy_(host["costs"][0], non_blocking=True)
@@ -671,21 +692,33 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
 
     def prefetch(i):
         d = sets[i % 2]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[i % 2])        # the step that last read this set has finished
-            for k in names:
-                d[k].copy_(host[k], non_blocking=True)
-            for k in lists:
-                for dd, ss in zip(d[k], host[k]):
+        jobs = [(d[k], host[k]) for k in names] + [(dd, ss) for k in lists for dd, ss in zip(d[k], host[k])]
+        for si, st in enumerate(copy_streams):
+            with torch.cuda.stream(st):
+                st.wait_event(consumed[i % 2])             # the step that last read this set has finished
+                for dd, ss in jobs[si::len(copy_streams)]:
                     dd.copy_(ss, non_blocking=True)
-            ready[i % 2].record(copy_stream)
+                ready[i % 2][si].record(st)
+
+    def draw_noise():
+        # acv_ddim.py:310 (unused start noise), then per non-final step :354 randn_like(img) (fp32 at step 1, fp64 after),
+        # :358 randint, :243 randn_like(asd) fp32 (only a dtype/shape template there), :360 rand_like fp64
+        torch.randn(shape_q, generator=gen, device=dev)
+        sn, rn_ = [], []
+        for i in range(T_STEPS - 1):
+            sn.append(torch.randn(shape_q, generator=gen, device=dev, dtype=torch.float32 if i == 0 else torch.float64))
+            torch.randint(0, 1000, (1,), generator=gen, device=dev)
+            torch.randn(shape_q, generator=gen, device=dev)
+            rn_.append(torch.rand(shape_q, generator=gen, device=dev, dtype=torch.float64))
+        return sn, rn_
 
     def compute(i):
         d = sets[i % 2]
         cur = torch.cuda.current_stream(dev)
-        cur.wait_event(ready[i % 2])
-        out = path(**{k: d[k] for k in names}, costs=stage_logits, shifts=d["shifts"], step_noises=d["step_noises"],
-                   renoises=d["renoises"])
+        for e in ready[i % 2]:
+            cur.wait_event(e)
+        sn, rn_ = draw_noise() if device_noise else (d["step_noises"], d["renoises"])
+        out = path(**{k: d[k] for k in names}, costs=stage_logits, shifts=d["shifts"], step_noises=sn, renoises=rn_)
         consumed[i % 2].record(cur)
         pred_host.copy_(out["pred"], non_blocking=True)
 
@@ -715,8 +748,12 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
         ms = float(tt.item())
     return {"value": round(B * world * steps / (ms / 1e3), 2), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": round(ms / steps, 3),
+            "h2d_GBs_per_gpu": round(h2d * steps / 1e9 / (ms / 1e3), 1),
+            "noise": "drawn on the device inside the timed region, reference order/dtypes (acv_ddim.py:310,354-360)"
+                     if device_noise else "pre-drawn on the host and copied with the inputs",
+            "copy_streams": len(copy_streams), "host_placement_rank0": placement,
             "note": f"pinned host inputs incl. the T=5 per-step {list(host['costs'][0].shape)} cost tensors; PCIe-bound; "
-                    "H2D of step i+1 overlapped with the compute of step i (copy stream + events)"}
+                    "H2D of step i+1 overlapped with the compute of step i (copy streams + events)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -835,6 +872,10 @@ def main():
                     help="full-resolution HxW of the synthetic pairs (multiples of 4): 540x960 is BASELINE.json's metric; "
                          "384x1248 (KITTI, 376 padded) is the north_star's second resolution")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-noise", choices=["device", "host"], default="device",
+                    help="device: DDIM noise drawn on the GPU inside the timed region (as the reference does); host: shipped over PCIe")
+    ap.add_argument("--e2e-copy-streams", type=int, default=2)
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's local CPUs before pinning")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay leg")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

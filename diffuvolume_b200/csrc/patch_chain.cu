@@ -252,6 +252,157 @@ static int launch_rows(const float *in, const float *w1, const float *w2, float 
     return finish_launch();
 }
 
+// ---- streaming kernel: one WARP walks one [H,W] plane top to bottom -------------------------------------------------------
+// The tile kernels above run at ~300 instructions per output quad (run-time tile shapes, e / qpr index splits, phase barriers,
+// 1.3x halo recompute of the intermediate) and are issue-bound (ncu: 70 % issue slots, DRAM 32 %).  Here a plane is a
+// stream of rows:
+//   * lane l owns PX adjacent columns; input rows arrive through an NI-deep ring of LDGSTS copies (one contiguous W*4-byte
+//     row per warp instruction pair, zero-filled below the image), NPF rows ahead of their use;
+//   * the first stencil (dilation 1) keeps rows m-1, m in REGISTERS and loads only row m+1 ((PX+8)/4 LDS.128), the
+//     intermediate row goes to an MR-deep shared ring (zero outside the image, like the reference's second zero padding);
+//   * the second stencil reads its three tap rows m-2 D2, m-D2, m from that ring and stores output row m-D2 (one
+//     contiguous row per warp);  no vertical halo is ever recomputed, and the only synchronisation is __syncwarp.
+// All shared offsets are compile-time (PITCH = 32 PX + 8: 4 zero columns left and right of the row).
+__device__ __forceinline__ void pc_cp_async16(void *dst_smem, const void *src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(sz) : "memory");
+}
+
+template <int D2, int PX, int NI>
+__global__ void __launch_bounds__(32)
+patch_chain_stream_kernel(const float *__restrict__ in, const float *__restrict__ w1, const float *__restrict__ w2,
+                          float *__restrict__ out, int C, int D, int H, int W, int c0) {
+    static_assert(PX % 4 == 0 && D2 >= 1 && D2 <= 3 && (NI & (NI - 1)) == 0, "quads; taps within the 4-column pad");
+    constexpr int NPF = NI - 2, MR = D2 == 1 ? 4 : 8, PITCH = 32 * PX + 8, NV = PX + 8, Q = PX / 4;
+    extern __shared__ __align__(16) float sm[];
+    float *rin = sm, *rmid = sm + NI * PITCH;
+    const int lane = threadIdx.x;
+    const int c = c0 + blockIdx.x / D, d = blockIdx.x % D, b = blockIdx.y;
+    const int64_t plane = ((static_cast<int64_t>(b) * C + c) * D + d) * H * W;
+    const float *ip = in + plane;
+    float *op = out + plane;
+    float k1[9], k2[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        k1[i] = __ldg(w1 + c * 9 + i);
+        k2[i] = __ldg(w2 + c * 9 + i);
+    }
+    for (int e = lane; e < (NI + MR) * PITCH / 4; e += 32) reinterpret_cast<float4 *>(sm)[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncwarp();
+    const int col0 = lane * PX;
+    // 16-byte chunk q of a row (chunk 0 = the left zero pad) lives at physical chunk sw(q): lanes read windows of NV/4 chunks
+    // at a stride of PX/4 chunks, which without the XOR puts lanes l and l+4 (PX = 8) / l+2 (PX = 16) of a quarter-warp on
+    // the same banks — ncu: 2/3 of the shared wavefronts were conflict replays, LSU pipe 90 % busy
+    auto sw = [](int q) { return PX == 8 ? (q ^ ((q >> 3) & 1)) : PX == 16 ? (q ^ ((q >> 3) & 3)) : q; };
+    int off[NV / 4];      // float offsets of this lane's window chunks inside a row; own data = chunks 1 .. Q
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) off[j] = 4 * sw(lane * Q + j);
+    bool qok[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) qok[j] = col0 + 4 * j < W;
+    auto issue_row = [&](int y) {   // rows >= H are zero rows of the padding
+        float *dst = rin + (y & (NI - 1)) * PITCH;
+        const float *src = ip + static_cast<int64_t>(y) * W + col0;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            const bool ok = y < H && qok[j];
+            pc_cp_async16(dst + off[1 + j], ok ? src + 4 * j : in, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto load_row = [&](const float *row, float (&v)[NV]) {   // columns col0-4 .. col0+PX+3
+#pragma unroll
+        for (int j = 0; j < NV / 4; ++j) {
+            const float4 t = *reinterpret_cast<const float4 *>(row + off[j]);
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+    };
+    for (int y = 0; y <= NPF; ++y) issue_row(y);
+    float ra[NV], rb[NV], rc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ra[i] = 0.0f;                  // row -1
+    asm volatile("cp.async.wait_group %0;" ::"n"(NPF) : "memory");
+    __syncwarp();
+    load_row(rin, rb);                                            // row 0
+    const int M = H + D2;
+    // one step: intermediate row m from input rows (r0, r1, r2) = (m-1, m, m+1), then output row m - D2
+    auto step = [&](int m, const float (&r0)[NV], const float (&r1)[NV], float (&r2)[NV]) {
+        issue_row(m + 1 + NPF);
+        asm volatile("cp.async.wait_group %0;" ::"n"(NPF) : "memory");
+        __syncwarp();
+        load_row(rin + ((m + 1) & (NI - 1)) * PITCH, r2);
+        float acc[PX];
+#pragma unroll
+        for (int i = 0; i < PX; ++i) acc[i] = 0.0f;
+        if (m < H) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int i = 0; i < PX; ++i) acc[i] = fmaf(k1[kx], r0[3 + i + kx], acc[i]);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int i = 0; i < PX; ++i) acc[i] = fmaf(k1[3 + kx], r1[3 + i + kx], acc[i]);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int i = 0; i < PX; ++i) acc[i] = fmaf(k1[6 + kx], r2[3 + i + kx], acc[i]);
+        }
+        float *mrow = rmid + (m & (MR - 1)) * PITCH;
+#pragma unroll
+        for (int j = 0; j < Q; ++j)     // the intermediate is ZERO outside the image (second zero padding)
+            *reinterpret_cast<float4 *>(mrow + off[1 + j]) = (m < H && qok[j])
+                ? make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        __syncwarp();
+        const int o = m - D2;
+        if (o < 0) return;
+        float res[PX];
+#pragma unroll
+        for (int i = 0; i < PX; ++i) res[i] = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            float v[NV];
+            load_row(rmid + ((o + (ky - 1) * D2) & (MR - 1)) * PITCH, v);   // rows < 0: slots still hold their initial zeros
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int i = 0; i < PX; ++i) res[i] = fmaf(k2[ky * 3 + kx], v[4 + i + (kx - 1) * D2], res[i]);
+        }
+        float *orow = op + static_cast<int64_t>(o) * W + col0;
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+            if (qok[j]) *reinterpret_cast<float4 *>(orow + 4 * j) = make_float4(res[4 * j], res[4 * j + 1], res[4 * j + 2], res[4 * j + 3]);
+    };
+    for (int m = 0; m < M; m += 3) {
+        step(m, ra, rb, rc);
+        if (m + 1 < M) step(m + 1, rb, rc, ra);
+        if (m + 2 < M) step(m + 2, rc, ra, rb);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int D2, int PX>
+static int launch_stream(const float *in, const float *w1, const float *w2, float *out, int B, int C, int D, int H, int W,
+                         int c0, int c1, cudaStream_t st) {
+    constexpr int NI = 8, MR = D2 == 1 ? 4 : 8, PITCH = 32 * PX + 8;
+    const size_t smem = sizeof(float) * (NI + MR) * PITCH;
+    auto kern = patch_chain_stream_kernel<D2, PX, NI>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return DV_ERR_LAUNCH;
+    dim3 grid(static_cast<unsigned>((c1 - c0) * D), static_cast<unsigned>(B));
+    kern<<<grid, 32, smem, st>>>(in, w1, w2, out, C, D, H, W, c0);
+    return finish_launch();
+}
+
+template <int D2>
+static int launch_stream_px(const float *in, const float *w1, const float *w2, float *out, int B, int C, int D, int H, int W,
+                            int c0, int c1, cudaStream_t st) {
+    if (W <= 256) return launch_stream<D2, 8>(in, w1, w2, out, B, C, D, H, W, c0, c1, st);
+    if (W <= 384) return launch_stream<D2, 12>(in, w1, w2, out, B, C, D, H, W, c0, c1, st);
+    return launch_stream<D2, 16>(in, w1, w2, out, B, C, D, H, W, c0, c1, st);
+}
+
 template <bool CHAIN>
 __global__ void __launch_bounds__(256)
 depthwise_chain_quad_kernel(const float *__restrict__ in, const float *__restrict__ w1, const float *__restrict__ w2,
@@ -321,6 +472,15 @@ extern "C" int dv_depthwise3x3_chain_f32(const float *in, const float *w1, const
     if (B > 65535 || (c1 - c0) * D > 65535 || H * W > INT32_MAX) return DV_ERR_BAD_SHAPE;
     if (in == out) return DV_ERR_UNSUPPORTED;  // tiles read their neighbours' inputs
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the ACVNet chain (patch dil 1 -> patch_l* dil 1..3) on planes up to 512 columns: the row-streaming kernel
+    if (w2 && dil1 == 1 && dil2 >= 1 && dil2 <= 3 && W % 4 == 0 && W >= 64 && W <= 512 && aligned16(in) && aligned16(out) &&
+        DV_TUNE("DV_PATCH_STREAM", 1)) {
+        const int Bi = static_cast<int>(B), Ci = static_cast<int>(C), Di = static_cast<int>(D), Hi = static_cast<int>(H),
+                  Wi = static_cast<int>(W), a = static_cast<int>(c0), z = static_cast<int>(c1);
+        if (dil2 == 1) return launch_stream_px<1>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
+        if (dil2 == 2) return launch_stream_px<2>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
+        return launch_stream_px<3>(in, w1, w2, out, Bi, Ci, Di, Hi, Wi, a, z, st);
+    }
     if (W % 4 == 0 && aligned16(in) && aligned16(out) && DV_TUNE("DV_PATCH_ROWS", 1)) {
         // compile-time dilations (everything ACVNet uses): the row-blocked kernel
         const int Bi = static_cast<int>(B), Ci = static_cast<int>(C), Di = static_cast<int>(D), Hi = static_cast<int>(H),

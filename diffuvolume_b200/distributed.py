@@ -112,3 +112,54 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
             kw["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend, **kw)
     return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------
+# Host placement of a rank: pinned staging buffers should live on the NUMA node its GPU hangs off
+# --------------------------------------------------------------------------------------------
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_info(device_index: int) -> Dict[str, object]:
+    """PCI address, NUMA node and local CPU list of a CUDA device as sysfs reports them (empty values when sysfs does not
+    expose the device, e.g. in a container without /sys/bus/pci)."""
+    import os
+    info: Dict[str, object] = {"pci": None, "numa_node": None, "local_cpus": None}
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        pci = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        info["pci"] = pci
+        base = f"/sys/bus/pci/devices/{pci}"
+        if os.path.exists(f"{base}/numa_node"):
+            info["numa_node"] = int(open(f"{base}/numa_node").read().strip())
+        if os.path.exists(f"{base}/local_cpulist"):
+            info["local_cpus"] = open(f"{base}/local_cpulist").read().strip()
+    except Exception:  # noqa: BLE001 — placement is an optimisation, never a failure
+        pass
+    return info
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[str]:
+    """Restrict this process to the CPUs local to its GPU (sched_setaffinity), so that the pinned host buffers it allocates
+    and first-touches afterwards land on that NUMA node and its H2D copies do not cross the socket interconnect.  Returns
+    the CPU list applied, or None when sysfs has no placement for the device or the mask would be empty."""
+    import os
+    cpus_txt = gpu_numa_info(device_index).get("local_cpus")
+    if not cpus_txt or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        allowed = os.sched_getaffinity(0)
+        want = set(_parse_cpulist(str(cpus_txt))) & allowed
+        if not want:
+            return None
+        os.sched_setaffinity(0, want)
+        return str(cpus_txt)
+    except OSError:
+        return None

@@ -1,4 +1,7 @@
-"""ncu target: one warm + one profiled launch of the secondary kernels at their BASELINE sizes."""
+"""ncu target: one warm pass, then one profiled launch (cudaProfilerStart/Stop window) of the secondary kernels at their
+BASELINE sizes.  Run as
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/rows_full python scripts/prof_rows.py
+"""
 import sys
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import torch
@@ -8,16 +11,77 @@ g = torch.Generator(device=dev); g.manual_seed(3)
 rn = lambda *s: torch.randn(*s, generator=g, device=dev)
 ru = lambda *s: torch.rand(*s, generator=g, device=dev)
 B = 8
-fl, fr = rn(B, 320, 135, 240), rn(B, 320, 135, 240)
-gv = rn(B, 40, 48, 135, 240)
-wp, wl = rn(40, 9), rn(40, 9)
-f1, f2 = rn(4, 32, 384, 1248), rn(4, 32, 384, 1248)
-dsp = (torch.linspace(2, 90, 1248, device=dev).view(1, 1, 1, -1).expand(4, 1, 384, 1248) + ru(4, 1, 384, 1248)).contiguous()
-a1, a2 = rn(B, 96, 96, 312), rn(B, 96, 96, 312)
-for _ in range(2):
-    ops.gwc_volume_bwd(gv, fl, fr, 40)
-    ops.acv_patch_volume(gv, wp, wl[:8], wl[8:24], wl[24:])
-    ops.corr_volume_2sided(f1, f2, 24, 1)
-    ops.warp(f2, dsp)
-    ops.corr1d_allpairs(a1, a2)
-torch.cuda.synchronize()
+only = set(sys.argv[1].split(",")) if len(sys.argv) > 1 else None
+jobs = []
+
+
+def job(name, setup):
+    if only is None or name in only:
+        jobs.append((name, setup))
+
+
+def acv_bwd():
+    fl, fr, gv = rn(B, 320, 135, 240), rn(B, 320, 135, 240), rn(B, 40, 48, 135, 240)
+    return lambda: ops.gwc_volume_bwd(gv, fl, fr, 40)
+
+
+def patch():
+    gv, wp, wl = rn(B, 40, 48, 135, 240), rn(40, 9), rn(40, 9)
+    return lambda: ops.acv_patch_volume(gv, wp, wl[:8], wl[8:24], wl[24:])
+
+
+def pcw():
+    f1, f2 = rn(4, 32, 384, 1248), rn(4, 32, 384, 1248)
+    dsp = (torch.linspace(2, 90, 1248, device=dev).view(1, 1, 1, -1).expand(4, 1, 384, 1248) + ru(4, 1, 384, 1248)).contiguous()
+    gw, gv = rn(4, 32, 384, 1248), rn(4, 1, 49, 384, 1248)
+    buf = torch.empty(4, 2 * 32 + 5 + 49, 384, 1248, device=dev)
+
+    def run():
+        ops.corr_volume_2sided(f1, f2, 24, 1)
+        ops.warp(f2, dsp)
+        ops.refine_input_assemble(f1, f2, dsp, 24, 1, corr_out=buf[:, 69:], diff_out=buf[:, :32], copy_out=buf[:, 32:64])
+        ops.warp_bwd(gw, f2, dsp)
+        ops.gwc_volume_bwd(gv, f1, f2, 1, two_sided_maxdisp=24)
+    return run
+
+
+def ups():
+    cq = rn(B, 1, 48, 135, 240) * 4.0
+    used = ru(B, 540, 960) * 191.0
+    return lambda: (ops.upsample_softmax_regress(cq, (192, 540, 960)),
+                    ops.upsample_softmax_regress(cq, (192, 540, 960), used=used, vote_thresholds=(1.0, 3.0)))
+
+
+def igev():
+    a1, a2 = rn(B, 96, 96, 312), rn(B, 96, 96, 312)
+    geo = rn(B, 8, 48, 96, 312)
+    corr = ops.corr1d_allpairs(a1, a2).reshape(B * 96 * 312, 1, 1, 312)
+    pk = ops.geo_pack(geo, 2)
+    cp = [corr, ops.avgpool_w2(corr)]
+    disp = ru(B, 1, 96, 312) * 40.0
+    coords = torch.arange(312, device=dev, dtype=torch.float32).view(1, 1, 1, 312).expand(B, 1, 96, 312).contiguous()
+    noisy = ru(B, 48, 96, 312)
+
+    def run():
+        ops.corr1d_allpairs(a1, a2)
+        ops.geo_pack(geo, 2)
+        f = ops.geo_filter_packed(pk, noisy)
+        ops.geo_lookup_packed(f, cp, disp, coords, None, 4)
+    return run
+
+
+job("acv_bwd", acv_bwd); job("patch", patch); job("pcw", pcw); job("ups", ups); job("igev", igev)
+for name, setup in jobs:
+    try:
+        fn = setup()
+        fn(); fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print("profiled", name, flush=True)
+    except Exception as e:  # keep going: one broken signature must not void the capture
+        print("FAILED", name, repr(e), flush=True)
+    del fn
+    torch.cuda.empty_cache()

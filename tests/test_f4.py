@@ -118,7 +118,11 @@ def test_patch_chain_golden(gold, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(1, 40, 6, 135, 240), (2, 40, 2, 33, 65), (1, 40, 1, 1, 1), (1, 40, 2, 3, 130)])
+@pytest.mark.parametrize("shape", [(1, 40, 6, 135, 240), (2, 40, 2, 33, 65), (1, 40, 1, 1, 1), (1, 40, 2, 3, 130),
+                                   # the row-streaming kernel: 12 / 16 columns per lane, a ragged last lane (244 = 30.5 x 8),
+                                   # planes shorter than the prefetch depth and than the dilation
+                                   (1, 40, 2, 96, 312), (1, 40, 1, 5, 400), (1, 40, 1, 1, 64), (1, 40, 1, 2, 244),
+                                   (2, 40, 1, 7, 68), (1, 40, 1, 3, 512)])
 def test_patch_chain_vs_oracle(shape):
     from diffuvolume_b200 import ops
     B, C, D, H, W = shape

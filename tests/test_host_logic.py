@@ -164,3 +164,15 @@ def test_fuse_acv_patch_is_transparent_on_cpu_and_restores_classes():
         install.uninstall()
     assert [type(m) for m in (net.patch, net.patch_l1, net.patch_l2, net.patch_l3)] == classes
     assert not install.fuse_acv_patch(torch.nn.Linear(2, 2))     # nothing to fuse
+
+
+def test_cpulist_parsing_and_numa_helpers_are_safe_without_a_gpu():
+    """Host placement helpers of distributed.py: the sysfs CPU-list grammar, and no exception (just None / empty info) on a
+    box without the device."""
+    from diffuvolume_b200.distributed import _parse_cpulist, bind_to_gpu_numa_node, gpu_numa_info
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _parse_cpulist("") == []
+    info = gpu_numa_info(0)
+    assert set(info) == {"pci", "numa_node", "local_cpus"}
+    if not torch.cuda.is_available():
+        assert info["pci"] is None and bind_to_gpu_numa_node(0) is None
