@@ -395,14 +395,23 @@ corr_negative_rows_kernel(const float *__restrict__ ref, const float *__restrict
     float acc[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.0f;
-#pragma unroll 4
-    for (int c = 0; c < cpg; ++c) {
-        const float rv = __ldg(l + c * HW), tv = __ldg(r + c * HW);
+    for (int c0 = 0; c0 < cpg; c0 += 16) {          // 32 loads in flight per lane before the first use
+        float rv[16], tv[16];
 #pragma unroll
-        for (int k = 1; k <= 32; ++k) {
-            if (k > m) break;                       // uniform
-            const float t = __shfl_sync(0xffffffffu, tv, (m - k + x) & 31);
-            acc[k - 1] = fmaf(rv, t, acc[k - 1]);   // meaningful for x < k only
+        for (int u = 0; u < 16; ++u) {
+            const int c = min(c0 + u, cpg - 1);
+            rv[u] = __ldg(l + c * HW);
+            tv[u] = __ldg(r + c * HW);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (c0 + u >= cpg) break;               // uniform
+#pragma unroll
+            for (int k = 1; k <= 32; ++k) {
+                if (k > m) break;                   // uniform
+                const float t = __shfl_sync(0xffffffffu, tv[u], (m - k + x) & 31);
+                acc[k - 1] = fmaf(rv[u], t, acc[k - 1]);   // meaningful for x < k only
+            }
         }
     }
     const float inv = 1.0f / static_cast<float>(cpg);

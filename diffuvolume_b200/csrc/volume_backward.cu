@@ -478,25 +478,38 @@ corr_negative_bwd_rows_kernel(const float *__restrict__ go, const float *__restr
     for (int s = 0; s < 32; ++s) gs[s] = (s < m && live) ? __ldg(gp + static_cast<int64_t>(s) * HW) : 0.0f;
     const int64_t frow = (static_cast<int64_t>(b) * C + static_cast<int64_t>(g) * cpg) * HW + static_cast<int64_t>(y) * W;
     const float inv = 1.0f / static_cast<float>(cpg);
-    for (int c = 0; c < cpg; ++c) {
-        const int64_t fr = frow + static_cast<int64_t>(c) * HW;
-        const float rv = __ldg(ref + fr + xc), tv = __ldg(tgt + fr + W - m + xc);
-        float ar = 0.0f, at = 0.0f;
+    for (int c0 = 0; c0 < cpg; c0 += 8) {            // loads (operands and the gradients to update) issued before the first use
+        float rv8[8], tv8[8], or8[8], ot8[8];
 #pragma unroll
-        for (int s = 31; s >= 0; --s) {                         // slot s <-> k = m - s, k ascending; static register index
-            if (s >= m) continue;                                // uniform
-            const int k = m - s;
-            // d_ref[x] += g[s][x] * tgt[W-k+x]              (x < k)        partner lane m-k+x = s+x
-            const float t = __shfl_sync(0xffffffffu, tv, (s + x) & 31);
-            if (x < k) ar = fmaf(gs[s], t, ar);
-            // d_tgt[W-m+x] += g[s][xs] * ref[xs], xs = x - s   (xs >= 0)     partner lane xs
-            const int xs = x - s;
-            const float gg = __shfl_sync(0xffffffffu, gs[s], xs & 31), rr = __shfl_sync(0xffffffffu, rv, xs & 31);
-            if (xs >= 0) at = fmaf(gg, rr, at);
+        for (int u = 0; u < 8; ++u) {
+            const int64_t fr = frow + static_cast<int64_t>(min(c0 + u, cpg - 1)) * HW;
+            rv8[u] = __ldg(ref + fr + xc);
+            tv8[u] = __ldg(tgt + fr + W - m + xc);
+            or8[u] = gref ? gref[fr + xc] : 0.0f;
+            ot8[u] = gtgt ? gtgt[fr + W - m + xc] : 0.0f;
         }
-        if (live) {
-            if (gref) gref[fr + x] += ar * inv;
-            if (gtgt) gtgt[fr + W - m + x] += at * inv;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (c0 + u >= cpg) break;                    // uniform
+            const int64_t fr = frow + static_cast<int64_t>(c0 + u) * HW;
+            const float rv = rv8[u], tv = tv8[u];
+            float ar = 0.0f, at = 0.0f;
+#pragma unroll
+            for (int s = 31; s >= 0; --s) {                         // slot s <-> k = m - s, k ascending; static register index
+                if (s >= m) continue;                                // uniform
+                const int k = m - s;
+                // d_ref[x] += g[s][x] * tgt[W-k+x]              (x < k)        partner lane m-k+x = s+x
+                const float t = __shfl_sync(0xffffffffu, tv, (s + x) & 31);
+                if (x < k) ar = fmaf(gs[s], t, ar);
+                // d_tgt[W-m+x] += g[s][xs] * ref[xs], xs = x - s   (xs >= 0)     partner lane xs
+                const int xs = x - s;
+                const float gg = __shfl_sync(0xffffffffu, gs[s], xs & 31), rr = __shfl_sync(0xffffffffu, rv, xs & 31);
+                if (xs >= 0) at = fmaf(gg, rr, at);
+            }
+            if (live) {
+                if (gref) gref[fr + x] = or8[u] + ar * inv;
+                if (gtgt) gtgt[fr + W - m + x] = ot8[u] + at * inv;
+            }
         }
     }
 }

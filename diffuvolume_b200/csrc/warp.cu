@@ -50,14 +50,14 @@ struct WarpTaps {
     }
 };
 
-template <bool ASSEMBLE>
+template <bool ASSEMBLE, int CG>
 __global__ void __launch_bounds__(256)
 warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *__restrict__ out, int C, int H, int W,
             int cgroups, float rcp_w, float rcp_h, int use_rcp, const float *__restrict__ ref, float *__restrict__ diff_out,
             int64_t diff_bstride, float *__restrict__ copy_out, int64_t copy_bstride) {
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, b = blockIdx.z / cgroups, cbeg = (blockIdx.z % cgroups) * kWarpCg;
-    const int cend = min(cbeg + kWarpCg, C);
+    const int y = blockIdx.y, b = blockIdx.z / cgroups, cbeg = (blockIdx.z % cgroups) * CG;
+    const int cend = min(cbeg + CG, C);
     if (px >= W) return;
     const int64_t HW = static_cast<int64_t>(H) * W;
     const WarpTaps t(disp[static_cast<int64_t>(b) * HW + static_cast<int64_t>(y) * W + px], px, y, H, W, rcp_w, rcp_h, use_rcp);
@@ -84,15 +84,15 @@ warp_kernel(const float *__restrict__ x, const float *__restrict__ disp, float *
     }
     // (measured, B = 8 at 384x1248: `ref` loads issued with the taps 0.72 ms; one dependent load per channel inside the
     // blend loop 1.28 ms; hoisted above the masked-pixel branch 0.85 ms)
-    float t00[kWarpCg], t01[kWarpCg], t10[kWarpCg], t11[kWarpCg], rr[ASSEMBLE ? kWarpCg : 1];
+    float t00[CG], t01[CG], t10[CG], t11[CG], rr[ASSEMBLE ? CG : 1];
 #pragma unroll
-    for (int k = 0; k < kWarpCg; ++k) {
+    for (int k = 0; k < CG; ++k) {
         const float *pc = xp + static_cast<int64_t>(min(cbeg + k, C - 1)) * HW;
         t00[k] = __ldg(pc + o00); t01[k] = __ldg(pc + o01); t10[k] = __ldg(pc + o10); t11[k] = __ldg(pc + o11);
         if (ASSEMBLE) rr[k] = rp ? __ldg(rp + static_cast<int64_t>(min(cbeg + k, C - 1)) * HW) : 0.0f;
     }
 #pragma unroll
-    for (int k = 0; k < kWarpCg; ++k) {
+    for (int k = 0; k < CG; ++k) {
         float v = __fmul_rn(t00[k], w00);
         v = __fadd_rn(v, __fmul_rn(t01[k], w01));
         v = __fadd_rn(v, __fmul_rn(t10[k], w10));
@@ -166,27 +166,42 @@ warp_bwd_kernel(const float *__restrict__ g, const float *__restrict__ x, const 
 
 }  // namespace dv
 
+template <bool ASSEMBLE, int CG>
+static int warp_launch(const float *x, const float *disp, float *out, const float *ref, float *diff_out, int64_t diff_bstride,
+                       float *copy_out, int64_t copy_bstride, int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t st) {
+    using namespace dv;
+    const int64_t cgroups = (C + CG - 1) / CG;
+    if (H * W > INT32_MAX || B * cgroups > 65535 || H > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
+    dim3 grid(static_cast<unsigned>((W + 255) / 256), static_cast<unsigned>(H), static_cast<unsigned>(B * cgroups));
+    const int use_rcp = (W - 1 <= 4096 && H - 1 <= 4096) ? 1 : 0;     // the range the reciprocal division was verified on
+    const float rcp_w = 1.0f / static_cast<float>(W > 1 ? W - 1 : 1), rcp_h = 1.0f / static_cast<float>(H > 1 ? H - 1 : 1);
+    warp_kernel<ASSEMBLE, CG><<<grid, 256, 0, st>>>(x, disp, out, static_cast<int>(C), static_cast<int>(H), static_cast<int>(W),
+                                                    static_cast<int>(cgroups), rcp_w, rcp_h, use_rcp, ref, diff_out, diff_bstride,
+                                                    copy_out, copy_bstride);
+    return finish_launch();
+}
+
 static int warp_impl(const float *x, const float *disp, float *out, const float *ref, float *diff_out, int64_t diff_bstride,
                      float *copy_out, int64_t copy_bstride, int64_t B, int64_t C, int64_t H, int64_t W, void *stream) {
     using namespace dv;
     if (!x || !disp || !out) return DV_ERR_NULL;
     if ((diff_out || copy_out) && !ref) return DV_ERR_NULL;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
-    const int64_t cgroups = (C + kWarpCg - 1) / kWarpCg;
-    if (H * W > INT32_MAX || B * cgroups > 65535 || H > 65535 || C > INT32_MAX) return DV_ERR_BAD_SHAPE;
-    dim3 grid(static_cast<unsigned>((W + 255) / 256), static_cast<unsigned>(H), static_cast<unsigned>(B * cgroups));
-    const int use_rcp = (W - 1 <= 4096 && H - 1 <= 4096) ? 1 : 0;     // the range the reciprocal division was verified on
-    const float rcp_w = 1.0f / static_cast<float>(W > 1 ? W - 1 : 1), rcp_h = 1.0f / static_cast<float>(H > 1 ? H - 1 : 1);
-    if (ref)
-        warp_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, disp, out, static_cast<int>(C), static_cast<int>(H),
-                                                                             static_cast<int>(W), static_cast<int>(cgroups), rcp_w,
-                                                                             rcp_h, use_rcp, ref, diff_out, diff_bstride, copy_out,
-                                                                             copy_bstride);
-    else
-        warp_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, disp, out, static_cast<int>(C), static_cast<int>(H),
-                                                                              static_cast<int>(W), static_cast<int>(cgroups), rcp_w,
-                                                                              rcp_h, use_rcp, nullptr, nullptr, 0, nullptr, 0);
-    return finish_launch();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!ref) {
+        switch (DV_TUNE("DV_WARP_CG", 8)) {
+            case 4: return warp_launch<false, 4>(x, disp, out, nullptr, nullptr, 0, nullptr, 0, B, C, H, W, st);
+            case 8: return warp_launch<false, 8>(x, disp, out, nullptr, nullptr, 0, nullptr, 0, B, C, H, W, st);
+            default: return warp_launch<false, kWarpCg>(x, disp, out, nullptr, nullptr, 0, nullptr, 0, B, C, H, W, st);
+        }
+    }
+    // the assembling variant keeps the `ref` loads in flight too: fewer channels per thread buy back the occupancy
+    switch (DV_TUNE("DV_WARP_ASM_CG", 4)) {
+        case 2: return warp_launch<true, 2>(x, disp, out, ref, diff_out, diff_bstride, copy_out, copy_bstride, B, C, H, W, st);
+        case 4: return warp_launch<true, 4>(x, disp, out, ref, diff_out, diff_bstride, copy_out, copy_bstride, B, C, H, W, st);
+        case 16: return warp_launch<true, 16>(x, disp, out, ref, diff_out, diff_bstride, copy_out, copy_bstride, B, C, H, W, st);
+        default: return warp_launch<true, 8>(x, disp, out, ref, diff_out, diff_bstride, copy_out, copy_bstride, B, C, H, W, st);
+    }
 }
 
 extern "C" int dv_warp_f32(const float *x, const float *disp, float *out, int64_t B, int64_t C, int64_t H, int64_t W,

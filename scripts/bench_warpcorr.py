@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, "/root/repo")
+import os; sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from diffuvolume_b200 import ops
 B, C, H, W = 8, 32, 384, 1248
 g = torch.Generator(device="cuda").manual_seed(0)
