@@ -189,7 +189,7 @@ static int warp_impl(const float *x, const float *disp, float *out, const float 
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!ref) {
-        switch (DV_TUNE("DV_WARP_CG", 8)) {
+        switch (DV_TUNE("DV_WARP_CG", 16)) {
             case 4: return warp_launch<false, 4>(x, disp, out, nullptr, nullptr, 0, nullptr, 0, B, C, H, W, st);
             case 8: return warp_launch<false, 8>(x, disp, out, nullptr, nullptr, 0, nullptr, 0, B, C, H, W, st);
             default: return warp_launch<false, kWarpCg>(x, disp, out, nullptr, nullptr, 0, nullptr, 0, B, C, H, W, st);
