@@ -508,7 +508,9 @@ def pcw_bytes(B, Hp=384, Wp=1248):
         "gwc_volume": sum((2 * 320 + 40 * Ds) * p for p, Ds in sc) * F4,
         "concat_volume": sum((2 * 12 + 24 * Ds) * p for p, Ds in sc) * F4,
         "filter": T * (2 * 32 * D * hw * F4 + 2 * D * hw * 8),                       # volume in/out, x_t in, n out
-        "softmax_regress": T * (2 * 192 * HW + HW) * F4,                              # logits in, probabilities + disparity out
+        # logits in, disparity out on every step; the probability volume is written on the last step only (the one ddim_sample
+        # returns) — on the other steps it is only reduced to the uncertainty, which re-reads the logits instead
+        "softmax_regress": (T * (192 * HW + HW) + 192 * HW) * F4,
         # warp (+ left - warped, + copy of left) and the +-24 volume, written into the refinement network's concat buffer:
         # right, disparity, left in; warped, difference, copy out; then left + warped in, 49 planes out
         "refine_input": T * ((32 + 1 + 32 + 3 * 32) + (2 * 32 + 49)) * HW * F4,
@@ -586,8 +588,8 @@ def extra_legs(args, dev, rank, world, barrier, dist):
     ms, kt = _timed(lambda t: ppath(**pin, timer=t), steps, warmup, barrier, dist, dev)
     leg = _leg_result("pcwnet", B, world, ms, kt, steps, pcw_bytes(B),
                       {"workload": "configs[2]: PCWNet+DiffuVolume KITTI12 384x1248: 4-scale gwc + concat(T); T=3 x {filter, "
-                                   "softmax/regression (+prob), refinement input (warp, left - warped, +-24 corr volume, assembled in the concat buffer), "
-                                   "uncertainty vote, DDIM step}; ensemble"})
+                                   "softmax/regression (+prob on the last step), refinement input (warp, left - warped, +-24 corr volume, assembled in the concat buffer), "
+                                   "uncertainty vote of the refined disparity from the logits, DDIM step}; ensemble"})
     if do_parity:
         one = pcw_inputs(1, dev, 777)
         got = ppath(**one, keep=True)

@@ -87,6 +87,7 @@ SIGNATURES = {
     "dv_softmax_regress_f32": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _F, _F, _P, _F, _I, _P, _P]),
     "dv_upsample_softmax_regress_f32": (_I, [_P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P, _P, _F, _F, _P, _F, _I, _P]),
     "dv_uncertainty_vote_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _F, _F, _P, _P, _P]),
+    "dv_softmax_uncertainty_vote_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _F, _F, _P, _P, _P, _P]),
     "dv_disparity_regression_f32": (_I, [_P, _P, _I64, _I64, _I64, _I64, _P]),
     "dv_q_sample": (_I, [_P, _I, _P, _I, _D, _D, _P, _I64, _P]),
     "dv_predict_noise_from_start": (_I, [_P, _I, _P, _I, _D, _D, _P, _I64, _P]),

@@ -63,7 +63,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
 template <int DPT, int V, int SL, int MINB, bool FULLD>
 __global__ void __launch_bounds__(SL * kSrLanes, MINB)
 softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__restrict__ disp_out,
-                       float *__restrict__ prob_out, const float *__restrict__ used, float *__restrict__ unc_out,
+                       float *__restrict__ prob_out, const float *__restrict__ used, const float *__restrict__ disp_ext,
+                       float *__restrict__ unc_out,
                        float *__restrict__ vote_out, float thr_dif, float thr_unc, float *__restrict__ ens_acc,
                        float ens_coef, int ens_init) {
     constexpr int kSrSlices = SL;   // disparity slices per CTA; thread (lane, slice) owns d = j*SL + slice
@@ -166,12 +167,16 @@ softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__r
     Vec<V> U;
 #pragma unroll
     for (int i = 0; i < V; ++i) U.v[i] = 0.0f;
+    // the disparity the uncertainty / vote are taken around: the regression itself, or an external map (PWCNet's refined
+    // disparity against the pre-refinement distribution, pwcnet_ddim.py:553-570)
+    Vec<V> dq = disp;
+    if (need_unc && disp_ext && live) dq = load_vec<V>(disp_ext + static_cast<int64_t>(b) * HW + pv * V);
     if (need_unc) {  // uniform across the block
 #pragma unroll
         for (int j = 0; j < DPT; ++j) {
             const float df = static_cast<float>(j * kSrSlices + slice);
 #pragma unroll
-            for (int i = 0; i < V; ++i) U.v[i] = fmaf(fabsf(disp.v[i] - df), x[j].v[i], U.v[i]);
+            for (int i = 0; i < V; ++i) U.v[i] = fmaf(fabsf(dq.v[i] - df), x[j].v[i], U.v[i]);
         }
         __syncthreads();  // red[0] is free again only after everyone has read the max
         red[0][slice][lane] = U;
@@ -194,11 +199,16 @@ softmax_regress_kernel(const float *__restrict__ cost, int D, int HW, float *__r
         if (disp_out) store_vec<V>(disp_out + o, disp);
         if (unc_out) store_vec<V>(unc_out + o, U);
         if (vote_out) {
-            const Vec<V> u0 = load_vec<V>(used + o);
             Vec<V> vt;
+            if (used) {
+                const Vec<V> u0 = load_vec<V>(used + o);
 #pragma unroll
-            for (int i = 0; i < V; ++i)
-                vt.v[i] = (fabsf(disp.v[i] - u0.v[i]) < thr_dif && U.v[i] < thr_unc) ? 1.0f : 0.0f;
+                for (int i = 0; i < V; ++i)
+                    vt.v[i] = (fabsf(dq.v[i] - u0.v[i]) < thr_dif && U.v[i] < thr_unc) ? 1.0f : 0.0f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) vt.v[i] = U.v[i] < thr_unc ? 1.0f : 0.0f;
+            }
             store_vec<V>(vote_out + o, vt);
         }
         if (ens_acc) {
@@ -239,8 +249,8 @@ template <int NJ, int NDS, int STAGES, int SPAN, int MINB, bool DYN, bool FULLD>
 __global__ void __launch_bounds__(SPAN / 4 * NDS + 32, MINB)
 softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int HW, int spans_per_b, int ntiles, int *ctr_arg, int slot,
                            float *__restrict__ disp_out, float *__restrict__ prob_out, const float *__restrict__ used,
-                           float *__restrict__ unc_out, float *__restrict__ vote_out, float thr_dif, float thr_unc,
-                           float *__restrict__ ens_acc, float ens_coef, int ens_init) {
+                           const float *__restrict__ disp_ext, float *__restrict__ unc_out, float *__restrict__ vote_out,
+                           float thr_dif, float thr_unc, float *__restrict__ ens_acc, float ens_coef, int ens_init) {
     constexpr int SQ = SPAN / 4, NCONS = SQ * NDS, NW = NCONS / 32;   // quads per span, consumer threads / warps
     extern __shared__ __align__(128) float smem[];              // [STAGES][D][SPAN]
     __shared__ float4 red[4][NW][SQ];
@@ -304,9 +314,10 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
         const int p = p0 + 4 * q;
         const bool live = p < HW;
         const int64_t o = static_cast<int64_t>(b) * HW + p;
-        float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = u4;
+        if (disp_ext && live) e4 = __ldg(reinterpret_cast<const float4 *>(disp_ext + o));   // every slice needs it
         if (fin && live) {   // issue the small map reads before waiting for the tile
-            if (vote_out) u4 = ldg_stream(reinterpret_cast<const float4 *>(used + o));
+            if (vote_out && used) u4 = ldg_stream(reinterpret_cast<const float4 *>(used + o));
             if (ens_acc && !ens_init) a4 = *reinterpret_cast<const float4 *>(ens_acc + o);
         }
         float4 x[NJ];
@@ -384,8 +395,9 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
                         make_float4(x[j].x * rS.x, x[j].y * rS.y, x[j].z * rS.z, x[j].w * rS.w);
         }
         float4 U = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 dq = disp_ext ? e4 : disp;   // the map the uncertainty / vote are taken around (see the register kernel)
         if (unc_out || vote_out) {   // uniform across the grid
-            const float4 t0 = make_float4(disp.x - dsf, disp.y - dsf, disp.z - dsf, disp.w - dsf);
+            const float4 t0 = make_float4(dq.x - dsf, dq.y - dsf, dq.z - dsf, dq.w - dsf);
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const float dj = static_cast<float>(NDS * j);
@@ -415,10 +427,11 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
             if (unc_out) *reinterpret_cast<float4 *>(unc_out + o) = U;
             if (vote_out) {
                 float4 vt;
-                vt.x = (fabsf(disp.x - u4.x) < thr_dif && U.x < thr_unc) ? 1.0f : 0.0f;
-                vt.y = (fabsf(disp.y - u4.y) < thr_dif && U.y < thr_unc) ? 1.0f : 0.0f;
-                vt.z = (fabsf(disp.z - u4.z) < thr_dif && U.z < thr_unc) ? 1.0f : 0.0f;
-                vt.w = (fabsf(disp.w - u4.w) < thr_dif && U.w < thr_unc) ? 1.0f : 0.0f;
+                const bool nu = used == nullptr;
+                vt.x = ((nu || fabsf(dq.x - u4.x) < thr_dif) && U.x < thr_unc) ? 1.0f : 0.0f;
+                vt.y = ((nu || fabsf(dq.y - u4.y) < thr_dif) && U.y < thr_unc) ? 1.0f : 0.0f;
+                vt.z = ((nu || fabsf(dq.z - u4.z) < thr_dif) && U.z < thr_unc) ? 1.0f : 0.0f;
+                vt.w = ((nu || fabsf(dq.w - u4.w) < thr_dif) && U.w < thr_unc) ? 1.0f : 0.0f;
                 *reinterpret_cast<float4 *>(vote_out + o) = vt;
             }
             if (ens_acc) {
@@ -432,7 +445,7 @@ softmax_regress_tma_kernel(const __grid_constant__ CUtensorMap tmap, int D, int 
 
 template <int NJ, int NDS, int STAGES, int SPAN, int MINB>
 static int launch_sr_tma(const float *cost, int B, int D, int HW, float *disp_out, float *prob_out, const float *used,
-                         float *unc_out, float *vote_out, float thr_dif, float thr_unc, float *ens_acc,
+                         const float *disp_ext, float *unc_out, float *vote_out, float thr_dif, float thr_unc, float *ens_acc,
                          float ens_coef, int ens_init, int *ctr, cudaStream_t st) {
     const size_t smem = sizeof(float) * STAGES * static_cast<size_t>(D) * SPAN;
     const int spans = (HW + SPAN - 1) / SPAN;
@@ -450,7 +463,7 @@ static int launch_sr_tma(const float *cost, int B, int D, int HW, float *disp_ou
             cudaSuccess)                                                                                               \
             return DV_ERR_LAUNCH;                                                                                      \
         kern<<<grid, SPAN / 4 * NDS + 32, smem, st>>>(tmap, D, HW, spans, static_cast<int>(ntiles), ctr, slot, disp_out,    \
-                                                      prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc,    \
+                                                      prob_out, used, disp_ext, unc_out, vote_out, thr_dif, thr_unc, ens_acc, \
                                                       ens_coef, ens_init);                                             \
     }
     if (D == NJ * NDS) DV_LAUNCH(true) else DV_LAUNCH(false)
@@ -461,9 +474,9 @@ static int launch_sr_tma(const float *cost, int B, int D, int HW, float *disp_ou
 // Any D: one thread per pixel, three passes over D (the re-reads hit L2).
 __global__ void softmax_regress_generic_kernel(const float *__restrict__ cost, int D, int HW,
                                                float *__restrict__ disp_out, float *__restrict__ prob_out,
-                                               const float *__restrict__ used, float *__restrict__ unc_out,
-                                               float *__restrict__ vote_out, float thr_dif, float thr_unc,
-                                               float *__restrict__ ens_acc, float ens_coef, int ens_init,
+                                               const float *__restrict__ used, const float *__restrict__ disp_ext,
+                                               float *__restrict__ unc_out, float *__restrict__ vote_out, float thr_dif,
+                                               float thr_unc, float *__restrict__ ens_acc, float ens_coef, int ens_init,
                                                int64_t total) {
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -478,17 +491,18 @@ __global__ void softmax_regress_generic_kernel(const float *__restrict__ cost, i
             Wd = fmaf(static_cast<float>(d), e, Wd);
         }
         const float rS = 1.0f / S, disp = Wd * rS;
+        const float dq = disp_ext ? disp_ext[idx] : disp;
         float U = 0.0f;
         if (prob_out || unc_out || vote_out) {
             for (int d = 0; d < D; ++d) {
                 const float pr = expf(cp[static_cast<int64_t>(d) * HW] - m) * rS;
                 if (prob_out) prob_out[b * D * HW + static_cast<int64_t>(d) * HW + p] = pr;
-                U = fmaf(fabsf(disp - static_cast<float>(d)), pr, U);
+                U = fmaf(fabsf(dq - static_cast<float>(d)), pr, U);
             }
         }
         if (disp_out) disp_out[idx] = disp;
         if (unc_out) unc_out[idx] = U;
-        if (vote_out) vote_out[idx] = (fabsf(disp - used[idx]) < thr_dif && U < thr_unc) ? 1.0f : 0.0f;
+        if (vote_out) vote_out[idx] = ((!used || fabsf(dq - used[idx]) < thr_dif) && U < thr_unc) ? 1.0f : 0.0f;
         if (ens_acc) ens_acc[idx] = fmaf(ens_coef, disp, ens_init ? 0.0f : ens_acc[idx]);
     }
 }
@@ -553,34 +567,31 @@ uncertainty_vote_kernel(const float *__restrict__ prob, const float *__restrict_
 
 template <int DPT, int V, int SL, int MINB>
 static void launch_sr(const float *cost, int B, int D, int HW, float *disp_out, float *prob_out, const float *used,
-                      float *unc_out, float *vote_out, float thr_dif, float thr_unc, float *ens_acc, float ens_coef,
+                      const float *disp_ext, float *unc_out, float *vote_out, float thr_dif, float thr_unc, float *ens_acc, float ens_coef,
                       int ens_init, cudaStream_t st) {
     const int pvs = (HW + V - 1) / V;
     dim3 grid((pvs + kSrLanes - 1) / kSrLanes, B);
     if (D == SL * DPT)
         softmax_regress_kernel<DPT, V, SL, MINB, true><<<grid, SL * kSrLanes, 0, st>>>(
-            cost, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init);
+            cost, D, HW, disp_out, prob_out, used, disp_ext, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init);
     else
         softmax_regress_kernel<DPT, V, SL, MINB, false><<<grid, SL * kSrLanes, 0, st>>>(
-            cost, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init);
+            cost, D, HW, disp_out, prob_out, used, disp_ext, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init);
 }
 
-}  // namespace dv
-
-extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, int64_t H, int64_t W, float *disp_out,
-                                      float *prob_out, const float *used, float *unc_out, float *vote_out,
-                                      float thr_dif, float thr_unc, float *ens_acc, float ens_coef, int ens_init,
-                                      void *tile_counters, void *stream) {
-    using namespace dv;
+static int softmax_regress_impl(const float *cost, int64_t B, int64_t D, int64_t H, int64_t W, float *disp_out,
+                                float *prob_out, const float *used, const float *disp_ext, float *unc_out, float *vote_out,
+                                float thr_dif, float thr_unc, float *ens_acc, float ens_coef, int ens_init,
+                                void *tile_counters, void *stream) {
     if (!cost) return DV_ERR_NULL;
-    if (vote_out && !used) return DV_ERR_NULL;
+    if (vote_out && !used && !disp_ext) return DV_ERR_NULL;
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return DV_ERR_BAD_SHAPE;
     const int64_t HW = H * W;
     if (HW > INT32_MAX || B > 65535 || D > INT32_MAX) return DV_ERR_BAD_SHAPE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto all_aligned = [&](uintptr_t mask) {
         auto ok = [mask](const void *p) { return !p || (reinterpret_cast<uintptr_t>(p) & mask) == 0; };
-        return ok(cost) && ok(disp_out) && ok(prob_out) && ok(used) && ok(unc_out) && ok(vote_out) && ok(ens_acc);
+        return ok(cost) && ok(disp_out) && ok(prob_out) && ok(used) && ok(disp_ext) && ok(unc_out) && ok(vote_out) && ok(ens_acc);
     };
     const bool vec4 = (HW % 4 == 0) && all_aligned(15);
     const bool vec2 = (HW % 2 == 0) && all_aligned(7);
@@ -588,7 +599,7 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
     const int variant = DV_TUNE("DV_SR_VARIANT", 4);
     if (vec4 && D <= 192 && DV_TUNE("DV_SR_TMA", 1) && static_cast<int64_t>((HW + 63) / 64) * B <= INT32_MAX) {
         int rc;
-#define DV_SR_TMA_ARGS cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, static_cast<int *>(tile_counters), st
+#define DV_SR_TMA_ARGS cost, B, D, HW, disp_out, prob_out, used, disp_ext, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, static_cast<int *>(tile_counters), st
         // thread = (quad of 16, slice of 8): 4 consumer warps per CTA, 2 CTAs per SM.  Measured at D = 192, B = 8
         // (gpurun_out/bench_sr3.log): 8 slices x 24 d per thread 0.496 ms (6.59 TB/s) vs 16 slices x 12 d 0.586 ms — half as
         // many partials to merge per pixel and half the per-tile overhead per element; 3 CTAs x 1 stage spills.
@@ -601,7 +612,7 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
         if (rc == DV_OK) return finish_launch();
         if (rc != DV_ERR_UNSUPPORTED) return rc;   // no tensor-map encoder: fall through to the register kernel
     }
-#define DV_SR_ARGS cost, B, D, HW, disp_out, prob_out, used, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, st
+#define DV_SR_ARGS cost, B, D, HW, disp_out, prob_out, used, disp_ext, unc_out, vote_out, thr_dif, thr_unc, ens_acc, ens_coef, ens_init, st
     if (D <= 48) {
         if (vec4) launch_sr<6, 4, 8, 4>(DV_SR_ARGS);
         else if (vec2) launch_sr<6, 2, 8, 4>(DV_SR_ARGS);
@@ -623,12 +634,31 @@ extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, i
         const int64_t blocks = (total + 255) / 256;
         const int grid = static_cast<int>(blocks < static_cast<int64_t>(num_sms()) * 32 ? blocks : static_cast<int64_t>(num_sms()) * 32);
         softmax_regress_generic_kernel<<<grid, 256, 0, st>>>(cost, static_cast<int>(D), static_cast<int>(HW), disp_out,
-                                                             prob_out, used, unc_out, vote_out, thr_dif, thr_unc,
+                                                             prob_out, used, disp_ext, unc_out, vote_out, thr_dif, thr_unc,
                                                              ens_acc, ens_coef, ens_init, total);
     }
 #undef DV_SR_ARGS
 #undef DV_SR
     return finish_launch();
+}
+
+}  // namespace dv
+
+extern "C" int dv_softmax_regress_f32(const float *cost, int64_t B, int64_t D, int64_t H, int64_t W, float *disp_out,
+                                      float *prob_out, const float *used, float *unc_out, float *vote_out,
+                                      float thr_dif, float thr_unc, float *ens_acc, float ens_coef, int ens_init,
+                                      void *tile_counters, void *stream) {
+    if (vote_out && !used) return DV_ERR_NULL;
+    return dv::softmax_regress_impl(cost, B, D, H, W, disp_out, prob_out, used, nullptr, unc_out, vote_out, thr_dif, thr_unc,
+                                    ens_acc, ens_coef, ens_init, tile_counters, stream);
+}
+
+extern "C" int dv_softmax_uncertainty_vote_f32(const float *cost, const float *disp, const float *used, int64_t B, int64_t D,
+                                               int64_t H, int64_t W, float thr_dif, float thr_unc, float *unc_out,
+                                               float *vote_out, void *tile_counters, void *stream) {
+    if (!disp || (!unc_out && !vote_out)) return DV_ERR_NULL;
+    return dv::softmax_regress_impl(cost, B, D, H, W, nullptr, nullptr, used, disp, unc_out, vote_out, thr_dif, thr_unc, nullptr,
+                                    0.0f, 0, tile_counters, stream);
 }
 
 extern "C" int dv_disparity_regression_f32(const float *x, float *out, int64_t B, int64_t D, int64_t H, int64_t W,

@@ -413,6 +413,26 @@ def uncertainty_vote(disp: torch.Tensor, prob: torch.Tensor, used: Optional[torc
     return (vote, unc) if return_unc else vote
 
 
+def softmax_uncertainty_vote(disp: torch.Tensor, cost: torch.Tensor, used: Optional[torch.Tensor], thr_dif: float,
+                             thr_unc: float, return_unc: bool = False):
+    """a11 from the logits — `uncertainty_vote(disp, softmax(cost, 1), ...)` without the probability volume: the softmax is
+    recomputed in registers from one read of `cost` (pwcnet_ddim.py:483 + :553-570)."""
+    B, D, H, W = cost.shape
+    _need_cuda(disp, cost, used)
+    cost = _f32c(cost, "cost")
+    disp = _f32c(disp.reshape(B, H, W), "disp")
+    if used is not None:
+        used = _f32c(used.reshape(B, H, W), "used")
+    vote = torch.empty((B, H, W), dtype=torch.float32, device=cost.device)
+    unc = torch.empty((B, H, W), dtype=torch.float32, device=cost.device) if return_unc else None
+    with torch.cuda.device(cost.device):
+        check(_lib.lib().dv_softmax_uncertainty_vote_f32(_ptr(cost), _ptr(disp), _ptr(used), B, D, H, W, float(thr_dif),
+                                                         float(thr_unc), _ptr(unc), _ptr(vote),
+                                                         _tile_counters(cost.device, 1), _stream(cost)),
+              "dv_softmax_uncertainty_vote_f32")
+    return (vote, unc) if return_unc else vote
+
+
 def disparity_regression(x: torch.Tensor, maxdisp: int, keepdim: bool = False) -> torch.Tensor:
     """a6 — SceneFlow/models/submodule.py:173-177 (keepdim=True: KITTI15/core/submodule.py:219-223)."""
     assert len(x.shape) == 4

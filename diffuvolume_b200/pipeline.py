@@ -229,14 +229,18 @@ class PcwHotPath:
     """BASELINE.json configs[2]: the kernel sequence PWCNet_ddim.forward (eval) + ddim_sample + model_predictions
     (KITTI12/models/pwcnet_ddim.py:604-625, :530-602, :466-528) issue outside their 2-D / 3-D convolutions, for a batch of
     pairs: 4-scale group-wise correlation volumes (D = 48/24/12/6) + concat volumes (variant T), then T = 3 x
-    {filter multiply on `combine` [B,32,48,h,w], softmax + regression over [B,192,H,W] with the probability volume kept
-    (model_predictions returns it), warp of the full-res right refinement features by the regressed disparity, the +-24
-    two-sided correlation volume, x_start / pred_noise, the uncertainty of the refined disparity against the kept
-    probabilities + renewal vote, fused DDIM step with cumulative re-noising}, ensemble.  The refinement network itself is a
+    {filter multiply on `combine` [B,32,48,h,w], softmax + regression over [B,192,H,W] (the probability volume is written on
+    the LAST step only — the one ddim_sample returns; on the other steps it is only ever reduced to an uncertainty, which
+    comes from a second read of the logits: `prob="every_step"` restores the reference's own materialisation), warp of the
+    full-res right refinement features by the regressed disparity, the +-24 two-sided correlation volume, x_start /
+    pred_noise, the uncertainty of the refined disparity against the pre-refinement distribution + renewal vote, fused DDIM
+    step with cumulative re-noising}, ensemble.  The refinement network itself is a
     convolution stack (out of scope): its output is stood in for by the regressed disparity."""
 
     def __init__(self, schedule: Optional[DdimSchedule] = None, num_groups: int = 40, maxdisp: int = 192,
-                 ensemble: Sequence[float] = PCW_ENSEMBLE):
+                 ensemble: Sequence[float] = PCW_ENSEMBLE, prob: str = "last_step"):
+        assert prob in ("last_step", "every_step")
+        self.prob_mode = prob
         self.sched = schedule or DdimSchedule(sampling_timesteps=3)
         self.G, self.maxdisp, self.D = num_groups, maxdisp, maxdisp // 4
         self.cof = tuple(ensemble)
@@ -277,9 +281,11 @@ class PcwHotPath:
             with tm("filter"):
                 vol_f, n = ops.volume_filter(combine, img, shifts[i], sched.scale, return_n=True)
             cost = costs[i if len(costs) > 1 else 0]
+            last = t_next < 0
+            want_prob = last or self.prob_mode == "every_step"
             with tm("softmax_regress"):
-                r = ops.softmax_regress(cost, return_prob=True)
-            disp, prob = r["disp"], r["prob"]
+                r = ops.softmax_regress(cost, return_prob=want_prob)
+            disp, prob = r["disp"], (r["prob"] if want_prob else None)
             # the refinement network's input assembled as the product does (sampler.pcw_model_predictions): warp, left - warped,
             # copy of left and the +-24 volume straight into the concat buffer — no subtraction / torch.cat passes
             Cf = feat_l_full.shape[1]
@@ -299,7 +305,8 @@ class PcwHotPath:
                 img = st["x_next"]
                 continue
             with tm("uncertainty_vote"):
-                vote = ops.uncertainty_vote(disp, prob, used, 1.0, 1.0)
+                vote = (ops.uncertainty_vote(disp, prob, used, 1.0, 1.0) if prob is not None
+                        else ops.softmax_uncertainty_vote(disp, cost, used, 1.0, 1.0))
             san, c, sigma = sched.update_coefficients(t, t_next)
             with tm("ddim_step"):
                 st = ops.ddim_step(disp=disp, xt=img, shift=shifts[i], scale=sched.scale, sqrt_recip=sched.sqrt_recip(t),

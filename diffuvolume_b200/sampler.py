@@ -351,7 +351,15 @@ def acvnet_forward(self, left, right):
 # PWCNet_ddim
 # ------------------------------------------------------------------------------------------------
 def pcw_model_predictions(self, volume, noise, t, features_left, features_right):
-    """PWCNet_ddim.model_predictions (pwcnet_ddim.py:466-528): returns (pred_noise, x_start, disp_finetune, pred3_volume).
+    """PWCNet_ddim.model_predictions (pwcnet_ddim.py:466-528), the reference's signature and return values."""
+    return _pcw_model_predictions_impl(self, volume, noise, t, features_left, features_right, want_prob=True)[:4]
+
+
+def _pcw_model_predictions_impl(self, volume, noise, t, features_left, features_right, want_prob):
+    """Returns (pred_noise, x_start, disp_finetune, pred3_volume or None, cost3 logits [B,maxdisp,H,W]).
+    want_prob=False is what pcw_ddim_sample uses on its non-final steps: there the probability volume is only ever reduced to
+    the uncertainty of the refined disparity (pwcnet_ddim.py:553-558), which `ops.softmax_uncertainty_vote` takes from the
+    logits — the 398 MB/pair write of pred3_volume and its read back never happen.
     Filter multiply :468-472, softmax + regression :483-484 (the probability volume IS returned here, so it is written
     once by the same kernel), warp + the +-24 correlation volume :493-494, x_start scatter :504-524 and pred_noise :526
     are the CUDA ops; the 3-D hourglasses, `dispupsample`, `refinenet3` and the two F.upsample calls are the reference's
@@ -366,8 +374,9 @@ def pcw_model_predictions(self, volume, noise, t, features_left, features_right)
     out3 = self.dres4(out2)
     cost3 = self.classif3(out3)
     cost3 = F.interpolate(cost3, [self.maxdisp, h * 4, w * 4], mode="trilinear", align_corners=True)
-    r = ops.softmax_regress(torch.squeeze(cost3, 1), return_prob=True)
-    pred3_volume = r["prob"]
+    cost3 = torch.squeeze(cost3, 1)
+    r = ops.softmax_regress(cost3, return_prob=want_prob)
+    pred3_volume = r["prob"] if want_prob else None
     pred3 = torch.unsqueeze(r["disp"], 1)
     refinenet_feature_left = F.interpolate(features_left["finetune_feature"], [h * 4, w * 4], mode="bilinear",
                                            align_corners=True)
@@ -392,7 +401,7 @@ def pcw_model_predictions(self, volume, noise, t, features_left, features_right)
                                      post_scale=0.25)
     x_start = ops.xstart_from_disp(disp_q, d, self.scale)
     pred_noise = ops.predict_noise_from_start(n, x_start, hb["sqrt_recip"][ti], hb["sqrt_recipm1"][ti])
-    return pred_noise, x_start, disp_finetune, pred3_volume
+    return pred_noise, x_start, disp_finetune, pred3_volume, cost3
 
 
 @torch.no_grad()
@@ -412,20 +421,31 @@ def pcw_ddim_sample(self, volume, used, asd, features_left, features_right):
     mask = torch.zeros((batch, h, w), dtype=torch.float32, device=dev)
     pred3_volume = None
     disp = None
+    # with our own model_predictions bound, the probability volume is materialised on the LAST step only (the one the method
+    # returns); a user-supplied model_predictions is called as is and its probability volume is used
+    ours = _is_ours(self, "model_predictions", pcw_model_predictions)
     for i, (time, time_next) in enumerate(pairs):
         time_cond = torch.full((batch,), time, device=dev, dtype=torch.long)
-        pred_noise, x_start, disp, pred3_volume = self.model_predictions(volume, img, time_cond, features_left,
-                                                                         features_right)
+        last = time_next < 0
+        cost3 = None
+        if ours:
+            pred_noise, x_start, disp, pred3_volume, cost3 = _pcw_model_predictions_impl(
+                self, volume, img, time_cond, features_left, features_right, want_prob=last)
+        else:
+            pred_noise, x_start, disp, pred3_volume = self.model_predictions(volume, img, time_cond, features_left,
+                                                                             features_right)
         disp = disp.float().contiguous()
         disps.append(disp)
-        last = time_next < 0
         if last:
             img = x_start
             continue
         vote = None
         if self.renewal:
             # uncertainty of the REFINED disparity against the pre-refinement distribution (pwcnet_ddim.py:553-558)
-            vote = ops.uncertainty_vote(disp, pred3_volume, used, 1.0, 1.0)
+            if pred3_volume is None:
+                vote = ops.softmax_uncertainty_vote(disp, cost3, used, 1.0, 1.0)
+            else:
+                vote = ops.uncertainty_vote(disp, pred3_volume, used, 1.0, 1.0)
         san, c, sigma = _update_coefficients(self, time, time_next)
         noise = torch.randn_like(img)
         torch.randint(time, time + 1, (1,), device=dev)

@@ -162,6 +162,15 @@ int dv_uncertainty_vote_f32(const float *prob, const float *disp, const float *u
                             int64_t B, int64_t D, int64_t H, int64_t W, float thr_dif, float thr_unc,
                             float *unc_out, float *vote_out, void *stream);
 
+/* ---- a11 from the LOGITS: the same uncertainty + vote without a probability volume in HBM
+ *          (KITTI12/models/pwcnet_ddim.py:483 F.softmax + :553-570: inside ddim_sample the [B,192,H,W] softmax is only ever
+ *          consumed by this reduction, so the sampler keeps the logits and the softmax is recomputed in registers:
+ *          the 398 MB/pair write of pred3_volume and its read back are replaced by one read of the logits)
+ * unc[b,p] = sum_d |disp[b,p] - d| * softmax_d(cost)[b,d,p];  vote as dv_uncertainty_vote_f32.  tile_counters as above. */
+int dv_softmax_uncertainty_vote_f32(const float *cost, const float *disp, const float *used,
+                                    int64_t B, int64_t D, int64_t H, int64_t W, float thr_dif, float thr_unc,
+                                    float *unc_out, float *vote_out, void *tile_counters, void *stream);
+
 /* ---- a6 alone: disparity_regression on an already-normalised volume
  *          (SceneFlow/models/submodule.py:173-177)  out[b,p] = sum_d d * x[b,d,p]              */
 int dv_disparity_regression_f32(const float *x, float *out,

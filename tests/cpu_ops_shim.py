@@ -167,6 +167,11 @@ def uncertainty_vote(disp, prob, used, thr_dif, thr_unc, return_unc=False):
     return (vote, _t(unc)) if return_unc else vote
 
 
+def softmax_uncertainty_vote(disp, cost, used, thr_dif, thr_unc, return_unc=False):
+    _, prob = O.softmax_regress(_np(cost), cost.shape[1])
+    return uncertainty_vote(disp, _t(prob), used, thr_dif, thr_unc, return_unc)
+
+
 def warp(x, disp):
     return _t(O.warp(_np(x), _np(disp)))
 

@@ -141,6 +141,38 @@ def test_uncertainty_vote_matches_oracle():
     assert np.array_equal(vote.cpu().numpy()[~near], want[~near])
 
 
+@pytest.mark.parametrize("shape", [(2, 192, 12, 20), (1, 192, 7, 9), (2, 48, 6, 10), (1, 96, 5, 6), (1, 200, 3, 5)])
+def test_softmax_uncertainty_vote_from_logits_matches_oracle(shape):
+    """dv_softmax_uncertainty_vote_f32: the uncertainty / vote of an EXTERNAL disparity against softmax(cost) taken straight
+    from the logits (pwcnet_ddim.py:483 + :553-570) — every kernel path (tensor-map, register, generic D > 192, odd H*W),
+    with and without `used`, and equal to the two-pass form through a materialised probability volume."""
+    from diffuvolume_b200 import ops
+    B, D, H, W = shape
+    cost = synth.normal(shape, 15) * np.float32(4)
+    disp_o, prob_o = O.softmax_regress(cost, D)
+    refined = disp_o + synth.normal((B, H, W), 16) * np.float32(0.7)
+    used = refined + (synth.uniform((B, H, W), 17, dtype=np.float32) - np.float32(0.5)) * np.float32(3)
+    unc_o = O.uncertainty(refined, prob_o)
+    thr = float(np.median(unc_o))
+    vote, unc = ops.softmax_uncertainty_vote(cu(refined), cu(cost), cu(used), 1.0, thr, return_unc=True)
+    np.testing.assert_allclose(unc.cpu().numpy(), unc_o, atol=1e-3)
+    want = O.renewal_vote(refined, used, unc_o, 1.0, thr)
+    near = (np.abs(np.abs(refined - used) - 1.0) < 1e-3) | (np.abs(unc_o - thr) < 1e-3)
+    assert np.array_equal(vote.cpu().numpy()[~near], want[~near])
+    # without `used` the vote is the uncertainty test alone
+    v2 = ops.softmax_uncertainty_vote(cu(refined), cu(cost), None, 1.0, thr).cpu().numpy()
+    near2 = np.abs(unc_o - thr) < 1e-3
+    assert np.array_equal(v2[~near2], (unc_o < thr).astype(np.float32)[~near2])
+    # two-pass form: softmax_regress(return_prob) + uncertainty_vote
+    prob = ops.softmax_regress(cu(cost), return_prob=True)["prob"]
+    _, unc2 = ops.uncertainty_vote(cu(refined), prob, cu(used), 1.0, thr, return_unc=True)
+    assert float((unc - unc2).abs().max()) < 1e-4
+    # the regression's own outputs are untouched by the external-disparity plumbing
+    r = ops.softmax_regress(cu(cost), used=cu(used), vote_thresholds=(1.0, thr), want_unc=True)
+    np.testing.assert_allclose(r["disp"].cpu().numpy(), disp_o, atol=2e-4)
+    np.testing.assert_allclose(r["unc"].cpu().numpy(), O.uncertainty(disp_o, prob_o), atol=1e-3)
+
+
 @pytest.mark.gpu
 def test_hot_path_cuda_graph_replay_matches_eager():
     """The whole ACV hot path captured in a CUDA graph: replays are bit-identical to eager calls, also after the
