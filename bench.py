@@ -677,7 +677,16 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
         for k in lists:
             d[k] = [torch.empty_like(t) for t in inp[k]]
         sets.append(d)
-    cost_bufs = [torch.empty_like(inp["costs"][0]) for _ in range(2)]   # double buffer for the per-step cost tensors
+    # the T cost tensors of a step are inputs of that step like everything else: both device-side sets hold all T of them and
+    # they are prefetched on the copy streams with the rest (round 1 copied each one on the compute stream right before its
+    # DDIM iteration, which serialised 1/4 of the H2D bytes with the kernels).  The full-resolution logits boundary keeps the
+    # two-buffer streaming form when T x 2 sets would not fit beside the working set (3.2 GB per tensor at B = 8).
+    cost_bytes = inp["costs"][0].numel() * 4
+    prefetch_costs = 2 * T_STEPS * cost_bytes < 24 * (1 << 30)
+    if prefetch_costs:
+        for d in sets:
+            d["costs"] = [torch.empty_like(inp["costs"][0]) for _ in range(T_STEPS)]
+    cost_bufs = [] if prefetch_costs else [torch.empty_like(inp["costs"][0]) for _ in range(2)]
     copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.e2e_copy_streams))]
     ready = [[torch.cuda.Event() for _ in copy_streams] for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
@@ -695,6 +704,9 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
     def prefetch(i):
         d = sets[i % 2]
         jobs = [(d[k], host[k]) for k in names] + [(dd, ss) for k in lists for dd, ss in zip(d[k], host[k])]
+        if prefetch_costs:
+            jobs += [(dd, host["costs"][0]) for dd in d["costs"]]
+        jobs.sort(key=lambda j: -j[0].numel())            # big tensors first, dealt round-robin to the copy streams
         for si, st in enumerate(copy_streams):
             with torch.cuda.stream(st):
                 st.wait_event(consumed[i % 2])             # the step that last read this set has finished
@@ -720,7 +732,8 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
         for e in ready[i % 2]:
             cur.wait_event(e)
         sn, rn_ = draw_noise() if device_noise else (d["step_noises"], d["renoises"])
-        out = path(**{k: d[k] for k in names}, costs=stage_logits, shifts=d["shifts"], step_noises=sn, renoises=rn_)
+        out = path(**{k: d[k] for k in names}, costs=d["costs"] if prefetch_costs else stage_logits, shifts=d["shifts"],
+                   step_noises=sn, renoises=rn_)
         consumed[i % 2].record(cur)
         pred_host.copy_(out["pred"], non_blocking=True)
 
@@ -753,7 +766,9 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
             "h2d_GBs_per_gpu": round(h2d * steps / 1e9 / (ms / 1e3), 1),
             "noise": "drawn on the device inside the timed region, reference order/dtypes (acv_ddim.py:310,354-360)"
                      if device_noise else "pre-drawn on the host and copied with the inputs",
-            "copy_streams": len(copy_streams), "host_placement_rank0": placement,
+            "copy_streams": len(copy_streams), "cost_tensors": "prefetched with the step's other inputs" if prefetch_costs
+            else "streamed on the compute stream, one DDIM iteration ahead (2 device buffers)",
+            "host_placement_rank0": placement,
             "note": f"pinned host inputs incl. the T=5 per-step {list(host['costs'][0].shape)} cost tensors; PCIe-bound; "
                     "H2D of step i+1 overlapped with the compute of step i (copy streams + events)"}
 

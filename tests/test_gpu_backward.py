@@ -240,3 +240,33 @@ def test_warp_backward_vs_float64_cpu_autograd_and_partial_needs():
     assert gd is None and torch.allclose(gx, a1.grad, rtol=1e-5, atol=1e-6)
     gx, gd = ops.warp_bwd(gt, a1.detach(), d1.detach(), need_x=False, need_disp=True)
     assert gx is None and torch.allclose(gd, d1.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_ring_kernels_are_run_to_run_deterministic():
+    """The shared-memory rings (K-chunked two-sided forward: mbarrier full/empty; gwc backward: cp.async + __syncthreads;
+    patch-chain stream: cp.async + __syncwarp) re-use their slots many times per CTA.  compute-sanitizer's racecheck does not
+    model mbarrier release/acquire pairs (it reports the same producer/consumer pattern in every such kernel), so slot re-use
+    is also pinned the blunt way: 40 back-to-back launches under a concurrent memory-bound stream must be bit-identical."""
+    from diffuvolume_b200 import ops
+    g = torch.Generator(device="cuda"); g.manual_seed(17)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")
+    fl, fr = rn(2, 32, 96, 312), rn(2, 32, 96, 312)
+    gv = rn(2, 1, 49, 96, 312)
+    gl, gr, gg = rn(2, 64, 27, 240), rn(2, 64, 27, 240), rn(2, 8, 48, 27, 240)
+    vol, wp, wl = rn(1, 40, 4, 54, 240), rn(40, 9), rn(40, 9)
+    noise = torch.empty(64 << 20, device="cuda")
+    side = torch.cuda.Stream()
+    ref = None
+    for it in range(40):
+        with torch.cuda.stream(side):
+            noise.normal_()                                   # keeps HBM and the SMs busy from another stream
+        out = (ops.corr_volume_2sided(fl, fr, 24, 1),
+               *ops.gwc_volume_bwd(gv, fl, fr, 1, two_sided_maxdisp=24),
+               *ops.gwc_volume_bwd(gg, gl, gr, 8),
+               ops.acv_patch_volume(vol, wp, wl[:8], wl[8:24], wl[24:]))
+        if ref is None:
+            ref = [t.clone() for t in out]
+        else:
+            for a, b in zip(out, ref):
+                assert torch.equal(a, b), it
+    torch.cuda.synchronize()
