@@ -270,3 +270,49 @@ def test_ring_kernels_are_run_to_run_deterministic():
             for a, b in zip(out, ref):
                 assert torch.equal(a, b), it
     torch.cuda.synchronize()
+
+
+def test_full_size_adjoint_identities():
+    """Size-independent property at BASELINE.json's full sizes: the volume ops are bilinear in (ref, tgt) and warp is linear
+    in x, so for any cotangent G   <op(ref, tgt), G> == <ref, d_ref> == <tgt, d_tgt>   (and <warp(x, d), G> == <x, d_x>).
+    Forward and backward are DIFFERENT kernels (streaming producers vs the cp.async ring / scatter-add), so the identity
+    cross-checks them where the fp64 CPU autograd reference would take minutes."""
+    from diffuvolume_b200 import ops
+    g = torch.Generator(device="cuda"); g.manual_seed(23)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")
+    dot = lambda a, b: float((a.double() * b.double()).sum())
+
+    def close(a, b, c=None, tol=2e-5):
+        ref_mag = max(abs(a), 1e-30)
+        assert abs(a - b) / ref_mag < tol, (a, b)
+        if c is not None:
+            assert abs(a - c) / ref_mag < tol, (a, c)
+
+    # configs[1]: gwc volume, one 540x960 pair at 1/4 resolution, C = 320, G = 40, D = 48
+    fl, fr = rn(1, 320, 135, 240), rn(1, 320, 135, 240)
+    G = rn(1, 40, 48, 135, 240)
+    v = ops.gwc_volume(fl, fr, 48, 40)
+    gl, gr = ops.gwc_volume_bwd(G, fl, fr, 40)
+    close(dot(v, G), dot(fl, gl), dot(fr, gr))
+    del v, G, gl, gr, fl, fr
+    # configs[2]: the +-24 two-sided volume at 384x1248, C = 32 (negative-shift quirk included)
+    fl, fr = rn(1, 32, 384, 1248), rn(1, 32, 384, 1248)
+    G = rn(1, 1, 49, 384, 1248)
+    v = ops.corr_volume_2sided(fl, fr, 24, 1)
+    gl, gr = ops.gwc_volume_bwd(G, fl, fr, 1, two_sided_maxdisp=24)
+    close(dot(v, G), dot(fl, gl), dot(fr, gr))
+    # warp at 384x1248: linear in the features
+    disp = torch.rand(1, 1, 384, 1248, generator=g, device="cuda") * 150.0 - 3.0
+    Gw = rn(1, 32, 384, 1248)
+    w = ops.warp(fr, disp)
+    gx, _ = ops.warp_bwd(Gw, fr, disp, need_x=True, need_disp=False)
+    close(dot(w, Gw), dot(fr, gx))
+    # the fused ACV volume (concat x softmax(att) x n): linear in each concat feature map
+    cl, cr = rn(1, 32, 135, 240), rn(1, 32, 135, 240)
+    att = rn(1, 1, 48, 135, 240)
+    from diffuvolume_b200 import functional as Fn
+    a1, a2 = cl.clone().requires_grad_(True), cr.clone().requires_grad_(True)
+    vol = Fn.acv_attention_volume(a1, a2, att, 48)
+    Gv = rn(*vol.shape)
+    vol.backward(Gv)
+    close(dot(vol.detach(), Gv), dot(cl, a1.grad) + dot(cr, a2.grad))
