@@ -597,9 +597,13 @@ def extra_legs(args, dev, rank, world, barrier, dist):
         ams, (pred, (x_last, mask, prob, corr, vols)) = _aten_time(lambda: P.pcw_hot_path_pair(**one, sched=sched))
         err = (got["pred"] - pred).abs()
         leg["parity"] = {"epe_px": float(err.mean()), "max_err_px": float(err.max()),
-                         # warp + the +-24 volume on the SAME disparity map (ours): the chained value also carries the
-                         # 1e-5 px disparity difference through warp's 0.999 validity threshold (a handful of pixels flip)
-                         "corr_volume_max_rel_err": _relerr(got["corr"], torch.squeeze(P.corr_volume_2sided(
+                         # warp + the +-24 volume on the SAME disparity map (ours), against the port run on the HOST: ATen's CUDA
+                         # grid_sample contracts its un-normalisation into an FMA, so its sampling positions differ from the
+                         # reference's CPU arithmetic (which warp.cu reproduces) by one ulp — 3e-5 in a tap weight at W = 1248 —
+                         # and a pixel at the 0.999 validity threshold can flip; that difference is reported separately
+                         "corr_volume_max_rel_err": _relerr(got["corr"].cpu(), torch.squeeze(P.corr_volume_2sided(
+                             one["feat_l_full"].cpu(), P.warp(one["feat_r_full"].cpu(), got["disp_last"].unsqueeze(1).cpu()), 24, 1), 1)),
+                         "corr_volume_max_rel_err_vs_aten_cuda_grid_sample": _relerr(got["corr"], torch.squeeze(P.corr_volume_2sided(
                              one["feat_l_full"], P.warp(one["feat_r_full"], got["disp_last"].unsqueeze(1)), 24, 1), 1)),
                          "corr_volume_chained_frac_within_1e-4": float(((got["corr"] - corr).abs()
                                                                         <= 1e-4 * corr.abs().max()).float().mean()),

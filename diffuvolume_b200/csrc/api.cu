@@ -5,7 +5,7 @@ namespace dv {
 std::atomic<int64_t> g_launch_count{0};
 }
 
-extern "C" int dv_version(void) { return 10000 * 0 + 100 * 3 + 0; }   // 0.3.0: caller-owned tile counters; 0.2.0: packed geo pyramid, f4, bf16 volumes
+extern "C" int dv_version(void) { return 10000 * 0 + 100 * 4 + 0; }   // 0.4.0: warp backward, fused backward passes, refinement-input assembly, softmax uncertainty vote, tcgen05 all-pairs; 0.3.0: caller-owned tile counters; 0.2.0: packed geo pyramid, f4, bf16 volumes
 
 extern "C" int dv_built_for_sm(void) { return 100; }
 
