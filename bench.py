@@ -545,7 +545,8 @@ def igev_bytes(B, iters=32, Hp=384, Wp=1248):
         "softmax_regress": (D + 1) * hw * F4,
         "geo_init": (2 * 96 * hw + 1.5 * hw * w + 2.5 * 8 * D * hw) * F4,           # all-pairs corr (+ pooled level), geo pack
         "filter_factor": T * D * hw * (8 + 4),
-        "geo_filter": T * (3 * 1.5 * 8 * D * hw * F4 + look),                        # pyramid in/out + noise, then the lookup
+        # packed pyramid (two levels = 1.5 x [8, D] per pixel) in and out, the raw noise rows once, then the step's first lookup
+        "geo_filter": T * (2 * 1.5 * 8 * D * hw * F4 + D * hw * F4 + look),
         "geo_lookup": T * (iters - 1) * look,
         "context_upsample": T * (10 * HW + hw) * F4,
         "fallback": T * 3 * HW * F4,

@@ -448,11 +448,60 @@ struct GeoFilterArgs {
     float *out[4];
     const float *noisy;
     int C, D, levels;
+    int fast;      // every level takes the vector path (geo_filter_level)
     int64_t N;
 };
+// Level-LVL noise of flat entry nj = n * D_l + j when D % 2^LVL == 0: the raw values [nj 2^LVL, (nj + 1) 2^LVL) reduced by the
+// same pairwise tree as noise_at — but inlined (noise_at is recursive, i.e. a CALL per element, and a call between two
+// loads keeps the second one from being issued before the first returns).
+template <int LVL>
+__device__ __forceinline__ float noise_flat(const float *__restrict__ p) {
+    if constexpr (LVL == 0) {
+        return __ldg(p);
+    } else {
+        return __fadd_rn(noise_flat<LVL - 1>(p), noise_flat<LVL - 1>(p + (1 << (LVL - 1)))) / 2.0f;
+    }
+}
+
+// Vector path of the filter (C % 4 == 0, D % 2^LVL == 0, < 2^31 float4 per level): a CTA owns a compact tile of 4 x 256
+// float4, every thread issues its four volume loads and four noise gathers before the first multiply (the one-load loop
+// below ran at 94 % occupancy with 25 long-scoreboard stall cycles per issue: 32 KB in flight per SM), no index divisions.
+template <int LVL>
+__device__ __forceinline__ void geo_filter_level(const GeoFilterArgs &a) {
+    const float4 *in = reinterpret_cast<const float4 *>(pick4(a.in, LVL));
+    float4 *out = reinterpret_cast<float4 *>(pick4w(a.out, LVL));
+    const unsigned c4 = static_cast<unsigned>(a.C / 4);
+    const unsigned total4 = static_cast<unsigned>(a.N * (a.D >> LVL) * c4);
+    for (unsigned q0 = blockIdx.x * 1024u + threadIdx.x; q0 < total4; q0 += gridDim.x * 1024u) {
+        float4 v[4];
+        float nz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned q = q0 + 256u * u;
+            if (q < total4) {
+                v[u] = __ldg(in + q);
+                nz[u] = noise_flat<LVL>(a.noisy + (static_cast<int64_t>(q / c4) << LVL));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned q = q0 + 256u * u;
+            if (q < total4)
+                out[q] = make_float4(__fmul_rn(v[u].x, nz[u]), __fmul_rn(v[u].y, nz[u]), __fmul_rn(v[u].z, nz[u]), __fmul_rn(v[u].w, nz[u]));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 geo_filter_packed_kernel(const GeoFilterArgs a) {
     const int lvl = blockIdx.y;
+    if (a.fast) {
+        if (lvl == 0) geo_filter_level<0>(a);
+        else if (lvl == 1) geo_filter_level<1>(a);
+        else if (lvl == 2) geo_filter_level<2>(a);
+        else geo_filter_level<3>(a);
+        return;
+    }
     const int Dl = a.D >> lvl;
     const float *in = pick4(a.in, lvl);
     float *out = pick4w(a.out, lvl);
@@ -881,8 +930,13 @@ extern "C" int dv_geo_filter_packed_f32(const float *const *rows_in, const float
     }
     a.noisy = noisy; a.C = static_cast<int>(C); a.D = static_cast<int>(D); a.levels = num_levels; a.N = N;
     const int64_t work = (N * D * C + 3) / 4;
-    const int64_t blocks = (work + 255) / 256;
-    const unsigned gx = static_cast<unsigned>(blocks < static_cast<int64_t>(num_sms()) * 16 ? blocks : static_cast<int64_t>(num_sms()) * 16);
+    bool fast = C % 4 == 0 && D % (1 << (num_levels - 1)) == 0 && work < 0x7fffffffLL && aligned16(noisy) &&
+                DV_TUNE("DV_GEO_FILTER_FAST", 1);
+    for (int i = 0; i < num_levels; ++i) fast = fast && aligned16(a.in[i]) && aligned16(a.out[i]);
+    a.fast = fast ? 1 : 0;
+    const int64_t blocks = fast ? (work + 1023) / 1024 : (work + 255) / 256;
+    const int64_t cap = fast ? 0x7fffffffLL : static_cast<int64_t>(num_sms()) * 16;
+    const unsigned gx = static_cast<unsigned>(blocks < cap ? blocks : cap);
     geo_filter_packed_kernel<<<dim3(gx, static_cast<unsigned>(num_levels)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return finish_launch();
 }
