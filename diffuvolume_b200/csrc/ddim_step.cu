@@ -269,6 +269,30 @@ struct EnsembleArgs {
     float cof[8];
     int n_maps;
 };
+// 128-bit path (n % 4 == 0, every map and `out` 16-byte aligned): all n_maps loads of a thread are issued before the first
+// product (the scalar loop below has one dependent load per term: 1.8 TB/s on 60-120 MB of maps); same products, same order.
+__global__ void __launch_bounds__(256)
+ensemble_vec4_kernel(const EnsembleArgs a, float *__restrict__ out, int64_t n4) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < a.n_maps) v[k] = ldg_stream(reinterpret_cast<const float4 *>(a.maps[k]) + i);
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < a.n_maps) {
+                acc.x = __fadd_rn(acc.x, __fmul_rn(v[k].x, a.cof[k]));
+                acc.y = __fadd_rn(acc.y, __fmul_rn(v[k].y, a.cof[k]));
+                acc.z = __fadd_rn(acc.z, __fmul_rn(v[k].z, a.cof[k]));
+                acc.w = __fadd_rn(acc.w, __fmul_rn(v[k].w, a.cof[k]));
+            }
+        }
+        reinterpret_cast<float4 *>(out)[i] = acc;
+    }
+}
+
 __global__ void ensemble_kernel(const EnsembleArgs a, float *__restrict__ out, int64_t n) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -417,6 +441,9 @@ extern "C" int dv_ensemble_f32(const float *const *maps, const float *cof, int n
         a.maps[k] = maps[k];
         a.cof[k] = cof[k];
     }
-    ensemble_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, out, n);
+    bool vec = n % 4 == 0 && aligned16(out);
+    for (int k = 0; k < n_maps; ++k) vec = vec && aligned16(maps[k]);
+    if (vec) ensemble_vec4_kernel<<<ew_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, out, n / 4);
+    else ensemble_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, out, n);
     return finish_launch();
 }
