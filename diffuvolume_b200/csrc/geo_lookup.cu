@@ -561,10 +561,20 @@ __device__ __forceinline__ float grid_coord_rcp(float x, float wm1, float rcp) {
 // packed pyramid once per timestep (geo_filter_packed_kernel) — the 32 GRU iterations of a step share one noise.  A tap whose
 // own floor() disagrees with the window position (possible only through rounding at exact integers) takes a
 // direct-load slow path with the same arithmetic.
-template <int C4, int R, int MINB>
+// COOP: the window gather is done by the WARP, not by the pixel's own lanes.  In the direct form one LDG.128 instruction
+// touches 16 pixels x one 32-byte sector each — 16 separate 32-byte requests to L2 — although the K hypothesis vectors of a
+// pixel are one contiguous run of K*C4 16-byte chunks.  Here consecutive lanes copy consecutive chunks of the same run
+// (lane -> (pixel, chunk) = divmod(i*32 + lane, K*C4); the pixel's window origin comes by shuffle from its owner lane) with
+// LDGSTS into shared memory, so a run arrives as 3-4 full 128-byte lines; each thread then reads its own chunks back
+// (pixel stride 22 chunks: conflict-free for a quarter warp).  Diagnostic builds had shown the gather half of this kernel
+// moving its bytes at only 3.2 TB/s.  0.086 -> 0.078 ms at B = 8, 96x312 with 8 CTAs/SM.  (The same treatment of the
+// 40-byte correlation windows — 4 chunks per pixel — measured slower, 0.082 ms, and was dropped.)
+template <int C4, int R, int MINB, bool COOP = false>
 __global__ void __launch_bounds__(128, MINB)
 geo_lookup_window_kernel(const GeoLookupPackedArgs a) {
     constexpr int TAPS = 2 * R + 1, K = TAPS + 1, CC = 4 * C4, PIX = 128 / C4;
+    constexpr int RUN = K * C4, PSTRIDE = RUN + 2;        // chunks per pixel run / per pixel slot in shared memory
+    extern __shared__ __align__(16) float4 win[];         // COOP only: [PIX][PSTRIDE]
     const int lvl = blockIdx.y;
     const int Dl = a.D >> lvl, Wl = a.W2 >> lvl;
     const int64_t n0 = blockIdx.x * static_cast<int64_t>(PIX);
@@ -602,16 +612,37 @@ geo_lookup_window_kernel(const GeoLookupPackedArgs a) {
         w1 = __fsub_rn(jx, fj);
     };
     // window fetch: hypothesis i00 + k, clamped (out-of-range ones are never blended)
-    float4 hyp[K];
+    float4 hyp[COOP ? 1 : K];
     int i00;
     {
         float w0, w1;
         geo_tap(0, i00, w0, w1);
     }
+    if (COOP) {
+        static_assert(!COOP || (32 % C4 == 0), "whole pixels per warp");
+        constexpr int PPW = 32 / C4;                      // pixels per warp
+        const int lane = threadIdx.x & 31, wbase = (threadIdx.x >> 5) * PPW;      // first pixel slot of this warp
+        const float *glvl = pick4(a.geo, lvl);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int i = min(max(i00 + k, 0), Dl - 1);
-        hyp[k] = __ldg(grow + static_cast<int64_t>(i) * C4);
+        for (int i = 0; i < (PPW * RUN + 31) / 32; ++i) {
+            const int e = i * 32 + lane;
+            const int pl = min(e / RUN, PPW - 1), ch = e - (e / RUN) * RUN;       // pixel of the warp, chunk of its run
+            const int org = __shfl_sync(0xffffffffu, i00, pl * C4);               // that pixel's window origin
+            const long long nn = __shfl_sync(0xffffffffu, static_cast<long long>(n), pl * C4);
+            if (e < PPW * RUN) {
+                const int hy = min(max(org + ch / C4, 0), Dl - 1);
+                const float4 *src = reinterpret_cast<const float4 *>(glvl + nn * static_cast<int64_t>(CC) * Dl) + hy * C4 + (ch % C4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&win[(wbase + pl) * PSTRIDE + ch])), "l"(src)
+                             : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = min(max(i00 + k, 0), Dl - 1);
+            hyp[k] = __ldg(grow + static_cast<int64_t>(i) * C4);
+        }
     }
     // corr taps owned by this lane: t % C4 == sub
     float cv0[TAPS], cv1[TAPS];
@@ -625,7 +656,13 @@ geo_lookup_window_kernel(const GeoLookupPackedArgs a) {
             cv1[t] = __ldg(crow + min(max(j0 + 1, 0), Wl - 1));
         }
     }
+    if (COOP) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();                                      // the chunks of a pixel were copied by other lanes of the warp
+    }
     if (!valid) return;
+    const float4 *mine = win + (threadIdx.x / C4) * PSTRIDE + sub;
+    float4 vnext = COOP ? mine[0] : hyp[0];
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) {
         int i0;
@@ -633,7 +670,8 @@ geo_lookup_window_kernel(const GeoLookupPackedArgs a) {
         geo_tap(t, i0, gw0, gw1);
         const int i1 = i0 + 1;
         const bool in0 = i0 >= 0 && i0 < Dl, in1 = i1 >= 0 && i1 < Dl;
-        float4 v0 = hyp[t], v1 = hyp[t + 1];
+        float4 v0 = vnext, v1 = COOP ? mine[(t + 1) * C4] : hyp[COOP ? 0 : t + 1];
+        vnext = v1;
         if (i0 != i00 + t) {  // rounding at an exact integer moved this tap off the window grid
             v0 = __ldg(grow + static_cast<int64_t>(min(max(i0, 0), Dl - 1)) * C4);
             v1 = __ldg(grow + static_cast<int64_t>(min(max(i1, 0), Dl - 1)) * C4);
@@ -905,7 +943,12 @@ extern "C" int dv_geo_lookup_packed_f32(const float *const *geo_pyr, const float
         const size_t smem = 0;
         const dim3 wgrid(static_cast<unsigned>(wblocks), static_cast<unsigned>(num_levels));
         const int minb = DV_TUNE("DV_GEO_MINB", 6);
-        if (minb == 4) geo_lookup_window_kernel<2, 4, 4><<<wgrid, 128, smem, st>>>(a);
+        const int coop = DV_TUNE("DV_GEO_COOP", 8);
+        const size_t csm = sizeof(float4) * 64 * (10 * 2 + 2);
+        if (coop == 8) geo_lookup_window_kernel<2, 4, 8, true><<<wgrid, 128, csm, st>>>(a);
+        else if (coop == 6) geo_lookup_window_kernel<2, 4, 6, true><<<wgrid, 128, csm, st>>>(a);
+        else if (coop == 10) geo_lookup_window_kernel<2, 4, 10, true><<<wgrid, 128, csm, st>>>(a);
+        else if (minb == 4) geo_lookup_window_kernel<2, 4, 4><<<wgrid, 128, smem, st>>>(a);
         else if (minb == 8) geo_lookup_window_kernel<2, 4, 8><<<wgrid, 128, smem, st>>>(a);
         else geo_lookup_window_kernel<2, 4, 6><<<wgrid, 128, smem, st>>>(a);
     } else if (al16 && C == 8 && radius == 4) geo_lookup_packed_kernel<2, 4><<<grid, 128, 0, st>>>(a);
