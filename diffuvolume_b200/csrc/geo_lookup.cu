@@ -280,12 +280,27 @@ struct GeoLookupArgs {
     int64_t N;
 };
 
-// level-i noise at column j: avg-pooled i times from the raw noisy row
+// Level-LVL noise of flat entry nj = n * D_l + j when D % 2^LVL == 0: the raw values [nj 2^LVL, (nj + 1) 2^LVL) reduced by the
+// same pairwise tree as noise_at — but inlined (noise_at is recursive, i.e. a CALL per element, and a call between two
+// loads keeps the second one from being issued before the first returns).
+template <int LVL>
+__device__ __forceinline__ float noise_flat(const float *__restrict__ p) {
+    if constexpr (LVL == 0) {
+        return __ldg(p);
+    } else {
+        return __fadd_rn(noise_flat<LVL - 1>(p), noise_flat<LVL - 1>(p + (1 << (LVL - 1)))) / 2.0f;
+    }
+}
+
+// level-i noise at column j: avg-pooled i times from the raw noisy row (levels 0-3, the C-ABI's limit) — a switch over the
+// inlined trees, not a recursion
 __device__ __forceinline__ float noise_at(const float *__restrict__ row, int level, int j) {
-    if (level == 0) return row[j];
-    if (level == 1) return __fadd_rn(row[2 * j], row[2 * j + 1]) / 2.0f;
-    const float a = noise_at(row, level - 1, 2 * j), b = noise_at(row, level - 1, 2 * j + 1);
-    return __fadd_rn(a, b) / 2.0f;
+    switch (level) {
+        case 0: return noise_flat<0>(row + j);
+        case 1: return noise_flat<1>(row + 2 * j);
+        case 2: return noise_flat<2>(row + 4 * j);
+        default: return noise_flat<3>(row + 8 * j);
+    }
 }
 
 // grid_sample(align_corners=True, zero padding) source coordinate for pixel coordinate x on a row of
@@ -451,18 +466,6 @@ struct GeoFilterArgs {
     int fast;      // every level takes the vector path (geo_filter_level)
     int64_t N;
 };
-// Level-LVL noise of flat entry nj = n * D_l + j when D % 2^LVL == 0: the raw values [nj 2^LVL, (nj + 1) 2^LVL) reduced by the
-// same pairwise tree as noise_at — but inlined (noise_at is recursive, i.e. a CALL per element, and a call between two
-// loads keeps the second one from being issued before the first returns).
-template <int LVL>
-__device__ __forceinline__ float noise_flat(const float *__restrict__ p) {
-    if constexpr (LVL == 0) {
-        return __ldg(p);
-    } else {
-        return __fadd_rn(noise_flat<LVL - 1>(p), noise_flat<LVL - 1>(p + (1 << (LVL - 1)))) / 2.0f;
-    }
-}
-
 // Vector path of the filter (C % 4 == 0, D % 2^LVL == 0, < 2^31 float4 per level): a CTA owns a compact tile of 4 x 256
 // float4, every thread issues its four volume loads and four noise gathers before the first multiply (the one-load loop
 // below ran at 94 % occupancy with 25 long-scoreboard stall cycles per issue: 32 KB in flight per SM), no index divisions.
