@@ -555,7 +555,9 @@ def igev_bytes(B, iters=32, Hp=384, Wp=1248):
         "geo_lookup": T * (iters - 1) * look,
         "context_upsample": T * (10 * HW + hw) * F4,
         "fallback": T * 3 * HW * F4,
-        "ddim_step": T * (3 * HW * F4 + D * hw * (8 + 8 + 4 + 4 + 8 + 8)),
+        # T = 2: step 0 reads the fp32 state, step noise, asd and its noise (4 x 4 B) and writes x0 (4 B), x_next and eps (fp64);
+        # the last step reads the fp64 state and writes x0 / x_next only; both read the upsampled + initial disparity maps
+        "ddim_step": T * 3 * HW * F4 + D * hw * ((4 * 4 + 4 + 8 + 8) + (8 + 4 + 8)),
         "ensemble": (T + 2) * HW * F4,
     }
     return {k: v * B for k, v in per_pair.items()}
