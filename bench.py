@@ -668,6 +668,9 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
     its GPU (diffuvolume_b200.distributed.bind_to_gpu_numa_node), so the pages sit on the GPU's NUMA node."""
     from diffuvolume_b200.distributed import bind_to_gpu_numa_node, gpu_numa_info
     B = args.batch
+    # the binding only matters while the pinned buffers are allocated and first touched; the original mask is restored at the
+    # end of the leg so that the CPU-baseline legs that follow still see every host core
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     placement = dict(gpu_numa_info(dev.index), bound_cpus=None if args.no_numa_bind else bind_to_gpu_numa_node(dev.index))
     device_noise = args.e2e_noise == "device"
     names = ["feat_l", "feat_r", "cfeat_l", "cfeat_r", "att_logits", "used", "disp_q"]
@@ -773,6 +776,11 @@ def run_e2e(args, path, inp, dev, barrier, dist, world):
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+    if affinity0 is not None:
+        try:
+            os.sched_setaffinity(0, affinity0)
+        except OSError:
+            pass
     return {"value": round(B * world * steps / (ms / 1e3), 2), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": round(ms / steps, 3),
             "h2d_GBs_per_gpu": round(h2d * steps / 1e9 / (ms / 1e3), 1),
